@@ -1,17 +1,24 @@
 /*
- * ref_driver.c -- runs the UNMODIFIED reference library (linked from
- * /root/reference by oracle/Makefile) on an arbitrary "case file".
- * TEST / BASELINE INFRASTRUCTURE ONLY.
+ * c3d_case_main.c -- a small MPI program around the PUBLIC API only
+ * (contour3d_execute + SimpleDecomp getters): renders a "case file".
  *
- *   MINIMPI_NP=<ranks> ref_driver <case.bin> <out.ppm> [dim_y dim_z] [repeat]
+ *   [MINIMPI_NP=<ranks>] c3d_case <case.bin> <out.ppm> [dim_y dim_z] [repeat]
  *
- * The case file (written by contour3d_b200/casefile.py) holds the scene, the
- * grids, the contour / line objects and one or more global fields (fp32 or
- * fp64, x fastest).  Every rank reads its own X1 pencil, widening fp32 to
- * double exactly, builds the reference's structs and calls the reference's
- * contour3d_execute (include/contour3d.h:58-86).  Rank 0 prints one JSON line
- * with the wall time of contour3d_execute (max over ranks, field I/O excluded).
+ * Because it touches nothing but include/contour3d.h it is built twice from
+ * this one source: against libcontour3d_b200.so (-> contour3d_b200/c3d_case,
+ * the drop-in demonstration) and, by oracle/Makefile, against the UNMODIFIED
+ * reference sources (-> oracle/_ref/ref_driver, the CPU baseline).
+ *
+ * The case file (contour3d_b200/casefile.py) holds the scene, the grids, the
+ * contour / line objects and one or more global fields (fp32 or fp64, x
+ * fastest).  Every rank reads its own X1 pencil, widening fp32 to double
+ * exactly, fills the public structs and calls contour3d_execute
+ * (include/contour3d.h:58-86).  Rank 0 prints one JSON line with the wall
+ * time of contour3d_execute (max over ranks, field I/O excluded).
  */
+#if !defined(C3D_IMPL_NAME)
+#define C3D_IMPL_NAME "contour3d_b200"
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -143,7 +150,7 @@ int main(int argc, char **argv) {
     sum += dt;
   }
   if (0 == rank) {
-    printf("{\"impl\": \"reference\", \"ranks\": %d, \"status\": %d, \"repeat\": %d, \"seconds_best\": %.6f, \"seconds_mean\": %.6f, "
+    printf("{\"impl\": \"" C3D_IMPL_NAME "\", \"ranks\": %d, \"status\": %d, \"repeat\": %d, \"seconds_best\": %.6f, \"seconds_mean\": %.6f, "
            "\"voxels\": %llu, \"contours\": %llu}\n",
            nranks, status, repeat, best, sum / repeat,
            (unsigned long long)(h.n[0] * h.n[1] * h.n[2]), (unsigned long long)h.ncontours);

@@ -1,0 +1,240 @@
+/*
+ * c3d_device.cuh -- device-side geometry shared by all kernels.
+ *
+ * Numerical contract: every floating-point expression that the reference
+ * evaluates after classification (interpolation, cross products, projection,
+ * barycentric weights, depth, shading) is evaluated here in fp64 in the SAME
+ * operation order with explicitly rounded intrinsics (__dadd_rn, __dmul_rn,
+ * __ddiv_rn, __dsqrt_rn), which the compiler never contracts into FMAs.  The
+ * reference is built with -std=c99 (no contraction, Makefile:2), so the two
+ * agree bit for bit, not just within a tolerance.
+ *
+ * File:line references are to NaokiHori/Contour3D @ c66854e.
+ */
+#pragma once
+
+#include "c3d_internal.h"
+
+#define C3D_FULL_MASK 0xffffffffu
+
+struct V3 { double x, y, z; };
+
+__device__ __forceinline__ double r_add(const double a, const double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double r_sub(const double a, const double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double r_mul(const double a, const double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double r_div(const double a, const double b) { return __ddiv_rn(a, b); }
+
+/* vector.c:5-76 */
+__device__ __forceinline__ V3 v_add(const V3 a, const V3 b) { return V3{r_add(a.x, b.x), r_add(a.y, b.y), r_add(a.z, b.z)}; }
+__device__ __forceinline__ V3 v_sub(const V3 a, const V3 b) { return V3{r_sub(a.x, b.x), r_sub(a.y, b.y), r_sub(a.z, b.z)}; }
+__device__ __forceinline__ V3 v_mul(const double w, const V3 a) { return V3{r_mul(w, a.x), r_mul(w, a.y), r_mul(w, a.z)}; }
+__device__ __forceinline__ double v_dot(const V3 a, const V3 b) {
+  return r_add(r_add(r_mul(a.x, b.x), r_mul(a.y, b.y)), r_mul(a.z, b.z));
+}
+__device__ __forceinline__ V3 v_cross(const V3 a, const V3 b) {
+  return V3{r_sub(r_mul(a.y, b.z), r_mul(a.z, b.y)), r_sub(r_mul(a.z, b.x), r_mul(a.x, b.z)), r_sub(r_mul(a.x, b.y), r_mul(a.y, b.x))};
+}
+__device__ __forceinline__ V3 v_unit(const V3 a) {
+  const double inv = r_div(1., __dsqrt_rn(v_dot(a, a)));
+  return V3{r_mul(a.x, inv), r_mul(a.y, inv), r_mul(a.z, inv)};
+}
+__device__ __forceinline__ V3 v_of(const double p[3]) { return V3{p[0], p[1], p[2]}; }
+
+/* total order on doubles as unsigned integers (larger double <-> larger key) */
+__device__ __forceinline__ unsigned long long ord_of(const double d) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_to_double(const unsigned long long o) {
+  const unsigned long long b = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+  return __longlong_as_double((long long)b);
+}
+
+__device__ __forceinline__ double ld_value(const FieldView &f, const long long idx) {
+  return 4 == f.elem_bytes ? (double)__ldg((const float *)f.data + idx) : __ldg((const double *)f.data + idx);
+}
+
+/* eight corner scalars + the two coordinates per axis (identity converter);
+   triangulate.c:156-173, 302-317 */
+struct Cube {
+  double val[8];
+  double px[2], py[2], pz[2];
+};
+
+__device__ __forceinline__ void load_cube(const FieldView &f, const long long i, const long long j, const long long k, Cube &c) {
+  const long long base = k * f.sz + j * f.sy + i;
+#pragma unroll
+  for (int n = 0; n < 8; n++) {
+    c.val[n] = ld_value(f, base + (n & 1) + ((n >> 1) & 1) * f.sy + (n >> 2) * f.sz);
+  }
+  c.px[0] = __ldg(f.g[0] + i); c.px[1] = __ldg(f.g[0] + i + 1);
+  c.py[0] = __ldg(f.g[1] + j); c.py[1] = __ldg(f.g[1] + j + 1);
+  c.pz[0] = __ldg(f.g[2] + k); c.pz[1] = __ldg(f.g[2] + k + 1);
+}
+
+/* corner bits: bit n set when thr < value[n] (strict), triangulate.c:176-179 */
+__device__ __forceinline__ unsigned int corner_code(const Cube &c, const double thr) {
+  unsigned int code = 0;
+#pragma unroll
+  for (int n = 0; n < 8; n++) code |= (unsigned int)(thr < c.val[n]) << n;
+  return code;
+}
+
+__device__ __forceinline__ V3 corner_pos(const Cube &c, const unsigned int n) {
+  return V3{c.px[n & 1u], c.py[(n >> 1) & 1u], c.pz[(n >> 2) & 1u]};
+}
+
+/* triangle vertex on the edge tail -> head, triangulate.c:40-73 */
+__device__ __forceinline__ V3 cut_edge(const Cube &c, const double thr, const unsigned int tail, const unsigned int head) {
+  const double v0 = c.val[tail], v1 = c.val[head];
+  const V3 p0 = corner_pos(c, tail);
+  const double dv = r_sub(v1, v0);
+  if (fabs(dv) < 1.e-8) return p0;
+  const double factor = r_div(r_sub(thr, v0), dv);
+  const V3 p1 = corner_pos(c, head);
+  return v_add(p0, v_mul(factor, v_sub(p1, p0)));
+}
+
+__device__ __forceinline__ void triangle_vertices(const Cube &c, const double thr, const unsigned int pairs, V3 v[3]) {
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    v[m] = cut_edge(c, thr, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+  }
+}
+
+/* face normal and |cross|, triangulate.c:75-93 */
+__device__ __forceinline__ void face_normal(const V3 v[3], V3 &fn, double &area) {
+  const V3 c = v_cross(v_sub(v[1], v[0]), v_sub(v[2], v[0]));
+  area = __dsqrt_rn(v_dot(c, c));
+  fn = v_mul(r_div(1., area), c);
+}
+
+/* add area * face_normal of the triangles of cube (i, j, k) that touch its
+   local edge `edge`, in triangle order; average(), normal.c:6-43 */
+__device__ __noinline__ void gather_cube(const FieldView &f, const DevTables &t, const long long i, const long long j, const long long k,
+                                         const unsigned int edge, V3 &sum) {
+  Cube c;
+  load_cube(f, i, j, k, c);
+  const unsigned int code = corner_code(c, f.thr);
+  const unsigned int n = __ldg(t.count + code);
+  for (unsigned int s = 0; s < n; s++) {
+    if ((__ldg(t.emask + code * C3D_MAX_TRIS + s) >> edge) & 1u) {
+      V3 v[3], fn;
+      double area;
+      triangle_vertices(c, f.thr, __ldg(t.pairs + code * C3D_MAX_TRIS + s), v);
+      face_normal(v, fn, area);
+      sum = v_add(sum, v_mul(area, fn));
+    }
+  }
+}
+
+/* vertex normal of the vertex on edge e of cube (i, j, k): the cubes sharing
+   the edge are visited in global (k, j, i) order with the edge renamed to each
+   cube's local id; the 19-way branch of normal.c:78-158, then normalise (159) */
+__device__ __noinline__ V3 vertex_normal(const FieldView &f, const DevTables &t, const long long i, const long long j, const long long k,
+                                         const unsigned int e) {
+  V3 sum = V3{0., 0., 0.};
+  if (e < 12u) {
+    const unsigned int axis = e >> 2, a = e & 1u, b = (e >> 1) & 1u;
+    for (unsigned int q = 0; q < 2; q++) {
+      for (unsigned int p = 0; p < 2; p++) {
+        const long long da = (long long)a - 1 + p, db = (long long)b - 1 + q;
+        const unsigned int local = 4u * axis + (1u - p) + 2u * (1u - q);
+        long long ii = i, jj = j, kk = k;
+        if (0u == axis) { jj += da; kk += db; }
+        else if (1u == axis) { ii += da; kk += db; }
+        else { ii += da; jj += db; }
+        gather_cube(f, t, ii, jj, kk, local, sum);
+      }
+    }
+  } else if (e < 18u) {
+    const unsigned int kind = (e - 12u) >> 1, a = e & 1u;
+    for (unsigned int p = 0; p < 2; p++) {
+      const long long da = (long long)a - 1 + p;
+      const unsigned int local = 12u + 2u * kind + (1u - p);
+      long long ii = i, jj = j, kk = k;
+      if (0u == kind) ii += da;
+      else if (1u == kind) jj += da;
+      else kk += da;
+      gather_cube(f, t, ii, jj, kk, local, sum);
+    }
+  } else {
+    gather_cube(f, t, i, j, k, 18u, sum);
+  }
+  return v_unit(sum);
+}
+
+/* project.c:9-67; returns false when the point is rejected */
+__device__ __forceinline__ bool project(const Cam &c, const V3 p, V3 &out) {
+  const V3 cam = v_of(c.cam), nrm = v_of(c.normal);
+  const V3 ray = v_sub(p, cam);
+  const double nr = v_dot(nrm, ray);
+  if (-1.e-8 < nr && nr < 1.e-8) return false;
+  const double tt = r_div(r_sub(c.d, c.nc), nr);
+  if (tt <= 0. || 1. <= tt) return false;
+  const V3 delta = V3{
+    r_sub(r_add(c.cam[0], r_mul(tt, ray.x)), c.center[0]),
+    r_sub(r_add(c.cam[1], r_mul(tt, ray.y)), c.center[1]),
+    r_sub(r_add(c.cam[2], r_mul(tt, ray.z)), c.center[2]),
+  };
+  out.x = r_div(v_dot(delta, v_of(c.lx)), c.lxlx);
+  out.y = r_div(v_dot(delta, v_of(c.ly)), c.lyly);
+  out.z = nr;
+  return true;
+}
+
+/* a projected triangle prepared for per-pixel tests (render.c:74-115) */
+struct Tri2D {
+  V3 q[3];
+  double area_inv;
+  long long imin, imax, jmin, jmax;
+};
+
+__device__ __forceinline__ long long clamp_ll(const long long lo, const long long hi, const long long v) {
+  const long long m = v < lo ? lo : v;
+  return hi < m ? hi : m;
+}
+
+__device__ __forceinline__ double edge_fn(const V3 &a, const V3 &b, const double px, const double py) {
+  /* render.c:38-46 */
+  return r_sub(r_mul(r_sub(px, a.x), r_sub(b.y, a.y)), r_mul(r_sub(py, a.y), r_sub(b.x, a.x)));
+}
+
+__device__ __forceinline__ bool setup_triangle(const Cam &c, const V3 v[3], Tri2D &t) {
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    if (!project(c, v[m], t.q[m])) return false;    /* render.c:62-72 */
+  }
+  const double xlo = fmin(t.q[0].x, fmin(t.q[1].x, t.q[2].x));
+  const double xhi = fmax(t.q[0].x, fmax(t.q[1].x, t.q[2].x));
+  const double ylo = fmin(t.q[0].y, fmin(t.q[1].y, t.q[2].y));
+  const double yhi = fmax(t.q[0].y, fmax(t.q[1].y, t.q[2].y));
+  /* truncation toward zero BEFORE clamping, render.c:81-89 */
+  const long long xmin = __double2ll_rz(r_sub(r_mul(r_add(0.5, xlo), c.W), 1.));
+  const long long xmax = __double2ll_rz(r_add(r_mul(r_add(0.5, xhi), c.W), 1.));
+  const long long ymin = __double2ll_rz(r_sub(r_mul(r_add(0.5, ylo), c.H), 1.));
+  const long long ymax = __double2ll_rz(r_add(r_mul(r_add(0.5, yhi), c.H), 1.));
+  t.imin = clamp_ll(0, c.w - 1, xmin);
+  t.imax = clamp_ll(0, c.w - 1, xmax);
+  t.jmin = clamp_ll(0, c.h - 1, ymin);
+  t.jmax = clamp_ll(0, c.h - 1, ymax);
+  const double area = edge_fn(t.q[0], t.q[1], t.q[2].x, t.q[2].y);
+  t.area_inv = r_div(1., area < 0. ? fmin(area, -1.e-16) : fmax(area, +1.e-16));
+  return true;
+}
+
+/* barycentric weights of pixel (i, j); false when outside (render.c:94-115) */
+__device__ __forceinline__ bool pixel_weights(const Cam &c, const Tri2D &t, const long long i, const long long j, double w[3]) {
+  const double px = r_sub(r_div(r_add((double)i, 0.5), c.W), 0.5);
+  const double py = r_sub(r_div(r_add((double)j, 0.5), c.H), 0.5);
+  w[0] = r_mul(t.area_inv, edge_fn(t.q[1], t.q[2], px, py));
+  w[1] = r_mul(t.area_inv, edge_fn(t.q[2], t.q[0], px, py));
+  w[2] = r_mul(t.area_inv, edge_fn(t.q[0], t.q[1], px, py));
+  const double slack = -1.e-8;
+  return !(w[0] < slack || w[1] < slack || w[2] < slack);
+}
+
+/* harmonic depth, render.c:120-124 */
+__device__ __forceinline__ double pixel_depth(const Tri2D &t, const double w[3]) {
+  return r_div(1., r_add(r_add(r_div(w[0], t.q[0].z), r_div(w[1], t.q[1].z)), r_div(w[2], t.q[2].z)));
+}

@@ -1,0 +1,90 @@
+/*
+ * c3d_internal.h -- structures shared by the host runtime (c3d_runtime.cu)
+ * and the kernels (c3d_kernels.cu).  Not part of the C-ABI.
+ */
+#if !defined(C3D_INTERNAL_H)
+#define C3D_INTERNAL_H
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "c3d_tables.h"
+
+struct DevTables {
+  const uint8_t *count;
+  const uint32_t *code24;
+  const uint32_t *pairs;
+  const uint32_t *emask;
+  const uint32_t *edges;
+};
+
+/* one contour object as the kernels see it: the extended local array */
+struct FieldView {
+  const void *data;        /* first point of the extended array */
+  int elem_bytes;          /* 4 or 8 */
+  long long n[3];          /* points in x, y, z */
+  long long sy, sz;        /* row / plane strides in elements */
+  const double *g[3];      /* device coordinates of exactly those points */
+  double thr;              /* iso value; classification is thr < value (strict) */
+  float thr_ge;            /* fp32 fields: smallest float f with (double)f > thr, so thr < v <=> v >= thr_ge */
+  unsigned char color[3];
+};
+
+/* camera + screen + light, with the projection invariants of project.c:34-36 hoisted */
+struct Cam {
+  double cam[3], center[3], lx[3], ly[3], normal[3], light[3];
+  double lxlx, lyly;       /* lx.lx, ly.ly */
+  double nc, d;            /* normal.cam, normal.center */
+  double W, H;             /* (double)width, (double)height */
+  long long w, h;
+};
+
+struct LineDev {
+  double e0[3], delta[3];  /* first point and per-segment step (line.c:138-140) */
+  double half_width_sq;    /* pow(0.5 * width, 2), line.c:87 */
+  unsigned long long first_segment; /* index of this line's first segment in the frame-wide numbering */
+  unsigned long long nsegments;
+  unsigned char color[3];
+};
+
+/* 64-bit winner key: object index + 1 in the top 16 bits, primitive below.
+   contours: primitive = cube * 16 + triangle; lines: primitive = segment.
+   Larger key = later in the reference's drawing order (contour, k, j, i, t;
+   then lines), which is what wins a depth tie (render.c:125-132). */
+#define C3D_KEY_OBJ_SHIFT 48
+#define C3D_KEY_PRIM_MASK ((1ull << C3D_KEY_OBJ_SHIFT) - 1ull)
+
+struct SweepRange { long long lo[3], hi[3]; }; /* inclusive cube ranges to emit */
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+/* launchers (c3d_kernels.cu); all asynchronous on `s`, return cudaError_t as int */
+int c3d_k_clear(unsigned long long *depth, unsigned long long *key, size_t npix, cudaStream_t s);
+int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned long long *list, unsigned long long *count,
+                unsigned long long capacity, int sm_count, cudaStream_t s);
+int c3d_k_raster(int pass, const FieldView *f, const Cam *c, const DevTables *t, const unsigned long long *list,
+                 const unsigned long long *count, unsigned long long capacity, unsigned long long obj,
+                 unsigned long long *depth, unsigned long long *key, int sm_count, cudaStream_t s);
+int c3d_k_lines(int pass, const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines, unsigned long long first_obj,
+                unsigned long long *depth, unsigned long long *key, cudaStream_t s);
+int c3d_k_shade(const Cam *c, const DevTables *t, const FieldView *contours_dev, size_t ncontours, const LineDev *lines_dev,
+                const unsigned long long *depth_local, const unsigned long long *depth_global, const unsigned long long *key,
+                unsigned int *rgba, size_t npix, cudaStream_t s);
+int c3d_k_pack(const unsigned int *rgba, const unsigned char bg[3], long long w, long long h, unsigned char *out, cudaStream_t s);
+int c3d_k_depth_to_double(const unsigned long long *depth, double *out, size_t npix, cudaStream_t s);
+int c3d_k_case_codes(const FieldView *f, const DevTables *t, unsigned int *codes, unsigned char *counts, cudaStream_t s);
+int c3d_k_emit(const FieldView *f, const DevTables *t, const unsigned long long *list, unsigned long long nlist,
+               unsigned long long *cursor, unsigned long long capacity, void *records, cudaStream_t s);
+int c3d_k_halo_pack_y(const void *data, int elem_bytes, long long nx, long long sy, long long sz, long long k0, long long nk,
+                      long long j0, void *buf, cudaStream_t s);
+int c3d_k_halo_unpack_y(void *data, int elem_bytes, long long nx, long long sy, long long sz, long long k0, long long nk,
+                        long long j0, const void *buf, cudaStream_t s);
+int c3d_k_synth(void *data, int elem_bytes, const long long n[3], long long sy, long long sz, const long long goff[3],
+                const long long gl[3], int kind, unsigned int seed, int octaves, double gain, cudaStream_t s);
+
+#if defined(__cplusplus)
+}
+#endif
+
+#endif /* C3D_INTERNAL_H */

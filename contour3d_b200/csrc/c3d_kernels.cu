@@ -1,0 +1,657 @@
+/*
+ * c3d_kernels.cu -- the sm_100a kernels of the per-frame pipeline and their
+ * launchers.  Compiled with -gencode arch=compute_100a,code=sm_100a.
+ *
+ *   k_sweep      streaming classification of the scalar field + compaction of
+ *                active cubes (the HBM-bound kernel; 4 B/voxel for fp32)
+ *   k_raster     per-cube tessellation + projection + bounding-box raster into
+ *                a 64-bit atomic z-buffer (pass 1) / winner-key buffer (pass 2)
+ *   k_lines      the same two passes for poly-line segments
+ *   k_shade      deferred shading of the winning primitive of every pixel
+ *                (vertex normals are gathered only for winners)
+ *   k_pack       y-flip + RGB byte packing (PPM payload)
+ *   + halo pack/unpack, debug/inspection kernels, synthetic fields
+ *
+ * File:line references are to NaokiHori/Contour3D @ c66854e.
+ */
+#include <float.h>
+#include "c3d_device.cuh"
+
+/* ------------------------------------------------------------------ clear */
+
+__global__ void k_clear(unsigned long long *depth, unsigned long long *key, const size_t npix) {
+  /* every pixel starts at depth -DBL_MAX with no winner (src/contour3d/main.c:95-103) */
+  const unsigned long long empty = ord_of(-DBL_MAX);
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+    depth[p] = empty;
+    key[p] = 0ull;
+  }
+}
+
+extern "C" int c3d_k_clear(unsigned long long *depth, unsigned long long *key, size_t npix, cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = (int)((npix + threads - 1) / threads < 148 * 16 ? (npix + threads - 1) / threads : 148 * 16);
+  k_clear<<<blocks > 0 ? blocks : 1, threads, 0, s>>>(depth, key, npix);
+  return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ sweep */
+
+struct SweepParams {
+  const void *data;
+  long long mx, my, mz, sy, sz;
+  float thr_ge;
+  double thr;
+  long long ilo, ihi, jlo, jhi, klo, khi;   /* inclusive cube ranges to emit */
+  long long cx, cy;                         /* cube-grid extents for the linear cube index */
+  int nxseg, nytile, nzchunk, zc;
+  unsigned long long ntiles;
+  unsigned long long *list, *count, capacity;
+};
+
+template <typename T> struct Above;
+template <> struct Above<float> {
+  float t;
+  __device__ __forceinline__ Above(const SweepParams &p) : t(p.thr_ge) {}
+  /* thr < (double)v  <=>  v >= (smallest float above thr) */
+  __device__ __forceinline__ unsigned int operator()(const float v) const { return v >= t ? 1u : 0u; }
+};
+template <> struct Above<double> {
+  double t;
+  __device__ __forceinline__ Above(const SweepParams &p) : t(p.thr) {}
+  __device__ __forceinline__ unsigned int operator()(const double v) const { return t < v ? 1u : 0u; }
+};
+
+template <typename T> struct Quad { T a, b, c, d; };
+
+template <typename T> __device__ __forceinline__ Quad<T> ld_quad(const T *p);
+template <> __device__ __forceinline__ Quad<float> ld_quad<float>(const float *p) {
+  const float4 v = __ldcs(reinterpret_cast<const float4 *>(p));     /* 128-bit streaming load */
+  return Quad<float>{v.x, v.y, v.z, v.w};
+}
+template <> __device__ __forceinline__ Quad<double> ld_quad<double>(const double *p) {
+  const double2 lo = __ldcs(reinterpret_cast<const double2 *>(p));
+  const double2 hi = __ldcs(reinterpret_cast<const double2 *>(p) + 1);
+  return Quad<double>{lo.x, lo.y, hi.x, hi.y};
+}
+
+/*
+ * One warp owns a tile of 128 points in x (lane l: points 4l..4l+3) by TY cube
+ * rows in y and marches over zc cube planes in z.  For every (row, plane) the
+ * lane keeps 5 bits: "above threshold" of its four points plus the first point
+ * of the lane to its right, so the eight corner bits of all its cubes are
+ * register-resident; nothing but the field is read and nothing but the compact
+ * list of active cubes is written.
+ *
+ * Each plane step loads TY+1 rows with independent 128-bit loads (the next
+ * plane is requested before the current one is classified).
+ */
+template <typename T, int TY, bool VEC>
+__global__ void __launch_bounds__(256) k_sweep(const SweepParams p) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long tile = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= p.ntiles) return;
+  const int xseg = (int)(tile % (unsigned long long)p.nxseg);
+  const int ytile = (int)((tile / (unsigned long long)p.nxseg) % (unsigned long long)p.nytile);
+  const int zchunk = (int)(tile / ((unsigned long long)p.nxseg * (unsigned long long)p.nytile));
+  const long long x0 = (long long)xseg * 128 + lane * 4;
+  const long long j0 = p.jlo + (long long)ytile * TY;
+  const long long k0 = p.klo + (long long)zchunk * p.zc;
+  const long long k1 = (k0 + p.zc - 1 < p.khi) ? k0 + p.zc - 1 : p.khi;
+  const T *const base = static_cast<const T *>(p.data);
+  const Above<T> above(p);
+  constexpr int ROWS = TY + 1;
+  constexpr unsigned long long ALL = (1ull << (5 * ROWS)) - 1ull;
+
+  Quad<T> raw[ROWS];
+  T extra[ROWS];
+
+  auto request = [&](const long long k) {
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      const long long j = j0 + r;
+      raw[r] = Quad<T>{T(0), T(0), T(0), T(0)};
+      extra[r] = T(0);
+      if (j < p.my && k < p.mz) {
+        const T *row = base + k * p.sz + j * p.sy;
+        if (VEC) {
+          if (x0 < p.mx) raw[r] = ld_quad<T>(row + x0);
+        } else {
+          if (x0 + 0 < p.mx) raw[r].a = __ldcs(row + x0 + 0);
+          if (x0 + 1 < p.mx) raw[r].b = __ldcs(row + x0 + 1);
+          if (x0 + 2 < p.mx) raw[r].c = __ldcs(row + x0 + 2);
+          if (x0 + 3 < p.mx) raw[r].d = __ldcs(row + x0 + 3);
+        }
+        /* the point right of the warp's segment belongs to another warp: lane 31 fetches it */
+        if (31 == lane && x0 + 4 < p.mx) extra[r] = __ldg(row + x0 + 4);
+      }
+    }
+  };
+  /* out-of-range points were loaded as 0 and must classify as "not above"
+     regardless of the threshold: mask them */
+  auto classify = [&](const long long k) -> unsigned long long {
+    unsigned long long bits = 0ull;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      const long long j = j0 + r;
+      unsigned int b = 0u;
+      if (j < p.my && k < p.mz) {
+        b = above(raw[r].a) | (above(raw[r].b) << 1) | (above(raw[r].c) << 2) | (above(raw[r].d) << 3);
+        if (!VEC) {
+          const long long left = p.mx - x0;
+          b &= left >= 4 ? 15u : (left > 0 ? (1u << left) - 1u : 0u);
+        } else if (x0 >= p.mx) {
+          b = 0u;
+        }
+        unsigned int nb = __shfl_down_sync(C3D_FULL_MASK, b & 1u, 1);
+        if (31 == lane) nb = (x0 + 4 < p.mx) ? above(extra[r]) : 0u;
+        b |= nb << 4;
+      }
+      bits |= (unsigned long long)b << (5 * r);
+    }
+    return bits;
+  };
+
+  request(k0);
+  unsigned long long lower = classify(k0);
+  request(k0 + 1);
+  for (long long k = k0; k <= k1; k++) {
+    const unsigned long long upper = classify(k + 1);
+    if (k < k1) request(k + 2);
+    /* quick reject: every point of both planes on the same side */
+    const bool candidate = ((lower | upper) != 0ull) && ((lower & upper) != ALL);
+    if (__any_sync(C3D_FULL_MASK, candidate)) {
+      unsigned int active = 0u;
+      if (candidate) {
+#pragma unroll
+        for (int r = 0; r < TY; r++) {
+          const long long j = j0 + r;
+          const unsigned int l0 = (unsigned int)(lower >> (5 * r)) & 31u, l1 = (unsigned int)(lower >> (5 * r + 5)) & 31u;
+          const unsigned int u0 = (unsigned int)(upper >> (5 * r)) & 31u, u1 = (unsigned int)(upper >> (5 * r + 5)) & 31u;
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const unsigned int code = ((l0 >> c) & 3u) | (((l1 >> c) & 3u) << 2) | (((u0 >> c) & 3u) << 4) | (((u1 >> c) & 3u) << 6);
+            const long long i = x0 + c;
+            const bool ok = code != 0u && code != 255u && i >= p.ilo && i <= p.ihi && j <= p.jhi;
+            active |= (ok ? 1u : 0u) << (r * 4 + c);
+          }
+        }
+      }
+      /* warp-aggregated append: one atomic per warp and plane */
+      const unsigned int n = __popc(active);
+      unsigned int incl = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int up = __shfl_up_sync(C3D_FULL_MASK, incl, d);
+        if (lane >= d) incl += up;
+      }
+      const unsigned int total = __shfl_sync(C3D_FULL_MASK, incl, 31);
+      if (total > 0u) {
+        unsigned long long start = 0ull;
+        if (0 == lane) start = atomicAdd(p.count, (unsigned long long)total);
+        start = __shfl_sync(C3D_FULL_MASK, start, 0);
+        unsigned long long at = start + incl - n;
+        while (active) {
+          const int bit = __ffs((int)active) - 1;
+          active &= active - 1u;
+          const int r = bit >> 2, c = bit & 3;
+          const unsigned int l0 = (unsigned int)(lower >> (5 * r)) & 31u, l1 = (unsigned int)(lower >> (5 * r + 5)) & 31u;
+          const unsigned int u0 = (unsigned int)(upper >> (5 * r)) & 31u, u1 = (unsigned int)(upper >> (5 * r + 5)) & 31u;
+          const unsigned int code = ((l0 >> c) & 3u) | (((l1 >> c) & 3u) << 2) | (((u0 >> c) & 3u) << 4) | (((u1 >> c) & 3u) << 6);
+          const unsigned long long cube = (unsigned long long)((k * p.cy + (j0 + r)) * p.cx + (x0 + c));
+          if (at < p.capacity) p.list[at] = (cube << 8) | code;
+          at++;
+        }
+      }
+    }
+    lower = upper;
+  }
+}
+
+extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned long long *list, unsigned long long *count,
+                           unsigned long long capacity, int sm_count, cudaStream_t s) {
+  SweepParams p;
+  p.data = f->data;
+  p.mx = f->n[0]; p.my = f->n[1]; p.mz = f->n[2];
+  p.sy = f->sy; p.sz = f->sz;
+  p.thr_ge = f->thr_ge; p.thr = f->thr;
+  p.ilo = r->lo[0]; p.ihi = r->hi[0];
+  p.jlo = r->lo[1]; p.jhi = r->hi[1];
+  p.klo = r->lo[2]; p.khi = r->hi[2];
+  p.cx = f->n[0] - 1; p.cy = f->n[1] - 1;
+  p.list = list; p.count = count; p.capacity = capacity;
+  if (p.ihi < p.ilo || p.jhi < p.jlo || p.khi < p.klo) return 0;
+  const int ty = 4 == f->elem_bytes ? 8 : 4;
+  p.nxseg = (int)((p.ihi + 1 + 127) / 128);              /* segments start at x = 0 to stay 512-byte aligned */
+  p.nytile = (int)((p.jhi - p.jlo + 1 + ty - 1) / ty);
+  const long long nk = p.khi - p.klo + 1;
+  const long long per_chunk = (long long)p.nxseg * p.nytile;
+  const long long target = 8ll * sm_count * 4;           /* a few waves of 8-warp CTAs */
+  long long want = (target + per_chunk - 1) / per_chunk;
+  if (want < 1) want = 1;
+  long long zc = nk / want;
+  if (zc > 64) zc = 64;
+  if (zc < 4) zc = 4;
+  if (zc > nk) zc = nk;
+  p.zc = (int)zc;
+  p.nzchunk = (int)((nk + zc - 1) / zc);
+  p.ntiles = (unsigned long long)per_chunk * (unsigned long long)p.nzchunk;
+  const int warps = 8;
+  const unsigned int blocks = (unsigned int)((p.ntiles + warps - 1) / warps);
+  const bool vec = (0 == p.mx % 4) && (0 == p.sy % 4) && (0 == p.sz % 4) && (0 == ((uintptr_t)p.data % 16));
+  if (4 == f->elem_bytes) {
+    if (vec) k_sweep<float, 8, true><<<blocks, warps * 32, 0, s>>>(p);
+    else k_sweep<float, 8, false><<<blocks, warps * 32, 0, s>>>(p);
+  } else {
+    if (vec) k_sweep<double, 4, true><<<blocks, warps * 32, 0, s>>>(p);
+    else k_sweep<double, 4, false><<<blocks, warps * 32, 0, s>>>(p);
+  }
+  return (int)cudaGetLastError();
+}
+
+/* ----------------------------------------------------------------- raster */
+
+/*
+ * One thread per active cube (grid-stride over the compact list): rebuild the
+ * cube's triangles from the field (positions are never stored), project,
+ * walk the +-1 pixel bounding box (render.c:81-89).
+ *   PASS 1: atomicMax of the order-preserving 64-bit image of the fp64 depth.
+ *   PASS 2: pixels where this triangle's depth EQUALS the final depth take
+ *           atomicMax of its key -> "later in drawing order wins ties"
+ *           (render.c:125-132) without depending on atomic ordering.
+ */
+template <int PASS>
+__global__ void __launch_bounds__(128) k_raster(const FieldView f, const Cam cam, const DevTables tab,
+                                                const unsigned long long *__restrict__ list,
+                                                const unsigned long long *__restrict__ count, const unsigned long long capacity,
+                                                const unsigned long long obj, unsigned long long *__restrict__ depth,
+                                                unsigned long long *__restrict__ key) {
+  unsigned long long n = *count;
+  if (n > capacity) n = capacity;
+  const long long cx = f.n[0] - 1, cy = f.n[1] - 1;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long entry = __ldg(list + idx);
+    const unsigned int code = (unsigned int)(entry & 255ull);
+    const unsigned long long cube = entry >> 8;
+    const long long i = (long long)(cube % (unsigned long long)cx);
+    const long long j = (long long)((cube / (unsigned long long)cx) % (unsigned long long)cy);
+    const long long k = (long long)(cube / ((unsigned long long)cx * (unsigned long long)cy));
+    Cube c;
+    load_cube(f, i, j, k, c);
+    const unsigned int ntri = __ldg(tab.count + code);
+    for (unsigned int s = 0; s < ntri; s++) {
+      V3 v[3];
+      triangle_vertices(c, f.thr, __ldg(tab.pairs + code * C3D_MAX_TRIS + s), v);
+      Tri2D t;
+      if (!setup_triangle(cam, v, t)) continue;
+      const unsigned long long mykey = ((obj + 1ull) << C3D_KEY_OBJ_SHIFT) | (cube * 16ull + s);
+      for (long long pj = t.jmin; pj <= t.jmax; pj++) {
+        for (long long pi = t.imin; pi <= t.imax; pi++) {
+          double w[3];
+          if (!pixel_weights(cam, t, pi, pj, w)) continue;
+          const unsigned long long o = ord_of(pixel_depth(t, w));
+          const long long pix = pj * cam.w + pi;
+          if (1 == PASS) {
+            if (o >= depth[pix]) atomicMax(depth + pix, o);
+          } else {
+            if (o == depth[pix]) atomicMax(key + pix, mykey);
+          }
+        }
+      }
+    }
+  }
+}
+
+extern "C" int c3d_k_raster(int pass, const FieldView *f, const Cam *c, const DevTables *t, const unsigned long long *list,
+                            const unsigned long long *count, unsigned long long capacity, unsigned long long obj,
+                            unsigned long long *depth, unsigned long long *key, int sm_count, cudaStream_t s) {
+  const int threads = 128;
+  const int blocks = sm_count * 8;
+  if (1 == pass) k_raster<1><<<blocks, threads, 0, s>>>(*f, *c, *t, list, count, capacity, obj, depth, key);
+  else k_raster<2><<<blocks, threads, 0, s>>>(*f, *c, *t, list, count, capacity, obj, depth, key);
+  return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ lines */
+
+/* one CTA per segment; draw_line_between_two_points, line.c:26-118 */
+template <int PASS>
+__global__ void __launch_bounds__(128) k_lines(const Cam cam, const LineDev *__restrict__ lines, const unsigned int nlines,
+                                               const unsigned long long first_obj, unsigned long long *__restrict__ depth,
+                                               unsigned long long *__restrict__ key) {
+  const unsigned long long seg_global = blockIdx.x;
+  unsigned int l = 0;
+  while (l + 1 < nlines && seg_global >= lines[l + 1].first_segment) l++;
+  const LineDev &ln = lines[l];
+  const unsigned long long seg = seg_global - ln.first_segment;
+  if (seg >= ln.nsegments) return;
+  /* s = head + n * delta, e = head + (n + 1) * delta (line.c:157-158) */
+  const V3 e0 = v_of(ln.e0), dl = v_of(ln.delta);
+  const V3 ps = v_add(e0, v_mul((double)seg, dl));
+  const V3 pe = v_add(e0, v_mul((double)(seg + 1ull), dl));
+  V3 p0, p1;
+  if (!project(cam, ps, p0)) return;
+  if (!project(cam, pe, p1)) return;
+  p0.x = r_mul(r_add(0.5, p0.x), cam.W); p0.y = r_mul(r_add(0.5, p0.y), cam.H);
+  p1.x = r_mul(r_add(0.5, p1.x), cam.W); p1.y = r_mul(r_add(0.5, p1.y), cam.H);
+  const long long imin = clamp_ll(0, cam.w - 1, __double2ll_rz(r_sub(fmin(p0.x, p1.x), 1.)));
+  const long long imax = clamp_ll(0, cam.w - 1, __double2ll_rz(r_add(fmax(p0.x, p1.x), 1.)));
+  const long long jmin = clamp_ll(0, cam.h - 1, __double2ll_rz(r_sub(fmin(p0.y, p1.y), 1.)));
+  const long long jmax = clamp_ll(0, cam.h - 1, __double2ll_rz(r_add(fmax(p0.y, p1.y), 1.)));
+  const double a = r_sub(p1.y, p0.y);
+  const double b = r_add(-p1.x, p0.x);
+  const double dx = r_sub(p1.x, p0.x), dy = r_sub(p1.y, p0.y);
+  const double cc = r_sub(r_mul(dx, p0.y), r_mul(dy, p0.x));
+  const double ab2 = r_add(r_mul(a, a), r_mul(b, b));
+  const double len2 = r_add(r_mul(dx, dx), r_mul(dy, dy));
+  const unsigned long long mykey = ((first_obj + l + 1ull) << C3D_KEY_OBJ_SHIFT) | seg;
+  const long long nx = imax - imin + 1, ny = jmax - jmin + 1;
+  for (long long q = threadIdx.x; q < nx * ny; q += blockDim.x) {
+    const long long i = imin + q % nx, j = jmin + q / nx;
+    const double fi = (double)i, fj = (double)j;
+    const double lin = r_add(r_add(r_mul(a, fi), r_mul(b, fj)), cc);
+    const double dist2 = r_div(r_mul(lin, lin), ab2);
+    if (ln.half_width_sq < dist2) continue;
+    const double param = r_div(r_mul(-1., r_add(r_mul(dx, r_sub(p0.x, fi)), r_mul(dy, r_sub(p0.y, fj)))), len2);
+    const double dist = r_div(1., r_add(r_div(param, p1.z), r_div(r_sub(1., param), p0.z)));
+    const unsigned long long o = ord_of(dist);
+    const long long pix = j * cam.w + i;
+    if (1 == PASS) {
+      if (o >= depth[pix]) atomicMax(depth + pix, o);
+    } else {
+      if (o == depth[pix]) atomicMax(key + pix, mykey);
+    }
+  }
+}
+
+extern "C" int c3d_k_lines(int pass, const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines,
+                           unsigned long long first_obj, unsigned long long *depth, unsigned long long *key, cudaStream_t s) {
+  if (0 == nlines) return 0;
+  const unsigned long long total = lines_host[nlines - 1].first_segment + lines_host[nlines - 1].nsegments;
+  if (0 == total) return 0;
+  if (1 == pass) k_lines<1><<<(unsigned int)total, 128, 0, s>>>(*c, lines_dev, (unsigned int)nlines, first_obj, depth, key);
+  else k_lines<2><<<(unsigned int)total, 128, 0, s>>>(*c, lines_dev, (unsigned int)nlines, first_obj, depth, key);
+  return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ shade */
+
+/*
+ * Deferred shading: one thread per pixel.  Only the winning triangle of a
+ * pixel gets vertex normals (compute_vertex_normals, normal.c:46-165,
+ * evaluated by gathering instead of three stored slices), then the
+ * barycentric blend + light factor + truncation of render.c:137-159.
+ * Output: 0xFF000000 | b << 16 | g << 8 | r, or 0 where this rank has nothing
+ * to contribute (background, or not the global winner).
+ */
+__global__ void __launch_bounds__(128) k_shade(const Cam cam, const DevTables tab, const FieldView *__restrict__ contours,
+                                               const unsigned int ncontours, const LineDev *__restrict__ lines,
+                                               const unsigned long long *__restrict__ depth_local,
+                                               const unsigned long long *__restrict__ depth_global,
+                                               const unsigned long long *__restrict__ key, unsigned int *__restrict__ rgba,
+                                               const size_t npix) {
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const unsigned long long mykey = key[pix];
+  unsigned int out = 0u;
+  if (0ull != mykey && (nullptr == depth_global || depth_local[pix] == depth_global[pix])) {
+    const unsigned int obj = (unsigned int)(mykey >> C3D_KEY_OBJ_SHIFT) - 1u;
+    const unsigned long long prim = mykey & C3D_KEY_PRIM_MASK;
+    if (obj >= ncontours) {
+      const LineDev &ln = lines[obj - ncontours];
+      out = 0xFF000000u | ((unsigned int)ln.color[2] << 16) | ((unsigned int)ln.color[1] << 8) | ln.color[0];
+    } else {
+      const FieldView f = contours[obj];
+      const unsigned long long cube = prim >> 4;
+      const unsigned int s = (unsigned int)(prim & 15ull);
+      const long long cx = f.n[0] - 1, cy = f.n[1] - 1;
+      const long long i = (long long)(cube % (unsigned long long)cx);
+      const long long j = (long long)((cube / (unsigned long long)cx) % (unsigned long long)cy);
+      const long long k = (long long)(cube / ((unsigned long long)cx * (unsigned long long)cy));
+      Cube c;
+      load_cube(f, i, j, k, c);
+      const unsigned int code = corner_code(c, f.thr);
+      V3 v[3];
+      triangle_vertices(c, f.thr, __ldg(tab.pairs + code * C3D_MAX_TRIS + s), v);
+      Tri2D t;
+      double w[3] = {0., 0., 0.};
+      if (setup_triangle(cam, v, t)) {
+        pixel_weights(cam, t, (long long)(pix % (size_t)cam.w), (long long)(pix / (size_t)cam.w), w);
+      }
+      const unsigned int edges = __ldg(tab.edges + code * C3D_MAX_TRIS + s);
+      V3 vn[3];
+      for (int m = 0; m < 3; m++) {
+        vn[m] = vertex_normal(f, tab, i, j, k, (edges >> (5 * m)) & 31u);
+      }
+      /* w0*n0 + (w1*n1 + w2*n2), render.c:137-146 */
+      const V3 nrm = v_unit(v_add(v_mul(w[0], vn[0]), v_add(v_mul(w[1], vn[1]), v_mul(w[2], vn[2]))));
+      const double factor = fmax(0.15, fabs(v_dot(nrm, v_of(cam.light))));
+      const unsigned int r = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[0])) & 255u;
+      const unsigned int g = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[1])) & 255u;
+      const unsigned int b = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[2])) & 255u;
+      out = 0xFF000000u | (b << 16) | (g << 8) | r;
+    }
+  }
+  rgba[pix] = out;
+}
+
+extern "C" int c3d_k_shade(const Cam *c, const DevTables *t, const FieldView *contours_dev, size_t ncontours, const LineDev *lines_dev,
+                           const unsigned long long *depth_local, const unsigned long long *depth_global,
+                           const unsigned long long *key, unsigned int *rgba, size_t npix, cudaStream_t s) {
+  const int threads = 128;
+  const unsigned int blocks = (unsigned int)((npix + threads - 1) / threads);
+  k_shade<<<blocks, threads, 0, s>>>(*c, *t, contours_dev, (unsigned int)ncontours, lines_dev, depth_local, depth_global, key, rgba, npix);
+  return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------- pack */
+
+/* RGB bytes in file order: row j of the file is canvas row h-1-j (output.c:113-123) */
+__global__ void k_pack(const unsigned int *__restrict__ rgba, const unsigned int bg, const long long w, const long long h,
+                       unsigned char *__restrict__ out) {
+  const long long npix = w * h;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < npix; q += (long long)gridDim.x * blockDim.x) {
+    const long long j = q / w, i = q % w;
+    unsigned int px = rgba[(h - 1 - j) * w + i];
+    if (0u == (px >> 24)) px = bg;
+    out[3 * q + 0] = (unsigned char)(px & 255u);
+    out[3 * q + 1] = (unsigned char)((px >> 8) & 255u);
+    out[3 * q + 2] = (unsigned char)((px >> 16) & 255u);
+  }
+}
+
+extern "C" int c3d_k_pack(const unsigned int *rgba, const unsigned char bg[3], long long w, long long h, unsigned char *out, cudaStream_t s) {
+  const unsigned int bgw = ((unsigned int)bg[2] << 16) | ((unsigned int)bg[1] << 8) | bg[0];
+  const long long npix = w * h;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_pack<<<(unsigned int)(blocks > 0 ? blocks : 1), 256, 0, s>>>(rgba, bgw, w, h, out);
+  return (int)cudaGetLastError();
+}
+
+__global__ void k_depth_to_double(const unsigned long long *__restrict__ depth, double *__restrict__ out, const size_t npix) {
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+    out[p] = ord_to_double(depth[p]);
+  }
+}
+
+extern "C" int c3d_k_depth_to_double(const unsigned long long *depth, double *out, size_t npix, cudaStream_t s) {
+  k_depth_to_double<<<148 * 8, 256, 0, s>>>(depth, out, npix);
+  return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------- inspection (parity tests) */
+
+__global__ void k_case_codes(const FieldView f, const DevTables tab, unsigned int *__restrict__ codes, unsigned char *__restrict__ counts) {
+  const long long cx = f.n[0] - 1, cy = f.n[1] - 1, cz = f.n[2] - 1;
+  const long long ncubes = cx * cy * cz;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < ncubes; q += (long long)gridDim.x * blockDim.x) {
+    const long long i = q % cx, j = (q / cx) % cy, k = q / (cx * cy);
+    const long long base = k * f.sz + j * f.sy + i;
+    unsigned int code = 0;
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      const double v = ld_value(f, base + (n & 1) + ((n >> 1) & 1) * f.sy + (n >> 2) * f.sz);
+      code |= (unsigned int)(f.thr < v) << n;
+    }
+    codes[q] = __ldg(tab.code24 + code);
+    counts[q] = __ldg(tab.count + code);
+  }
+}
+
+extern "C" int c3d_k_case_codes(const FieldView *f, const DevTables *t, unsigned int *codes, unsigned char *counts, cudaStream_t s) {
+  k_case_codes<<<148 * 8, 256, 0, s>>>(*f, *t, codes, counts);
+  return (int)cudaGetLastError();
+}
+
+struct TriangleRecord {     /* == c3d_triangle_t, 208 bytes */
+  unsigned long long cube;
+  unsigned int tri, has_vn, edge[3], pad;
+  double area, v[9], fn[3], vn[9];
+};
+
+/* full triangle records for every listed cube (mesh export / parity dumps) */
+__global__ void __launch_bounds__(128) k_emit(const FieldView f, const DevTables tab, const unsigned long long *__restrict__ list,
+                                              const unsigned long long nlist, unsigned long long *cursor,
+                                              const unsigned long long capacity, TriangleRecord *__restrict__ out) {
+  const long long cx = f.n[0] - 1, cy = f.n[1] - 1, cz = f.n[2] - 1;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nlist;
+       idx += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long entry = list[idx];
+    const unsigned int code = (unsigned int)(entry & 255ull);
+    const unsigned long long cube = entry >> 8;
+    const long long i = (long long)(cube % (unsigned long long)cx);
+    const long long j = (long long)((cube / (unsigned long long)cx) % (unsigned long long)cy);
+    const long long k = (long long)(cube / ((unsigned long long)cx * (unsigned long long)cy));
+    const unsigned int ntri = __ldg(tab.count + code);
+    const unsigned long long at = atomicAdd(cursor, (unsigned long long)ntri);
+    /* the reference smooths cubes 1..m-3 of every direction only (normal.c:54-55, contour/main.c:71,92-93) */
+    const bool inner = i >= 1 && i + 1 < cx && j >= 1 && j + 1 < cy && k >= 1 && k + 1 < cz;
+    Cube c;
+    load_cube(f, i, j, k, c);
+    for (unsigned int s = 0; s < ntri; s++) {
+      if (at + s >= capacity) break;
+      TriangleRecord rec;
+      V3 v[3], fn;
+      triangle_vertices(c, f.thr, __ldg(tab.pairs + code * C3D_MAX_TRIS + s), v);
+      face_normal(v, fn, rec.area);
+      const unsigned int edges = __ldg(tab.edges + code * C3D_MAX_TRIS + s);
+      rec.cube = cube; rec.tri = s; rec.has_vn = inner ? 1u : 0u; rec.pad = 0u;
+      for (int m = 0; m < 3; m++) {
+        const unsigned int e = (edges >> (5 * m)) & 31u;
+        rec.edge[m] = e;
+        rec.v[3 * m + 0] = v[m].x; rec.v[3 * m + 1] = v[m].y; rec.v[3 * m + 2] = v[m].z;
+        V3 n = V3{0., 0., 0.};
+        if (inner) n = vertex_normal(f, tab, i, j, k, e);
+        rec.vn[3 * m + 0] = n.x; rec.vn[3 * m + 1] = n.y; rec.vn[3 * m + 2] = n.z;
+      }
+      rec.fn[0] = fn.x; rec.fn[1] = fn.y; rec.fn[2] = fn.z;
+      out[at + s] = rec;
+    }
+  }
+}
+
+extern "C" int c3d_k_emit(const FieldView *f, const DevTables *t, const unsigned long long *list, unsigned long long nlist,
+                          unsigned long long *cursor, unsigned long long capacity, void *records, cudaStream_t s) {
+  if (0 == nlist) return 0;
+  k_emit<<<148 * 4, 128, 0, s>>>(*f, *t, list, nlist, cursor, capacity, static_cast<TriangleRecord *>(records));
+  return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------- halo */
+
+/* rows [j0, j0+2) of planes [k0, k0+nk) <-> contiguous buffer (the y halo is
+   strided: communicate_in_y's hvector, contour/extend.c:71-77) */
+template <typename T, bool PACK>
+__global__ void k_halo_y(T *__restrict__ data, const long long nx, const long long sy, const long long sz, const long long k0,
+                         const long long nk, const long long j0, T *__restrict__ buf) {
+  const long long total = nk * 2 * nx;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const long long i = q % nx, r = (q / nx) % 2, k = q / (2 * nx);
+    T *cell = data + (k0 + k) * sz + (j0 + r) * sy + i;
+    if (PACK) buf[q] = *cell; else *cell = buf[q];
+  }
+}
+
+extern "C" int c3d_k_halo_pack_y(const void *data, int elem_bytes, long long nx, long long sy, long long sz, long long k0, long long nk,
+                                 long long j0, void *buf, cudaStream_t s) {
+  if (4 == elem_bytes) k_halo_y<float, true><<<148 * 4, 256, 0, s>>>((float *)data, nx, sy, sz, k0, nk, j0, (float *)buf);
+  else k_halo_y<double, true><<<148 * 4, 256, 0, s>>>((double *)data, nx, sy, sz, k0, nk, j0, (double *)buf);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int c3d_k_halo_unpack_y(void *data, int elem_bytes, long long nx, long long sy, long long sz, long long k0, long long nk,
+                                   long long j0, const void *buf, cudaStream_t s) {
+  if (4 == elem_bytes) k_halo_y<float, false><<<148 * 4, 256, 0, s>>>((float *)data, nx, sy, sz, k0, nk, j0, (float *)buf);
+  else k_halo_y<double, false><<<148 * 4, 256, 0, s>>>((double *)data, nx, sy, sz, k0, nk, j0, (double *)buf);
+  return (int)cudaGetLastError();
+}
+
+/* -------------------------------------------------------- synthetic fields */
+
+__device__ __forceinline__ unsigned int lowbias32(unsigned int x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+__device__ __forceinline__ float lattice_value(const int x, const int y, const int z, const unsigned int seed) {
+  const unsigned int h = lowbias32((unsigned int)x * 0x9E3779B1u ^ lowbias32((unsigned int)y * 0x85EBCA77u ^ lowbias32((unsigned int)z * 0xC2B2AE3Du ^ seed)));
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+__device__ float value_noise(const float x, const float y, const float z, const unsigned int seed) {
+  const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  float tx = x - fx, ty = y - fy, tz = z - fz;
+  tx = tx * tx * (3.f - 2.f * tx); ty = ty * ty * (3.f - 2.f * ty); tz = tz * tz * (3.f - 2.f * tz);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+    const float w = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+    acc += w * lattice_value(ix + dx, iy + dy, iz + dz, seed);
+  }
+  return acc;
+}
+
+/* kind 0: gyroid sin X cos Y + sin Y cos Z + sin Z cos X, X = 2 pi 4 x;
+   kind 1: sum_o gain^o * valuenoise(2^(o+2) p, seed + o), mapped to [-1, 1].
+   Coordinates are the cell centres x_n = -0.5 + (n + 0.5) / N of the GLOBAL grid. */
+template <typename T>
+__global__ void k_synth(T *__restrict__ data, const long long nx, const long long ny, const long long nz, const long long sy,
+                        const long long sz, const long long ox, const long long oy, const long long oz, const long long gx,
+                        const long long gy, const long long gz, const int kind, const unsigned int seed, const int octaves,
+                        const float gain) {
+  const long long total = nx * ny * nz;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const long long i = q % nx, j = (q / nx) % ny, k = q / (nx * ny);
+    const float x = -0.5f + ((float)(i + ox) + 0.5f) / (float)gx;
+    const float y = -0.5f + ((float)(j + oy) + 0.5f) / (float)gy;
+    const float z = -0.5f + ((float)(k + oz) + 0.5f) / (float)gz;
+    float v;
+    if (0 == kind) {
+      const float s = 6.2831853071795864769f * 4.f;
+      v = sinf(s * x) * cosf(s * y) + sinf(s * y) * cosf(s * z) + sinf(s * z) * cosf(s * x);
+    } else {
+      float amp = 1.f, sum = 0.f, norm = 0.f, freq = 4.f;
+      for (int o = 0; o < octaves; o++) {
+        sum += amp * (2.f * value_noise((x + 0.5f) * freq, (y + 0.5f) * freq, (z + 0.5f) * freq, seed + (unsigned int)o) - 1.f);
+        norm += amp;
+        amp *= gain;
+        freq *= 2.f;
+      }
+      v = sum / norm;
+    }
+    data[k * sz + j * sy + i] = (T)v;
+  }
+}
+
+extern "C" int c3d_k_synth(void *data, int elem_bytes, const long long n[3], long long sy, long long sz, const long long goff[3],
+                           const long long gl[3], int kind, unsigned int seed, int octaves, double gain, cudaStream_t s) {
+  if (4 == elem_bytes)
+    k_synth<float><<<148 * 16, 256, 0, s>>>((float *)data, n[0], n[1], n[2], sy, sz, goff[0], goff[1], goff[2], gl[0], gl[1], gl[2], kind, seed, octaves, (float)gain);
+  else
+    k_synth<double><<<148 * 16, 256, 0, s>>>((double *)data, n[0], n[1], n[2], sy, sz, goff[0], goff[1], goff[2], gl[0], gl[1], gl[2], kind, seed, octaves, (float)gain);
+  return (int)cudaGetLastError();
+}

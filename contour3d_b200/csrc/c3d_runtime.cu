@@ -1,0 +1,832 @@
+/*
+ * c3d_runtime.cu -- host side of the C-ABI (include/contour3d_b200.h):
+ * persistent context (stream, NCCL communicator, canvases, work lists),
+ * device-resident fields with halo room, halo exchange, frame orchestration.
+ *
+ * No CPU fallback: every entry point needs a CUDA device and fails loudly
+ * ("[CONTOUR3D ERROR] ...", return 1) otherwise.
+ *
+ * File:line references are to NaokiHori/Contour3D @ c66854e.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <stdarg.h>
+#include <string.h>
+#include <errno.h>
+#include <math.h>
+#include <float.h>
+#include <algorithm>
+#include <vector>
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include "contour3d_b200.h"
+#include "c3d_internal.h"
+
+#define C3D_MAX_OBJECTS 16
+#define C3D_STR__(x) #x
+#define C3D_STR_(x) C3D_STR__(x)
+
+/* same format as the reference's logger (src/contour3d/logger.c:5-18) */
+static int c3d_error(const char *fmt, ...) {
+  va_list args;
+  va_start(args, fmt);
+  fprintf(stderr, "[CONTOUR3D ERROR] ");
+  vfprintf(stderr, fmt, args);
+  fprintf(stderr, "\n");
+  fflush(stderr);
+  va_end(args);
+  return 1;
+}
+
+#define CUDA_OK(call) \
+  do { \
+    const cudaError_t err_ = (call); \
+    if (cudaSuccess != err_) return c3d_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err_), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH_OK(call) \
+  do { \
+    const int err_ = (call); \
+    if (0 != err_) return c3d_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString((cudaError_t)err_), __FILE__, __LINE__); \
+  } while (0)
+
+#define NCCL_OK(call) \
+  do { \
+    const ncclResult_t err_ = (call); \
+    if (ncclSuccess != err_) return c3d_error("%s failed: %s (%s:%d)", #call, ncclGetErrorString(err_), __FILE__, __LINE__); \
+  } while (0)
+
+struct c3d_field {
+  c3d_decomp_t decomp;
+  size_t gl[3], mysizes[3], offsets[3];
+  size_t ext[3], ext_off[3], lo[3];   /* extended sizes, global index of the first extended point, low halo widths */
+  int elem_bytes;
+  void *data;
+  bool halo_valid;
+};
+
+enum { EV_START, EV_HALO, EV_CLEAR, EV_SWEEP, EV_RASTER, EV_LINES, EV_RESOLVE, EV_REDUCE0, EV_SHADE, EV_REDUCE1, EV_PACK, EV_DOWNLOAD, EV_COUNT };
+
+struct c3d_context {
+  int device, rank, size, sm_count;
+  cudaStream_t stream;
+  ncclComm_t comm;
+  bool has_comm;
+  void *table_mem;
+  DevTables tab;
+  /* canvases */
+  size_t npix_cap;
+  unsigned long long *depth, *key, *depth_global;
+  unsigned int *rgba;
+  unsigned char *ppm_dev, *ppm_host;
+  size_t width, height;
+  /* active-cube lists: one region per contour object */
+  unsigned long long *list;
+  size_t list_cap;
+  unsigned long long *counts_dev, *counts_host;
+  /* per-frame descriptors */
+  FieldView *views_dev;
+  LineDev *lines_dev;
+  size_t lines_cap;
+  double *grids_dev;
+  size_t grids_cap;
+  void *halo_buf;
+  size_t halo_cap;
+  cudaEvent_t ev[EV_COUNT];
+  cudaEvent_t ev_sweep[C3D_MAX_OBJECTS + 1];
+  c3d_timings_t last;
+};
+
+extern "C" const char *c3d_version(void) { return "contour3d_b200 0.1 (sm_100a, CUDA " C3D_STR_(CUDART_VERSION) ")"; }
+
+extern "C" int c3d_nccl_unique_id(void *id128) {
+  if (NULL == id128) return c3d_error("c3d_nccl_unique_id: NULL output");
+  static_assert(sizeof(ncclUniqueId) == C3D_NCCL_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_OK(ncclGetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank, int comm_size, const void *nccl_id128) {
+  if (NULL == out) return c3d_error("c3d_context_create: NULL output");
+  *out = NULL;
+  if (comm_size < 1 || comm_rank < 0 || comm_rank >= comm_size) return c3d_error("c3d_context_create: bad rank %d of %d", comm_rank, comm_size);
+  int ndev = 0;
+  const cudaError_t probe = cudaGetDeviceCount(&ndev);
+  if (cudaSuccess != probe || ndev < 1) {
+    return c3d_error("no usable CUDA device (%s); this library has no CPU path", cudaSuccess != probe ? cudaGetErrorString(probe) : "device count is 0");
+  }
+  if (device < 0) device = comm_rank % ndev;
+  if (device >= ndev) return c3d_error("device %d requested but only %d present", device, ndev);
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return c3d_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  c3d_context *ctx = (c3d_context *)calloc(1, sizeof(c3d_context));
+  if (NULL == ctx) return c3d_error("out of host memory");
+  ctx->device = device;
+  ctx->rank = comm_rank;
+  ctx->size = comm_size;
+  ctx->sm_count = prop.multiProcessorCount;
+  CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (int e = 0; e < EV_COUNT; e++) CUDA_OK(cudaEventCreate(&ctx->ev[e]));
+  for (int e = 0; e <= C3D_MAX_OBJECTS; e++) CUDA_OK(cudaEventCreate(&ctx->ev_sweep[e]));
+  /* case tables -> device */
+  c3d_tables_t *host_tab = (c3d_tables_t *)malloc(sizeof(c3d_tables_t));
+  if (NULL == host_tab) return c3d_error("out of host memory");
+  c3d_tables_build(host_tab);
+  CUDA_OK(cudaMalloc(&ctx->table_mem, sizeof(c3d_tables_t)));
+  CUDA_OK(cudaMemcpy(ctx->table_mem, host_tab, sizeof(c3d_tables_t), cudaMemcpyHostToDevice));
+  free(host_tab);
+  const char *tb = (const char *)ctx->table_mem;
+  ctx->tab.count = (const uint8_t *)(tb + offsetof(c3d_tables_t, count));
+  ctx->tab.code24 = (const uint32_t *)(tb + offsetof(c3d_tables_t, code24));
+  ctx->tab.pairs = (const uint32_t *)(tb + offsetof(c3d_tables_t, pairs));
+  ctx->tab.emask = (const uint32_t *)(tb + offsetof(c3d_tables_t, emask));
+  ctx->tab.edges = (const uint32_t *)(tb + offsetof(c3d_tables_t, edges));
+  CUDA_OK(cudaMalloc(&ctx->counts_dev, (C3D_MAX_OBJECTS + 2) * sizeof(unsigned long long)));
+  CUDA_OK(cudaMallocHost(&ctx->counts_host, (C3D_MAX_OBJECTS + 2) * sizeof(unsigned long long)));
+  CUDA_OK(cudaMalloc(&ctx->views_dev, C3D_MAX_OBJECTS * sizeof(FieldView)));
+  if (comm_size > 1) {
+    if (NULL == nccl_id128) return c3d_error("c3d_context_create: %d ranks need an NCCL unique id", comm_size);
+    ncclUniqueId id;
+    memcpy(&id, nccl_id128, sizeof(id));
+    NCCL_OK(ncclCommInitRank(&ctx->comm, comm_size, id, comm_rank));
+    ctx->has_comm = true;
+  }
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
+  if (NULL == ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->has_comm) ncclCommDestroy(ctx->comm);
+  cudaFree(ctx->table_mem);
+  cudaFree(ctx->depth); cudaFree(ctx->key); cudaFree(ctx->depth_global); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
+  if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
+  cudaFree(ctx->list); cudaFree(ctx->counts_dev);
+  if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
+  cudaFree(ctx->views_dev); cudaFree(ctx->lines_dev); cudaFree(ctx->grids_dev); cudaFree(ctx->halo_buf);
+  for (int e = 0; e < EV_COUNT; e++) cudaEventDestroy(ctx->ev[e]);
+  for (int e = 0; e <= C3D_MAX_OBJECTS; e++) cudaEventDestroy(ctx->ev_sweep[e]);
+  cudaStreamDestroy(ctx->stream);
+  free(ctx);
+  return 0;
+}
+
+extern "C" int c3d_context_device(const c3d_context_t *ctx) { return ctx ? ctx->device : -1; }
+extern "C" uintptr_t c3d_context_stream(const c3d_context_t *ctx) { return ctx ? (uintptr_t)ctx->stream : 0; }
+extern "C" int c3d_context_synchronize(c3d_context_t *ctx) {
+  if (NULL == ctx) return c3d_error("NULL context");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+/* ---------------------------------------------------------- decomposition */
+
+extern "C" int c3d_decomp_make(const int dims[3], int comm_rank, c3d_decomp_t *out) {
+  if (NULL == dims || NULL == out) return c3d_error("c3d_decomp_make: NULL argument");
+  if (1 != dims[0]) return c3d_error("the x direction is never decomposed (dims[0] = %d)", dims[0]);
+  if (dims[1] < 1 || dims[2] < 1) return c3d_error("bad process grid {%d, %d, %d}", dims[0], dims[1], dims[2]);
+  const int size = dims[1] * dims[2];
+  if (comm_rank < 0 || comm_rank >= size) return c3d_error("rank %d outside the %d-process grid", comm_rank, size);
+  /* row-major coordinates, last dimension fastest (MPI_Cart_create) */
+  const int cy = comm_rank / dims[2], cz = comm_rank % dims[2];
+  for (int d = 0; d < 3; d++) out->nprocs[d] = dims[d];
+  out->myrank[0] = 0; out->myrank[1] = cy; out->myrank[2] = cz;
+  out->neighbours[0][0] = out->neighbours[0][1] = -1;
+  out->neighbours[1][0] = cy > 0 ? (cy - 1) * dims[2] + cz : -1;
+  out->neighbours[1][1] = cy < dims[1] - 1 ? (cy + 1) * dims[2] + cz : -1;
+  out->neighbours[2][0] = cz > 0 ? cy * dims[2] + cz - 1 : -1;
+  out->neighbours[2][1] = cz < dims[2] - 1 ? cy * dims[2] + cz + 1 : -1;
+  return 0;
+}
+
+extern "C" int c3d_decomp_local(const c3d_decomp_t *d, const size_t glsizes[3], size_t mysizes[3], size_t offsets[3]) {
+  if (NULL == d || NULL == glsizes || NULL == mysizes || NULL == offsets) return c3d_error("c3d_decomp_local: NULL argument");
+  for (int dir = 0; dir < 3; dir++) {
+    const size_t p = (size_t)d->nprocs[dir], r = (size_t)d->myrank[dir];
+    if (p < 1 || r >= p) return c3d_error("bad decomposition in direction %d (%zu of %zu)", dir, r, p);
+    if (glsizes[dir] < p) return c3d_error("glsize (%zu) should be equal to or more than nprocs (%zu)", glsizes[dir], p);
+    /* sdecomp/kernel.c:89, 111-116 */
+    mysizes[dir] = (glsizes[dir] + r) / p;
+    size_t off = 0;
+    for (size_t q = 0; q < r; q++) off += (glsizes[dir] + q) / p;
+    offsets[dir] = off;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ fields */
+
+extern "C" int c3d_field_create(c3d_context_t *ctx, const c3d_decomp_t *decomp, const size_t glsizes[3], int elem_bytes, c3d_field_t **out) {
+  if (NULL == ctx || NULL == decomp || NULL == glsizes || NULL == out) return c3d_error("c3d_field_create: NULL argument");
+  *out = NULL;
+  if (4 != elem_bytes && 8 != elem_bytes) return c3d_error("element size must be 4 or 8 bytes, received %d", elem_bytes);
+  if (1 != decomp->nprocs[0]) return c3d_error("the x direction is never decomposed (nprocs[0] = %d)", decomp->nprocs[0]);
+  if ((long long)decomp->nprocs[1] * decomp->nprocs[2] != ctx->size)
+    return c3d_error("process grid %dx%dx%d does not match the %d-rank context", decomp->nprocs[0], decomp->nprocs[1], decomp->nprocs[2], ctx->size);
+  c3d_field *f = (c3d_field *)calloc(1, sizeof(c3d_field));
+  if (NULL == f) return c3d_error("out of host memory");
+  f->decomp = *decomp;
+  f->elem_bytes = elem_bytes;
+  if (0 != c3d_decomp_local(decomp, glsizes, f->mysizes, f->offsets)) { free(f); return 1; }
+  size_t total = 1;
+  for (int d = 0; d < 3; d++) {
+    f->gl[d] = glsizes[d];
+    /* two extra points towards every neighbour, none at the domain boundary (contour/extend.c:216-252) */
+    const size_t lo = decomp->myrank[d] > 0 ? 2 : 0;
+    const size_t hi = decomp->myrank[d] < decomp->nprocs[d] - 1 ? 2 : 0;
+    if ((lo || hi) && f->mysizes[d] < 2) { free(f); return c3d_error("local size %zu in direction %d is too small for a 2-point halo", f->mysizes[d], d); }
+    f->lo[d] = lo;
+    f->ext[d] = f->mysizes[d] + lo + hi;
+    f->ext_off[d] = f->offsets[d] - lo;
+    total *= f->ext[d];
+  }
+  CUDA_OK(cudaSetDevice(ctx->device));
+  const cudaError_t err = cudaMalloc(&f->data, total * (size_t)elem_bytes);
+  if (cudaSuccess != err) { free(f); return c3d_error("failed to allocate %zu bytes of device memory for a field: %s", total * (size_t)elem_bytes, cudaGetErrorString(err)); }
+  f->halo_valid = (1 == ctx->size);
+  *out = f;
+  return 0;
+}
+
+extern "C" int c3d_field_destroy(c3d_context_t *ctx, c3d_field_t *field) {
+  if (NULL == field) return 0;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  cudaFree(field->data);
+  free(field);
+  return 0;
+}
+
+static inline char *interior_ptr(const c3d_field *f) {
+  return (char *)f->data + ((f->lo[2] * f->ext[1] + f->lo[1]) * f->ext[0] + f->lo[0]) * (size_t)f->elem_bytes;
+}
+
+extern "C" int c3d_field_upload(c3d_context_t *ctx, c3d_field_t *f, const void *local) {
+  if (NULL == ctx || NULL == f || NULL == local) return c3d_error("c3d_field_upload: NULL argument");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  const size_t eb = (size_t)f->elem_bytes;
+  p.srcPtr = make_cudaPitchedPtr((void *)local, f->mysizes[0] * eb, f->mysizes[0] * eb, f->mysizes[1]);
+  p.dstPtr = make_cudaPitchedPtr(f->data, f->ext[0] * eb, f->ext[0] * eb, f->ext[1]);
+  p.dstPos = make_cudaPos(f->lo[0] * eb, f->lo[1], f->lo[2]);
+  p.extent = make_cudaExtent(f->mysizes[0] * eb, f->mysizes[1], f->mysizes[2]);
+  p.kind = cudaMemcpyDefault;
+  CUDA_OK(cudaMemcpy3DAsync(&p, ctx->stream));
+  f->halo_valid = (1 == ctx->size);
+  return 0;
+}
+
+extern "C" int c3d_field_geometry(const c3d_field_t *f, size_t ext_sizes[3], size_t ext_offsets[3], size_t mysizes[3], size_t offsets[3]) {
+  if (NULL == f) return c3d_error("c3d_field_geometry: NULL field");
+  for (int d = 0; d < 3; d++) {
+    if (ext_sizes) ext_sizes[d] = f->ext[d];
+    if (ext_offsets) ext_offsets[d] = f->ext_off[d];
+    if (mysizes) mysizes[d] = f->mysizes[d];
+    if (offsets) offsets[d] = f->offsets[d];
+  }
+  return 0;
+}
+
+extern "C" int c3d_field_interior(const c3d_field_t *f, void **device_ptr, size_t strides_elems[2]) {
+  if (NULL == f || NULL == device_ptr || NULL == strides_elems) return c3d_error("c3d_field_interior: NULL argument");
+  *device_ptr = interior_ptr(f);
+  strides_elems[0] = f->ext[0];
+  strides_elems[1] = f->ext[0] * f->ext[1];
+  return 0;
+}
+
+extern "C" int c3d_field_mark_dirty(c3d_field_t *f) {
+  if (NULL == f) return c3d_error("c3d_field_mark_dirty: NULL field");
+  f->halo_valid = false;
+  return 0;
+}
+
+static int ensure_bytes(void **ptr, size_t *cap, const size_t need) {
+  if (need <= *cap && NULL != *ptr) return 0;
+  if (*ptr) CUDA_OK(cudaFree(*ptr));
+  *ptr = NULL;
+  *cap = 0;
+  CUDA_OK(cudaMalloc(ptr, need));
+  *cap = need;
+  return 0;
+}
+
+/*
+ * Halo exchange, y first and z second so that z planes carry the freshly
+ * received y halos into the corners (same ordering argument as
+ * contour/extend.c:211-213).  Domain-boundary ranks have no halo at all
+ * (the reference exchanges and then clips, extend.c:216-278).
+ *   y: 2 rows x nx per interior plane, strided -> pack kernel + ncclSend/Recv
+ *   z: 2 full extended planes, contiguous      -> ncclSend/Recv in place
+ */
+extern "C" int c3d_field_exchange(c3d_context_t *ctx, c3d_field_t *f) {
+  if (NULL == ctx || NULL == f) return c3d_error("c3d_field_exchange: NULL argument");
+  if (1 == ctx->size) { f->halo_valid = true; return 0; }
+  CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t eb = (size_t)f->elem_bytes;
+  const long long nx = (long long)f->ext[0], sy = (long long)f->ext[0], sz = (long long)(f->ext[0] * f->ext[1]);
+  const ncclDataType_t dt = 4 == f->elem_bytes ? ncclFloat : ncclDouble;
+  {
+    const int lo = f->decomp.neighbours[1][0], hi = f->decomp.neighbours[1][1];
+    if (lo >= 0 || hi >= 0) {
+      const long long nk = (long long)f->mysizes[2], k0 = (long long)f->lo[2];
+      const size_t chunk = (size_t)nk * 2 * (size_t)nx;           /* elements per message */
+      if (0 != ensure_bytes(&ctx->halo_buf, &ctx->halo_cap, 4 * chunk * eb)) return 1;
+      char *buf = (char *)ctx->halo_buf;
+      void *send_lo = buf, *send_hi = buf + chunk * eb, *recv_lo = buf + 2 * chunk * eb, *recv_hi = buf + 3 * chunk * eb;
+      const long long jfirst = (long long)f->lo[1], jlast = (long long)(f->lo[1] + f->mysizes[1]) - 2;
+      if (lo >= 0) LAUNCH_OK(c3d_k_halo_pack_y(f->data, f->elem_bytes, nx, sy, sz, k0, nk, jfirst, send_lo, ctx->stream));
+      if (hi >= 0) LAUNCH_OK(c3d_k_halo_pack_y(f->data, f->elem_bytes, nx, sy, sz, k0, nk, jlast, send_hi, ctx->stream));
+      NCCL_OK(ncclGroupStart());
+      if (lo >= 0) { NCCL_OK(ncclSend(send_lo, chunk, dt, lo, ctx->comm, ctx->stream)); NCCL_OK(ncclRecv(recv_lo, chunk, dt, lo, ctx->comm, ctx->stream)); }
+      if (hi >= 0) { NCCL_OK(ncclSend(send_hi, chunk, dt, hi, ctx->comm, ctx->stream)); NCCL_OK(ncclRecv(recv_hi, chunk, dt, hi, ctx->comm, ctx->stream)); }
+      NCCL_OK(ncclGroupEnd());
+      if (lo >= 0) LAUNCH_OK(c3d_k_halo_unpack_y(f->data, f->elem_bytes, nx, sy, sz, k0, nk, 0, recv_lo, ctx->stream));
+      if (hi >= 0) LAUNCH_OK(c3d_k_halo_unpack_y(f->data, f->elem_bytes, nx, sy, sz, k0, nk, (long long)(f->lo[1] + f->mysizes[1]), recv_hi, ctx->stream));
+    }
+  }
+  {
+    const int lo = f->decomp.neighbours[2][0], hi = f->decomp.neighbours[2][1];
+    if (lo >= 0 || hi >= 0) {
+      const size_t plane = (size_t)sz, chunk = 2 * plane;
+      char *base = (char *)f->data;
+      const size_t kfirst = f->lo[2], klast = f->lo[2] + f->mysizes[2] - 2;
+      NCCL_OK(ncclGroupStart());
+      if (lo >= 0) {
+        NCCL_OK(ncclSend(base + kfirst * plane * eb, chunk, dt, lo, ctx->comm, ctx->stream));
+        NCCL_OK(ncclRecv(base, chunk, dt, lo, ctx->comm, ctx->stream));
+      }
+      if (hi >= 0) {
+        NCCL_OK(ncclSend(base + klast * plane * eb, chunk, dt, hi, ctx->comm, ctx->stream));
+        NCCL_OK(ncclRecv(base + (f->lo[2] + f->mysizes[2]) * plane * eb, chunk, dt, hi, ctx->comm, ctx->stream));
+      }
+      NCCL_OK(ncclGroupEnd());
+    }
+  }
+  f->halo_valid = true;
+  return 0;
+}
+
+extern "C" int c3d_field_download_ext(c3d_context_t *ctx, const c3d_field_t *f, void *host) {
+  if (NULL == ctx || NULL == f || NULL == host) return c3d_error("c3d_field_download_ext: NULL argument");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  CUDA_OK(cudaMemcpyAsync(host, f->data, f->ext[0] * f->ext[1] * f->ext[2] * (size_t)f->elem_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int c3d_field_synthesize(c3d_context_t *ctx, c3d_field_t *f, int kind, uint32_t seed, int octaves, double gain) {
+  if (NULL == ctx || NULL == f) return c3d_error("c3d_field_synthesize: NULL argument");
+  if (kind < 0 || kind > 1) return c3d_error("unknown synthetic field kind %d", kind);
+  CUDA_OK(cudaSetDevice(ctx->device));
+  /* the generator is a function of the GLOBAL index, so it can fill the halo too: no exchange needed */
+  const long long n[3] = {(long long)f->ext[0], (long long)f->ext[1], (long long)f->ext[2]};
+  const long long off[3] = {(long long)f->ext_off[0], (long long)f->ext_off[1], (long long)f->ext_off[2]};
+  const long long gl[3] = {(long long)f->gl[0], (long long)f->gl[1], (long long)f->gl[2]};
+  LAUNCH_OK(c3d_k_synth(f->data, f->elem_bytes, n, n[0], n[0] * n[1], off, gl, kind, seed, octaves, gain, ctx->stream));
+  f->halo_valid = true;
+  return 0;
+}
+
+/* ------------------------------------------------------------------- frame */
+
+static float smallest_float_above(const double thr) {
+  /* smallest float f with (double)f > thr: then, for any float v, thr < (double)v <=> v >= f */
+  if (thr >= (double)FLT_MAX) return INFINITY;
+  if (thr < -(double)FLT_MAX) return -FLT_MAX;
+  float f = (float)thr;
+  if ((double)f > thr) {
+    const float below = nextafterf(f, -INFINITY);
+    return (double)below > thr ? below : f;
+  }
+  return nextafterf(f, INFINITY);
+}
+
+static int make_view(c3d_context *ctx, const c3d_field *f, const double *const grids[3], const double threshold,
+                     const uint8_t color[3], double *grid_slot, FieldView *v) {
+  v->data = f->data;
+  v->elem_bytes = f->elem_bytes;
+  for (int d = 0; d < 3; d++) v->n[d] = (long long)f->ext[d];
+  v->sy = (long long)f->ext[0];
+  v->sz = (long long)(f->ext[0] * f->ext[1]);
+  double *at = grid_slot;
+  for (int d = 0; d < 3; d++) {
+    if (NULL == grids || NULL == grids[d]) return c3d_error("grid coordinates of direction %d are missing", d);
+    CUDA_OK(cudaMemcpyAsync(at, grids[d] + f->ext_off[d], f->ext[d] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    v->g[d] = at;
+    at += f->ext[d];
+  }
+  v->thr = threshold;
+  v->thr_ge = smallest_float_above(threshold);
+  v->color[0] = color[0]; v->color[1] = color[1]; v->color[2] = color[2];
+  return 0;
+}
+
+static void rendered_range(const FieldView *v, const int rendered_only, SweepRange *r) {
+  /* cubes 1..m-3 per direction are rendered (contour/main.c:71,92-93); all cubes are 0..m-2 */
+  for (int d = 0; d < 3; d++) {
+    r->lo[d] = rendered_only ? 1 : 0;
+    r->hi[d] = rendered_only ? v->n[d] - 3 : v->n[d] - 2;
+  }
+}
+
+static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
+  const size_t npix = w * h;
+  if (npix > ctx->npix_cap) {
+    cudaFree(ctx->depth); cudaFree(ctx->key); cudaFree(ctx->depth_global); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
+    if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
+    ctx->depth = ctx->key = ctx->depth_global = NULL; ctx->rgba = NULL; ctx->ppm_dev = NULL; ctx->ppm_host = NULL;
+    ctx->npix_cap = 0;
+    CUDA_OK(cudaMalloc(&ctx->depth, npix * 8));
+    CUDA_OK(cudaMalloc(&ctx->key, npix * 8));
+    if (ctx->size > 1) CUDA_OK(cudaMalloc(&ctx->depth_global, npix * 8));
+    CUDA_OK(cudaMalloc(&ctx->rgba, npix * 4));
+    CUDA_OK(cudaMalloc(&ctx->ppm_dev, npix * 3));
+    CUDA_OK(cudaMallocHost(&ctx->ppm_host, npix * 3));
+    ctx->npix_cap = npix;
+  }
+  ctx->width = w;
+  ctx->height = h;
+  return 0;
+}
+
+static void make_cam(const c3d_scene_t *s, Cam *c) {
+  /* init_light / init_screen, src/contour3d/main.c:24-63: host fp64 (x86-64 without -march: no FMA) */
+  auto unit = [](const double v[3], double out[3]) {
+    const double inv = 1. / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    out[0] = v[0] * inv; out[1] = v[1] * inv; out[2] = v[2] * inv;
+  };
+  auto dot = [](const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+  for (int d = 0; d < 3; d++) {
+    c->cam[d] = s->camera[d]; c->center[d] = s->center[d]; c->lx[d] = s->local_x[d]; c->ly[d] = s->local_y[d];
+  }
+  unit(s->light, c->light);
+  const double cross[3] = {
+    s->local_x[1] * s->local_y[2] - s->local_x[2] * s->local_y[1],
+    s->local_x[2] * s->local_y[0] - s->local_x[0] * s->local_y[2],
+    s->local_x[0] * s->local_y[1] - s->local_x[1] * s->local_y[0],
+  };
+  unit(cross, c->normal);
+  c->lxlx = dot(c->lx, c->lx);
+  c->lyly = dot(c->ly, c->ly);
+  c->nc = dot(c->normal, c->cam);
+  c->d = dot(c->normal, c->center);
+  c->W = (double)s->width;
+  c->H = (double)s->height;
+  c->w = (long long)s->width;
+  c->h = (long long)s->height;
+}
+
+static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t nc, const c3d_contour_t *contours,
+                      const size_t nl, const c3d_line_t *lines, uint8_t *host_rgb, const char *fname, bool *overflow) {
+  *overflow = false;
+  cudaStream_t s = ctx->stream;
+  const size_t npix = scene->width * scene->height;
+  Cam cam;
+  make_cam(scene, &cam);
+  uint32_t launches = 0;
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_START], s));
+  /* halos */
+  for (size_t n = 0; n < nc; n++) {
+    c3d_field *f = (c3d_field *)contours[n].field;
+    if (!f->halo_valid) {
+      if (0 != c3d_field_exchange(ctx, f)) return 1;
+      launches += 4;
+    }
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_HALO], s));
+  /* descriptors */
+  size_t grid_elems = 0;
+  for (size_t n = 0; n < nc; n++) {
+    const c3d_field *f = contours[n].field;
+    grid_elems += f->ext[0] + f->ext[1] + f->ext[2];
+  }
+  {
+    size_t cap = ctx->grids_cap * sizeof(double);
+    if (0 != ensure_bytes((void **)&ctx->grids_dev, &cap, (grid_elems + 8) * sizeof(double))) return 1;
+    ctx->grids_cap = cap / sizeof(double);
+  }
+  FieldView views[C3D_MAX_OBJECTS];
+  {
+    double *slot = ctx->grids_dev;
+    for (size_t n = 0; n < nc; n++) {
+      const c3d_field *f = contours[n].field;
+      if (0 != make_view(ctx, f, contours[n].grids, contours[n].threshold, contours[n].color, slot, &views[n])) return 1;
+      slot += f->ext[0] + f->ext[1] + f->ext[2];
+    }
+  }
+  if (nc > 0) CUDA_OK(cudaMemcpyAsync(ctx->views_dev, views, nc * sizeof(FieldView), cudaMemcpyHostToDevice, s));
+  std::vector<LineDev> hl(nl);
+  {
+    unsigned long long first = 0;
+    for (size_t n = 0; n < nl; n++) {
+      const c3d_line_t *l = &lines[n];
+      if (l->nitems < 2) return c3d_error("give more than two points to draw a line, received %zu", l->nitems);
+      /* deltas = (1 / (npoints - 1)) * (tail - head), line.c:138-140 */
+      const double inv = 1. / (double)(l->nitems - 1);
+      for (int d = 0; d < 3; d++) {
+        hl[n].e0[d] = l->edges[0][d];
+        hl[n].delta[d] = inv * (l->edges[1][d] - l->edges[0][d]);
+      }
+      hl[n].half_width_sq = pow(0.5 * l->width, 2.);
+      hl[n].first_segment = first;
+      hl[n].nsegments = l->nitems - 1;
+      hl[n].color[0] = l->color[0]; hl[n].color[1] = l->color[1]; hl[n].color[2] = l->color[2];
+      first += l->nitems - 1;
+    }
+    if (nl > ctx->lines_cap) {
+      cudaFree(ctx->lines_dev);
+      ctx->lines_dev = NULL;
+      CUDA_OK(cudaMalloc(&ctx->lines_dev, nl * sizeof(LineDev)));
+      ctx->lines_cap = nl;
+    }
+    if (nl > 0) CUDA_OK(cudaMemcpyAsync(ctx->lines_dev, hl.data(), nl * sizeof(LineDev), cudaMemcpyHostToDevice, s));
+  }
+  /* work lists: equal share of the list buffer per contour object */
+  if (nc > 0 && 0 == ctx->list_cap) {
+    size_t want = 0;
+    for (size_t n = 0; n < nc; n++) {
+      const c3d_field *f = contours[n].field;
+      const size_t cubes = f->ext[0] * f->ext[1] * f->ext[2];
+      want += std::max<size_t>(1u << 20, cubes / 16);
+    }
+    CUDA_OK(cudaMalloc(&ctx->list, want * 8));
+    ctx->list_cap = want;
+  }
+  const size_t share = nc > 0 ? ctx->list_cap / nc : 0;
+  CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, (C3D_MAX_OBJECTS + 2) * sizeof(unsigned long long), s));
+  LAUNCH_OK(c3d_k_clear(ctx->depth, ctx->key, npix, s));
+  launches += 1;
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_CLEAR], s));
+  /* 1. classification sweeps */
+  for (size_t n = 0; n < nc; n++) {
+    CUDA_OK(cudaEventRecord(ctx->ev_sweep[n], s));
+    SweepRange r;
+    rendered_range(&views[n], 1, &r);
+    LAUNCH_OK(c3d_k_sweep(&views[n], &r, ctx->list + n * share, ctx->counts_dev + n, share, ctx->sm_count, s));
+    launches += 1;
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev_sweep[nc], s));
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_SWEEP], s));
+  /* 2. depth pass: contours in order, then lines (src/contour3d/main.c:105-129) */
+  for (size_t n = 0; n < nc; n++) {
+    LAUNCH_OK(c3d_k_raster(1, &views[n], &cam, &ctx->tab, ctx->list + n * share, ctx->counts_dev + n, share, n, ctx->depth, ctx->key, ctx->sm_count, s));
+    launches += 1;
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_RASTER], s));
+  LAUNCH_OK(c3d_k_lines(1, &cam, ctx->lines_dev, hl.data(), nl, nc, ctx->depth, ctx->key, s));
+  if (nl > 0) launches += 1;
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_LINES], s));
+  /* 3. winner pass: among the primitives that reach the final depth, the last in drawing order */
+  for (size_t n = 0; n < nc; n++) {
+    LAUNCH_OK(c3d_k_raster(2, &views[n], &cam, &ctx->tab, ctx->list + n * share, ctx->counts_dev + n, share, n, ctx->depth, ctx->key, ctx->sm_count, s));
+    launches += 1;
+  }
+  LAUNCH_OK(c3d_k_lines(2, &cam, ctx->lines_dev, hl.data(), nl, nc, ctx->depth, ctx->key, s));
+  if (nl > 0) launches += 1;
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_RESOLVE], s));
+  /* 4. nearest depth across ranks (replaces the depth half of MPI_Reduce, output.c:10-30,82) */
+  const unsigned long long *depth_global = NULL;
+  if (ctx->size > 1) {
+    NCCL_OK(ncclAllReduce(ctx->depth, ctx->depth_global, npix, ncclUint64, ncclMax, ctx->comm, s));
+    depth_global = ctx->depth_global;
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
+  /* 5. shade only what survived */
+  LAUNCH_OK(c3d_k_shade(&cam, &ctx->tab, ctx->views_dev, nc, ctx->lines_dev, ctx->depth, depth_global, ctx->key, ctx->rgba, npix, s));
+  launches += 1;
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
+  /* 6. colours to the writer (the colour half of the reference's reduce) */
+  if (ctx->size > 1) {
+    NCCL_OK(ncclReduce(ctx->rgba, ctx->rgba, npix, ncclUint32, ncclMax, 0, ctx->comm, s));
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE1], s));
+  if (0 == ctx->rank) {
+    LAUNCH_OK(c3d_k_pack(ctx->rgba, scene->bg, cam.w, cam.h, ctx->ppm_dev, s));
+    launches += 1;
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_PACK], s));
+  const bool want_host = (0 == ctx->rank) && (NULL != host_rgb || NULL != fname);
+  if (want_host) CUDA_OK(cudaMemcpyAsync(ctx->ppm_host, ctx->ppm_dev, 3 * npix, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, (C3D_MAX_OBJECTS + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_DOWNLOAD], s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  /* capacity policy: a list that overflowed is grown and the frame is redone */
+  size_t need = 0;
+  for (size_t n = 0; n < nc; n++) {
+    if (ctx->counts_host[n] > share) *overflow = true;
+    need = std::max<size_t>(need, (size_t)ctx->counts_host[n]);
+  }
+  if (*overflow) {
+    cudaFree(ctx->list);
+    ctx->list = NULL;
+    ctx->list_cap = 0;
+    const size_t want = (need + need / 4 + 1024) * nc;
+    const cudaError_t err = cudaMalloc(&ctx->list, want * 8);
+    if (cudaSuccess != err) return c3d_error("failed to grow the active-cube list to %zu entries: %s", want, cudaGetErrorString(err));
+    ctx->list_cap = want;
+    return 0;
+  }
+  /* timings */
+  c3d_timings_t *t = &ctx->last;
+  memset(t, 0, sizeof(*t));
+  auto ms = [&](int a, int b) { float v = 0.f; cudaEventElapsedTime(&v, ctx->ev[a], ctx->ev[b]); return v; };
+  t->halo = ms(EV_START, EV_HALO);
+  t->clear = ms(EV_HALO, EV_CLEAR);
+  t->sweep = ms(EV_CLEAR, EV_SWEEP);
+  t->raster = ms(EV_SWEEP, EV_RASTER);
+  t->lines = ms(EV_RASTER, EV_LINES);
+  t->resolve = ms(EV_LINES, EV_RESOLVE);
+  t->reduce = ms(EV_RESOLVE, EV_REDUCE0) + ms(EV_SHADE, EV_REDUCE1);
+  t->shade = ms(EV_REDUCE0, EV_SHADE);
+  t->pack = ms(EV_REDUCE1, EV_PACK);
+  t->download = ms(EV_PACK, EV_DOWNLOAD);
+  t->total = ms(EV_START, EV_DOWNLOAD);
+  t->ncontours = (uint32_t)nc;
+  t->launches = launches;
+  for (size_t n = 0; n < nc && n < 16; n++) {
+    cudaEventElapsedTime(&t->sweep_each[n], ctx->ev_sweep[n], ctx->ev_sweep[n + 1]);
+    t->active_cubes[n] = ctx->counts_host[n];
+    const c3d_field *f = contours[n].field;
+    t->sweep_bytes[n] = (uint64_t)f->ext[0] * f->ext[1] * f->ext[2] * (uint64_t)f->elem_bytes;
+  }
+  if (want_host) {
+    if (NULL != host_rgb) memcpy(host_rgb, ctx->ppm_host, 3 * npix);
+    if (NULL != fname) {
+      /* binary P6, output.c:125-146 */
+      errno = 0;
+      FILE *fp = fopen(fname, "w");
+      if (NULL == fp) return c3d_error("%s: %s", fname, strerror(errno));
+      fprintf(fp, "P6\n%zu %zu\n255\n", scene->width, scene->height);
+      const size_t wrote = fwrite(ctx->ppm_host, 3, npix, fp);
+      fclose(fp);
+      if (wrote != npix) return c3d_error("fwrite failed (%zu expected, %zu returned)", npix, wrote);
+    }
+  }
+  return 0;
+}
+
+extern "C" int c3d_frame_render(c3d_context_t *ctx, const c3d_scene_t *scene, size_t nc, const c3d_contour_t *contours,
+                                size_t nl, const c3d_line_t *lines, uint8_t *host_rgb, const char *fname) {
+  if (NULL == ctx || NULL == scene) return c3d_error("c3d_frame_render: NULL argument");
+  if (nc > C3D_MAX_OBJECTS) return c3d_error("at most %d contour objects per frame, received %zu", C3D_MAX_OBJECTS, nc);
+  if (nc > 0 && NULL == contours) return c3d_error("contour objects are missing");
+  if (nl > 0 && NULL == lines) return c3d_error("line objects are missing");
+  if (0 == scene->width || 0 == scene->height) return c3d_error("empty screen (%zu x %zu)", scene->width, scene->height);
+  if (nc + nl >= 65535) return c3d_error("too many objects (%zu)", nc + nl);
+  for (size_t n = 0; n < nc; n++) {
+    if (NULL == contours[n].field) return c3d_error("contour object %zu has no field", n);
+  }
+  CUDA_OK(cudaSetDevice(ctx->device));
+  if (0 != ensure_canvas(ctx, scene->width, scene->height)) return 1;
+  for (int attempt = 0; attempt < 4; attempt++) {
+    bool overflow = false;
+    if (0 != frame_once(ctx, scene, nc, contours, nl, lines, host_rgb, fname, &overflow)) return 1;
+    if (!overflow) return 0;
+  }
+  return c3d_error("active-cube list kept overflowing");
+}
+
+extern "C" int c3d_frame_timings(const c3d_context_t *ctx, c3d_timings_t *out) {
+  if (NULL == ctx || NULL == out) return c3d_error("c3d_frame_timings: NULL argument");
+  *out = ctx->last;
+  return 0;
+}
+
+extern "C" int c3d_frame_canvas(c3d_context_t *ctx, double *host_depth, uint64_t *host_key) {
+  if (NULL == ctx) return c3d_error("c3d_frame_canvas: NULL context");
+  const size_t npix = ctx->width * ctx->height;
+  if (0 == npix) return c3d_error("no frame has been rendered yet");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  if (host_depth) {
+    double *tmp = NULL;
+    CUDA_OK(cudaMalloc(&tmp, npix * sizeof(double)));
+    LAUNCH_OK(c3d_k_depth_to_double(ctx->depth, tmp, npix, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(host_depth, tmp, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    CUDA_OK(cudaFree(tmp));
+  }
+  if (host_key) {
+    CUDA_OK(cudaMemcpyAsync(host_key, ctx->key, npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------ stage level */
+
+static int stage_view(c3d_context *ctx, const c3d_field *f, const double *const grids[3], const double thr, FieldView *v) {
+  const uint8_t white[3] = {255, 255, 255};
+  size_t cap = ctx->grids_cap * sizeof(double);
+  const size_t elems = f->ext[0] + f->ext[1] + f->ext[2];
+  if (0 != ensure_bytes((void **)&ctx->grids_dev, &cap, (elems + 8) * sizeof(double))) return 1;
+  ctx->grids_cap = cap / sizeof(double);
+  if (NULL == grids) {
+    /* classification does not need coordinates */
+    v->data = f->data; v->elem_bytes = f->elem_bytes;
+    for (int d = 0; d < 3; d++) { v->n[d] = (long long)f->ext[d]; v->g[d] = ctx->grids_dev; }
+    v->sy = (long long)f->ext[0]; v->sz = (long long)(f->ext[0] * f->ext[1]);
+    v->thr = thr; v->thr_ge = smallest_float_above(thr);
+    return 0;
+  }
+  return make_view(ctx, f, grids, thr, white, ctx->grids_dev, v);
+}
+
+extern "C" int c3d_case_codes(c3d_context_t *ctx, const c3d_field_t *f, double threshold, uint32_t *host_codes, uint8_t *host_counts) {
+  if (NULL == ctx || NULL == f || NULL == host_codes || NULL == host_counts) return c3d_error("c3d_case_codes: NULL argument");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  if (f->ext[0] < 2 || f->ext[1] < 2 || f->ext[2] < 2) return c3d_error("array too small");
+  const size_t ncubes = (f->ext[0] - 1) * (f->ext[1] - 1) * (f->ext[2] - 1);
+  FieldView v;
+  if (0 != stage_view(ctx, f, NULL, threshold, &v)) return 1;
+  unsigned int *codes = NULL;
+  unsigned char *counts = NULL;
+  CUDA_OK(cudaMalloc(&codes, ncubes * 4));
+  CUDA_OK(cudaMalloc(&counts, ncubes));
+  LAUNCH_OK(c3d_k_case_codes(&v, &ctx->tab, codes, counts, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(host_codes, codes, ncubes * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(host_counts, counts, ncubes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(codes);
+  cudaFree(counts);
+  return 0;
+}
+
+static int sweep_to_device(c3d_context *ctx, const FieldView *v, const int rendered_only, unsigned long long **list, unsigned long long *count) {
+  SweepRange r;
+  rendered_range(v, rendered_only, &r);
+  size_t cap = 1u << 20;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    CUDA_OK(cudaMalloc(list, cap * 8));
+    CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, 8, ctx->stream));
+    LAUNCH_OK(c3d_k_sweep(v, &r, *list, ctx->counts_dev, cap, ctx->sm_count, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    *count = ctx->counts_host[0];
+    if (*count <= cap) return 0;
+    CUDA_OK(cudaFree(*list));
+    *list = NULL;
+    cap = (size_t)*count + 1024;
+  }
+  return c3d_error("sweep list did not converge");
+}
+
+extern "C" int c3d_sweep(c3d_context_t *ctx, const c3d_field_t *f, double threshold, int rendered_only, size_t capacity,
+                         uint64_t *host_entries, uint64_t *count) {
+  if (NULL == ctx || NULL == f || NULL == count) return c3d_error("c3d_sweep: NULL argument");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  FieldView v;
+  if (0 != stage_view(ctx, f, NULL, threshold, &v)) return 1;
+  unsigned long long *list = NULL, n = 0;
+  if (0 != sweep_to_device(ctx, &v, rendered_only, &list, &n)) return 1;
+  *count = n;
+  const size_t take = std::min<size_t>((size_t)n, capacity);
+  if (take > 0 && NULL != host_entries) {
+    CUDA_OK(cudaMemcpyAsync(host_entries, list, take * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFree(list);
+  return 0;
+}
+
+extern "C" int c3d_tessellate(c3d_context_t *ctx, const c3d_field_t *f, const double *const grids[3], double threshold,
+                              size_t capacity, c3d_triangle_t *host_out, uint64_t *count) {
+  if (NULL == ctx || NULL == f || NULL == grids || NULL == count) return c3d_error("c3d_tessellate: NULL argument");
+  static_assert(sizeof(c3d_triangle_t) == 208, "record layout");
+  CUDA_OK(cudaSetDevice(ctx->device));
+  FieldView v;
+  if (0 != stage_view(ctx, f, grids, threshold, &v)) return 1;
+  unsigned long long *list = NULL, ncubes = 0;
+  if (0 != sweep_to_device(ctx, &v, 0, &list, &ncubes)) return 1;
+  /* at most 12 triangles per cube: size the record buffer from the exact count */
+  std::vector<unsigned long long> entries((size_t)ncubes);
+  if (ncubes) CUDA_OK(cudaMemcpy(entries.data(), list, (size_t)ncubes * 8, cudaMemcpyDeviceToHost));
+  c3d_tables_t *tab = (c3d_tables_t *)malloc(sizeof(c3d_tables_t));
+  c3d_tables_build(tab);
+  unsigned long long total = 0;
+  for (unsigned long long e : entries) total += tab->count[e & 255ull];
+  free(tab);
+  *count = total;
+  if (0 == total || NULL == host_out || 0 == capacity) { cudaFree(list); return 0; }
+  void *records = NULL;
+  CUDA_OK(cudaMalloc(&records, (size_t)total * sizeof(c3d_triangle_t)));
+  CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, 8, ctx->stream));
+  LAUNCH_OK(c3d_k_emit(&v, &ctx->tab, list, ncubes, ctx->counts_dev, total, records, ctx->stream));
+  std::vector<c3d_triangle_t> all((size_t)total);
+  CUDA_OK(cudaMemcpyAsync(all.data(), records, (size_t)total * sizeof(c3d_triangle_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(records);
+  cudaFree(list);
+  std::sort(all.begin(), all.end(), [](const c3d_triangle_t &a, const c3d_triangle_t &b) {
+    return a.cube != b.cube ? a.cube < b.cube : a.tri < b.tri;
+  });
+  memcpy(host_out, all.data(), std::min<size_t>((size_t)total, capacity) * sizeof(c3d_triangle_t));
+  return 0;
+}

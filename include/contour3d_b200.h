@@ -1,0 +1,168 @@
+/*
+ * contour3d_b200.h -- C-ABI of the CUDA (sm_100a) implementation.
+ *
+ * This is the layer the drop-in entry point contour3d_execute()
+ * (include/contour3d.h) is written on, and what foreign-language hosts bind
+ * (ctypes: contour3d_b200/api.py).  Plain pointers and sizes only; every
+ * function returns 0 on success and non-zero on failure after printing one
+ * "[CONTOUR3D ERROR] ..." line to stderr (reference: src/contour3d/logger.c:5-18).
+ * There is no CPU fallback anywhere behind this interface.
+ *
+ * Each entry point names the reference code it replaces (paths relative to
+ * the reference repository NaokiHori/Contour3D @ c66854e).
+ */
+#if !defined(CONTOUR3D_B200_H)
+#define CONTOUR3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define C3D_NCCL_ID_BYTES 128
+
+typedef struct c3d_context c3d_context_t;   /* device, streams, NCCL communicator, canvases, work lists */
+typedef struct c3d_field c3d_field_t;       /* one device-resident local array with halo room */
+
+/* Position of this rank in the process grid: what contour/extend.c:216-252
+   obtains from sdecomp.get_nprocs / get_myrank / get_neighbours.  Direction 0
+   (x) is never split by SimpleDecomp (sdecomp/main.c:65-73,133-139). */
+typedef struct {
+  int nprocs[3];
+  int myrank[3];
+  int neighbours[3][2];       /* communicator ranks of the -/+ neighbours, -1 = none */
+} c3d_decomp_t;
+
+/* reference: arguments of contour3d_execute (include/contour3d.h:58-86) and
+   init_camera / init_light / init_screen (src/contour3d/main.c:13-63) */
+typedef struct {
+  double camera[3];
+  double light[3];            /* any length; normalised internally */
+  double center[3];
+  double local_x[3];
+  double local_y[3];
+  size_t width, height;
+  uint8_t bg[3];
+} c3d_scene_t;
+
+/* reference: contour3d_contour_obj_t (include/contour3d.h:22-40); the array is
+   a c3d_field_t, the converter is the identity */
+typedef struct {
+  const c3d_field_t *field;
+  const double *grids[3];     /* HOST pointers, global coordinates (glsizes[d] each) */
+  double threshold;
+  uint8_t color[3];
+} c3d_contour_t;
+
+/* reference: contour3d_line_obj_t (include/contour3d.h:42-56), identity converter */
+typedef struct {
+  double edges[2][3];
+  size_t nitems;
+  double width;
+  uint8_t color[3];
+} c3d_line_t;
+
+/* same 208-byte record as the oracle's dump (oracle/c3d_oracle.h) */
+typedef struct {
+  uint64_t cube;              /* (k*(my-1)+j)*(mx-1)+i on the extended local array */
+  uint32_t tri;
+  uint32_t has_vn;
+  uint32_t edge[3];
+  uint32_t pad;
+  double area;
+  double v[9];
+  double fn[3];
+  double vn[9];
+} c3d_triangle_t;
+
+/* per-stage device times of the last frame, milliseconds (CUDA events) */
+typedef struct {
+  float upload, halo, clear, sweep, raster, lines, resolve, reduce, shade, pack, download, total;
+  float sweep_each[16];       /* per contour object */
+  uint64_t active_cubes[16];  /* per contour object, rendered range */
+  uint64_t sweep_bytes[16];   /* algorithmic bytes of each sweep launch */
+  uint32_t ncontours;
+  uint32_t launches;          /* kernels launched by this library in the frame */
+} c3d_timings_t;
+
+/* ---- life cycle ---- */
+
+/* fills a 128-byte ncclUniqueId on one rank; the host distributes it
+   (MPI_Bcast in contour3d_execute.c, torch.distributed in bench.py) */
+int c3d_nccl_unique_id(void *id128);
+
+/* device < 0 selects comm_rank % device_count.  nccl_id may be NULL when comm_size == 1 */
+int c3d_context_create(c3d_context_t **ctx, int device, int comm_rank, int comm_size, const void *nccl_id128);
+int c3d_context_destroy(c3d_context_t *ctx);
+int c3d_context_device(const c3d_context_t *ctx);
+/* cudaStream_t the pipeline runs on, as an integer (for event timing from outside) */
+uintptr_t c3d_context_stream(const c3d_context_t *ctx);
+int c3d_context_synchronize(c3d_context_t *ctx);
+
+/* block decomposition of SimpleDecomp (sdecomp/kernel.c:89,111-116) for a
+   process grid dims = {1, Py, Pz}, ranks row-major with z fastest (MPI_Cart_create) */
+int c3d_decomp_make(const int dims[3], int comm_rank, c3d_decomp_t *out);
+int c3d_decomp_local(const c3d_decomp_t *d, const size_t glsizes[3], size_t mysizes[3], size_t offsets[3]);
+
+/* ---- fields: replaces the host-side padding + copy of contour/extend.c:182-278 ---- */
+
+/* elem_bytes 4 (float) or 8 (double).  The device buffer already has the
+   extended shape (two extra points on every side that has a neighbour) */
+int c3d_field_create(c3d_context_t *ctx, const c3d_decomp_t *decomp, const size_t glsizes[3], int elem_bytes, c3d_field_t **field);
+int c3d_field_destroy(c3d_context_t *ctx, c3d_field_t *field);
+/* copy the local pencil (mysizes, x fastest; host or device pointer, same element type) into the interior */
+int c3d_field_upload(c3d_context_t *ctx, c3d_field_t *field, const void *local);
+/* extended shape / global offsets of the first extended point / device pointer + strides of the INTERIOR */
+int c3d_field_geometry(const c3d_field_t *field, size_t ext_sizes[3], size_t ext_offsets[3], size_t mysizes[3], size_t offsets[3]);
+int c3d_field_interior(const c3d_field_t *field, void **device_ptr, size_t strides_elems[2]);
+/* tell the library the interior was written through c3d_field_interior (halo must be re-exchanged) */
+int c3d_field_mark_dirty(c3d_field_t *field);
+/* halo exchange: replaces communicate_in_{x,y,z}, contour/extend.c:10-147 (ncclSend/ncclRecv) */
+int c3d_field_exchange(c3d_context_t *ctx, c3d_field_t *field);
+/* copy the extended array to the host (tests) */
+int c3d_field_download_ext(c3d_context_t *ctx, const c3d_field_t *field, void *host);
+
+/* synthetic benchmark fields, generated on the device (kind: 0 gyroid, 1 multi-octave value noise) */
+int c3d_field_synthesize(c3d_context_t *ctx, c3d_field_t *field, int kind, uint32_t seed, int octaves, double gain);
+
+/* ---- whole frame: replaces contour3d_execute's body, src/contour3d/main.c:68-146 ---- */
+
+/* Renders all contour objects and lines, reduces across ranks, and on
+   communicator rank 0 optionally copies the y-flipped RGB bytes (3*W*H, PPM
+   payload order, output.c:113-123) to host_rgb and/or writes the PPM file.
+   host_rgb and fname may be NULL (result stays on the device). */
+int c3d_frame_render(c3d_context_t *ctx, const c3d_scene_t *scene,
+                     size_t num_contours, const c3d_contour_t *contours,
+                     size_t num_lines, const c3d_line_t *lines,
+                     uint8_t *host_rgb, const char *fname);
+int c3d_frame_timings(const c3d_context_t *ctx, c3d_timings_t *out);
+/* canvas of the last frame on this rank, canvas order (row j, column i; not flipped):
+   depth as double (-DBL_MAX where empty), winner key (0 = background) */
+int c3d_frame_canvas(c3d_context_t *ctx, double *host_depth, uint64_t *host_key);
+
+/* ---- stage-level entry points (parity tests, mesh export) ---- */
+
+/* replaces the classification of triangulate_tetrahedron (triangulate.c:145-152,176-192):
+   per cube of the extended array the six pre-fold 4-bit masks (24 bits) and the triangle count */
+int c3d_case_codes(c3d_context_t *ctx, const c3d_field_t *field, double threshold, uint32_t *host_codes, uint8_t *host_counts);
+/* the streaming sweep: compact list of active cubes, (cube << 8) | corner bits.
+   rendered_only = 1 restricts to the cubes the reference renders (contour/main.c:92-93).
+   Writes min(*count, capacity) entries in unspecified order. */
+int c3d_sweep(c3d_context_t *ctx, const c3d_field_t *field, double threshold, int rendered_only,
+              size_t capacity, uint64_t *host_entries, uint64_t *count);
+/* replaces contour3d_contour_triangulate_slice + compute_vertex_normals for the whole array
+   (triangulate.c:287-342, normal.c:46-165): all triangles, vertex normals for interior cubes,
+   sorted by (cube, tri).  Writes min(*count, capacity) records. */
+int c3d_tessellate(c3d_context_t *ctx, const c3d_field_t *field, const double *const grids[3], double threshold,
+                   size_t capacity, c3d_triangle_t *host_out, uint64_t *count);
+
+/* library / build information, e.g. "contour3d_b200 0.1 sm_100a" */
+const char *c3d_version(void);
+
+#if defined(__cplusplus)
+}
+#endif
+
+#endif /* CONTOUR3D_B200_H */
