@@ -143,7 +143,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -m contour3d_b200.build` (there is no CPU fallback)")
         compat()
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(LIB_PATH)
         vp, sz, dbl, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_int
         L.c3d_version.restype = C.c_char_p
         L.c3d_nccl_unique_id.argtypes = [vp]

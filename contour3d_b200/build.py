@@ -88,7 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force or _newer(LIB, objs):
         # `sdecomp` and the MPI_* symbols stay undefined: the embedding program
         # (or libc3d_sdecomp_compat.so) provides them
-        _run([nvcc, "-shared", "-o", LIB] + objs + ["-lnccl", "-Xlinker", "--allow-shlib-undefined"])
+        _run([nvcc, "-shared", "-o", LIB] + objs + ["-ldl", "-Xlinker", "--allow-shlib-undefined"])
     if not have_real_mpi():
         srcs = [os.path.join(CSRC, "c3d_sdecomp_compat.c"), os.path.join(MINIMPI, "minimpi.c")]
         if force or _newer(COMPAT, srcs + headers):

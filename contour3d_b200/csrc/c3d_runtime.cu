@@ -19,6 +19,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include <nccl.h>
+#include <dlfcn.h>
 #include "contour3d_b200.h"
 #include "c3d_internal.h"
 
@@ -53,8 +54,44 @@ static int c3d_error(const char *fmt, ...) {
 #define NCCL_OK(call) \
   do { \
     const ncclResult_t err_ = (call); \
-    if (ncclSuccess != err_) return c3d_error("%s failed: %s (%s:%d)", #call, ncclGetErrorString(err_), __FILE__, __LINE__); \
+    if (ncclSuccess != err_) return c3d_error("%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(err_), __FILE__, __LINE__); \
   } while (0)
+
+/*
+ * NCCL is bound lazily with dlopen the first time a multi-rank context is
+ * created: a single-GPU process never loads it, and a process that already
+ * holds an NCCL (e.g. the one bundled with PyTorch, same soname libnccl.so.2)
+ * re-uses that copy instead of pulling in a second, possibly older, one.
+ */
+struct NcclApi {
+  void *handle;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)(void);
+  ncclResult_t (*GroupEnd)(void);
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t);
+  const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi g_nccl;
+
+static int nccl_load(void) {
+  if (NULL != g_nccl.handle) return 0;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (NULL == h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (NULL == h) return c3d_error("multi-GPU runs need NCCL, but libnccl.so.2 could not be loaded: %s", dlerror());
+#define C3D_BIND(name) \
+  *(void **)(&g_nccl.name) = dlsym(h, "nccl" #name); \
+  if (NULL == g_nccl.name) return c3d_error("libnccl.so.2 lacks nccl" #name)
+  C3D_BIND(GetUniqueId); C3D_BIND(CommInitRank); C3D_BIND(CommDestroy); C3D_BIND(GroupStart); C3D_BIND(GroupEnd);
+  C3D_BIND(Send); C3D_BIND(Recv); C3D_BIND(AllReduce); C3D_BIND(Reduce); C3D_BIND(GetErrorString);
+#undef C3D_BIND
+  g_nccl.handle = h;
+  return 0;
+}
 
 struct c3d_field {
   c3d_decomp_t decomp;
@@ -102,8 +139,9 @@ extern "C" const char *c3d_version(void) { return "contour3d_b200 0.1 (sm_100a, 
 extern "C" int c3d_nccl_unique_id(void *id128) {
   if (NULL == id128) return c3d_error("c3d_nccl_unique_id: NULL output");
   static_assert(sizeof(ncclUniqueId) == C3D_NCCL_ID_BYTES, "ncclUniqueId size");
+  if (0 != nccl_load()) return 1;
   ncclUniqueId id;
-  NCCL_OK(ncclGetUniqueId(&id));
+  NCCL_OK(g_nccl.GetUniqueId(&id));
   memcpy(id128, &id, sizeof(id));
   return 0;
 }
@@ -150,9 +188,10 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   CUDA_OK(cudaMalloc(&ctx->views_dev, C3D_MAX_OBJECTS * sizeof(FieldView)));
   if (comm_size > 1) {
     if (NULL == nccl_id128) return c3d_error("c3d_context_create: %d ranks need an NCCL unique id", comm_size);
+    if (0 != nccl_load()) return 1;
     ncclUniqueId id;
     memcpy(&id, nccl_id128, sizeof(id));
-    NCCL_OK(ncclCommInitRank(&ctx->comm, comm_size, id, comm_rank));
+    NCCL_OK(g_nccl.CommInitRank(&ctx->comm, comm_size, id, comm_rank));
     ctx->has_comm = true;
   }
   *out = ctx;
@@ -163,7 +202,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   if (NULL == ctx) return 0;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->has_comm) ncclCommDestroy(ctx->comm);
+  if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
   cudaFree(ctx->table_mem);
   cudaFree(ctx->depth); cudaFree(ctx->key); cudaFree(ctx->depth_global); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
   if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
@@ -344,10 +383,10 @@ extern "C" int c3d_field_exchange(c3d_context_t *ctx, c3d_field_t *f) {
       const long long jfirst = (long long)f->lo[1], jlast = (long long)(f->lo[1] + f->mysizes[1]) - 2;
       if (lo >= 0) LAUNCH_OK(c3d_k_halo_pack_y(f->data, f->elem_bytes, nx, sy, sz, k0, nk, jfirst, send_lo, ctx->stream));
       if (hi >= 0) LAUNCH_OK(c3d_k_halo_pack_y(f->data, f->elem_bytes, nx, sy, sz, k0, nk, jlast, send_hi, ctx->stream));
-      NCCL_OK(ncclGroupStart());
-      if (lo >= 0) { NCCL_OK(ncclSend(send_lo, chunk, dt, lo, ctx->comm, ctx->stream)); NCCL_OK(ncclRecv(recv_lo, chunk, dt, lo, ctx->comm, ctx->stream)); }
-      if (hi >= 0) { NCCL_OK(ncclSend(send_hi, chunk, dt, hi, ctx->comm, ctx->stream)); NCCL_OK(ncclRecv(recv_hi, chunk, dt, hi, ctx->comm, ctx->stream)); }
-      NCCL_OK(ncclGroupEnd());
+      NCCL_OK(g_nccl.GroupStart());
+      if (lo >= 0) { NCCL_OK(g_nccl.Send(send_lo, chunk, dt, lo, ctx->comm, ctx->stream)); NCCL_OK(g_nccl.Recv(recv_lo, chunk, dt, lo, ctx->comm, ctx->stream)); }
+      if (hi >= 0) { NCCL_OK(g_nccl.Send(send_hi, chunk, dt, hi, ctx->comm, ctx->stream)); NCCL_OK(g_nccl.Recv(recv_hi, chunk, dt, hi, ctx->comm, ctx->stream)); }
+      NCCL_OK(g_nccl.GroupEnd());
       if (lo >= 0) LAUNCH_OK(c3d_k_halo_unpack_y(f->data, f->elem_bytes, nx, sy, sz, k0, nk, 0, recv_lo, ctx->stream));
       if (hi >= 0) LAUNCH_OK(c3d_k_halo_unpack_y(f->data, f->elem_bytes, nx, sy, sz, k0, nk, (long long)(f->lo[1] + f->mysizes[1]), recv_hi, ctx->stream));
     }
@@ -358,16 +397,16 @@ extern "C" int c3d_field_exchange(c3d_context_t *ctx, c3d_field_t *f) {
       const size_t plane = (size_t)sz, chunk = 2 * plane;
       char *base = (char *)f->data;
       const size_t kfirst = f->lo[2], klast = f->lo[2] + f->mysizes[2] - 2;
-      NCCL_OK(ncclGroupStart());
+      NCCL_OK(g_nccl.GroupStart());
       if (lo >= 0) {
-        NCCL_OK(ncclSend(base + kfirst * plane * eb, chunk, dt, lo, ctx->comm, ctx->stream));
-        NCCL_OK(ncclRecv(base, chunk, dt, lo, ctx->comm, ctx->stream));
+        NCCL_OK(g_nccl.Send(base + kfirst * plane * eb, chunk, dt, lo, ctx->comm, ctx->stream));
+        NCCL_OK(g_nccl.Recv(base, chunk, dt, lo, ctx->comm, ctx->stream));
       }
       if (hi >= 0) {
-        NCCL_OK(ncclSend(base + klast * plane * eb, chunk, dt, hi, ctx->comm, ctx->stream));
-        NCCL_OK(ncclRecv(base + (f->lo[2] + f->mysizes[2]) * plane * eb, chunk, dt, hi, ctx->comm, ctx->stream));
+        NCCL_OK(g_nccl.Send(base + klast * plane * eb, chunk, dt, hi, ctx->comm, ctx->stream));
+        NCCL_OK(g_nccl.Recv(base + (f->lo[2] + f->mysizes[2]) * plane * eb, chunk, dt, hi, ctx->comm, ctx->stream));
       }
-      NCCL_OK(ncclGroupEnd());
+      NCCL_OK(g_nccl.GroupEnd());
     }
   }
   f->halo_valid = true;
@@ -595,7 +634,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   /* 4. nearest depth across ranks (replaces the depth half of MPI_Reduce, output.c:10-30,82) */
   const unsigned long long *depth_global = NULL;
   if (ctx->size > 1) {
-    NCCL_OK(ncclAllReduce(ctx->depth, ctx->depth_global, npix, ncclUint64, ncclMax, ctx->comm, s));
+    NCCL_OK(g_nccl.AllReduce(ctx->depth, ctx->depth_global, npix, ncclUint64, ncclMax, ctx->comm, s));
     depth_global = ctx->depth_global;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
@@ -605,7 +644,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
   /* 6. colours to the writer (the colour half of the reference's reduce) */
   if (ctx->size > 1) {
-    NCCL_OK(ncclReduce(ctx->rgba, ctx->rgba, npix, ncclUint32, ncclMax, 0, ctx->comm, s));
+    NCCL_OK(g_nccl.Reduce(ctx->rgba, ctx->rgba, npix, ncclUint32, ncclMax, 0, ctx->comm, s));
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE1], s));
   if (0 == ctx->rank) {

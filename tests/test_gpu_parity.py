@@ -1,0 +1,261 @@
+"""GPU: the CUDA path, called through the C-ABI, against the oracle and the golden vectors.
+
+Bars (BASELINE.json): triangle counts and per-cube case codes bit-exact; vertex
+positions / normals within 1e-5 relative (we assert bit-equality, which is
+stronger); image differing in <= 0.1 % of pixels by <= 1 LSB (we assert 0)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_records_equal, image_diff, load_golden
+from contour3d_b200 import api, casefile, scenes
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5          # positions and normals, relative (BASELINE.json north_star)
+MAX_PIXEL_FRACTION = 1e-3
+MAX_LSB = 1
+
+
+def _grids_for(shape, rng=None):
+    nz, ny, nx = shape
+    if rng is None:
+        return scenes.uniform_grids(nx, ny, nz)
+    return [np.sort(rng.uniform(-0.5, 0.5, n)) for n in (nx, ny, nz)]
+
+
+def _check_stage(ctx, field, grids, thr):
+    nz, ny, nx = field.shape
+    f = ctx.field((nx, ny, nz), dtype=field.dtype).upload(field)
+    try:
+        codes, counts = ctx.case_codes(f, thr)
+        ocodes, ocounts = oracle.case_codes(field, grids, thr)
+        assert np.array_equal(codes, ocodes), "per-cube case codes differ"
+        assert np.array_equal(counts, ocounts), "per-cube triangle counts differ"
+        # streaming sweep: all active cubes, then the rendered subset
+        for rendered_only in (False, True):
+            entries = np.sort(ctx.sweep(f, thr, rendered_only=rendered_only))
+            cz, cy, cx = counts.shape
+            act = counts > 0
+            if rendered_only:
+                m = np.zeros_like(act)
+                m[1:cz - 1, 1:cy - 1, 1:cx - 1] = True
+                act &= m
+            want_cubes = np.flatnonzero(act.reshape(-1)).astype(np.uint64)
+            assert np.array_equal(entries >> np.uint64(8), want_cubes), "active-cube list differs"
+        got = ctx.tessellate(f, grids, thr)
+        want, _ = oracle.tessellate(field, grids, thr)
+        assert_records_equal(got, want, "tessellate")
+        # the tolerance the north star states, written out (bit-equality above implies it)
+        if len(got):
+            scale = np.abs(want["v"]).max()
+            assert np.abs(got["v"] - want["v"]).max() <= REL_TOL * scale
+    finally:
+        f.destroy()
+
+
+@pytest.mark.parametrize("shape,thr,dtype,seed", [
+    ((16, 16, 16), 0.05, np.float64, 0),
+    ((9, 10, 11), -0.2, np.float64, 1),       # ragged, scalar-load path (nx % 4 != 0)
+    ((7, 6, 132), 0.1, np.float32, 2),        # two x segments, aligned
+    ((5, 9, 130), 0.0, np.float32, 3),        # two x segments, unaligned rows
+    ((4, 4, 4), 0.1, np.float32, 4),          # smallest array with a rendered cube
+    ((2, 2, 2), 0.0, np.float64, 5),          # single cube, nothing rendered
+    ((40, 33, 20), 0.3, np.float32, 6),       # several y tiles and z chunks
+])
+def test_stage_parity_random_fields(ctx, shape, thr, dtype, seed):
+    rng = np.random.default_rng(seed)
+    field = (rng.normal(size=shape) * 0.4).astype(dtype)
+    _check_stage(ctx, field, _grids_for(shape, rng), float(dtype(thr)))
+
+
+def test_stage_parity_smooth_field(ctx):
+    f, g = scenes.sines(36, seed=5)
+    _check_stage(ctx, f, g, 0.1)
+
+
+def test_stage_parity_empty_surface(ctx):
+    field = np.zeros((8, 8, 8), dtype=np.float32)
+    _check_stage(ctx, field, _grids_for(field.shape), 0.5)     # all below
+    _check_stage(ctx, field, _grids_for(field.shape), -0.5)    # all above
+
+
+@pytest.mark.parametrize("name", ["tess_ragged.npz", "tess_exact_hits.npz"])
+def test_stage_parity_golden_from_reference(ctx, name):
+    g = load_golden(name)
+    grids = [g["gx"], g["gy"], g["gz"]]
+    nz, ny, nx = g["field"].shape
+    f = ctx.field((nx, ny, nz), dtype=np.float64).upload(g["field"])
+    try:
+        assert_records_equal(ctx.tessellate(f, grids, g["threshold"]), g["triangles"], name)
+    finally:
+        f.destroy()
+
+
+def _render_both(ctx, scene, fields, grids, contours, lines, dtype=None):
+    nz, ny, nx = fields[0].shape
+    dev = [ctx.field((nx, ny, nz), dtype=f.dtype).upload(f) for f in fields]
+    try:
+        cs = [dict(field=dev[c.get("field", 0)], grids=grids, threshold=c["threshold"], color=c["color"]) for c in contours]
+        img = ctx.render(scene, cs, lines)
+        depth, key = ctx.canvas(scene["width"], scene["height"])
+    finally:
+        for d in dev:
+            d.destroy()
+    ocs = [dict(field=fields[c.get("field", 0)], grids=grids, threshold=c["threshold"], color=c["color"]) for c in contours]
+    rgb, odepth, stats = oracle.frame(scene, ocs, lines, nthreads=4)
+    return img, rgb[::-1], depth, odepth, key
+
+
+def _assert_image(img, want):
+    frac, worst = image_diff(img, want)
+    assert frac <= MAX_PIXEL_FRACTION and worst <= MAX_LSB, (frac, worst)
+    assert frac == 0.0, f"{frac} of the pixels differ (bit-exactness expected)"
+
+
+@pytest.mark.parametrize("name", ["frame_sines24.npz", "frame_gyroid32.npz"])
+def test_frame_golden_from_reference(ctx, name):
+    g = load_golden(name)
+    grids = [g["gx"], g["gy"], g["gz"]]
+    img, want, depth, odepth, key = _render_both(ctx, g["scene"], [g["field"]], grids, g["contours"], g["lines"])
+    _assert_image(img, g["image"])
+    _assert_image(img, want)
+    assert np.array_equal(depth, odepth), "z-buffer differs from the oracle"
+
+
+def test_frame_three_isovalues_noise_fp32(ctx):
+    """config 3 in miniature: multi-octave noise, 3 isovalues, 16:9"""
+    f = scenes.noise(48, seed=1234)
+    g = scenes.uniform_grids(48, 48, 48)
+    scene = scenes.scene(384, 216)
+    contours = [dict(threshold=float(np.float32(t)), color=c) for t, c in
+                ((-0.3, (255, 80, 80)), (0.05, (80, 255, 80)), (0.4, (80, 80, 255)))]
+    img, want, depth, odepth, key = _render_both(ctx, scene, [f], g, contours, scenes.box_lines(nitems=32, width=3.0))
+    _assert_image(img, want)
+    assert np.array_equal(depth, odepth)
+    assert (key != 0).sum() > 0.05 * key.size
+
+
+def test_frame_two_fields(ctx):
+    """config 4 in miniature: two different fields sharing camera and light"""
+    a = scenes.noise(32, seed=1)
+    b = scenes.gyroid(32, periods=1.5)
+    g = scenes.uniform_grids(32, 32, 32)
+    scene = scenes.scene(256, 144)
+    contours = [dict(field=0, threshold=0.1, color=(250, 250, 50)), dict(field=1, threshold=float(np.float32(0.2)), color=(50, 250, 250)),
+                dict(field=0, threshold=-0.1, color=(250, 50, 250))]
+    img, want, depth, odepth, _ = _render_both(ctx, scene, [a, b], g, contours, [])
+    _assert_image(img, want)
+    assert np.array_equal(depth, odepth)
+
+
+def test_frame_lines_only_and_background(ctx):
+    scene = scenes.scene(160, 120, bg=(7, 8, 9))
+    g = scenes.uniform_grids(8, 8, 8)
+    f = np.zeros((8, 8, 8), dtype=np.float32)
+    img, want, *_ = _render_both(ctx, scene, [f], g, [dict(threshold=0.5, color=(1, 2, 3))], scenes.box_lines(nitems=9, width=5.0))
+    _assert_image(img, want)
+    assert (img == np.array([7, 8, 9], dtype=np.uint8)).all(axis=2).any()
+
+
+def test_frame_partly_off_screen_and_behind_camera(ctx):
+    """triangles whose vertices fail projection are dropped silently (render.c:62-72), bbox clamps to the screen"""
+    f, g = scenes.sines(24, seed=9)
+    scene = scenes.scene(200, 150)
+    scene["camera"] = (0.2, -0.45, 0.3)            # inside the volume: part of the surface is behind the screen
+    scene["center"] = (0.1, -0.225, 0.15)
+    img, want, depth, odepth, _ = _render_both(ctx, scene, [f], g, [dict(threshold=0.0, color=(255, 255, 255))], scenes.box_lines(nitems=20, width=2.0))
+    _assert_image(img, want)
+    assert np.array_equal(depth, odepth)
+
+
+def test_frame_exact_threshold_hits_nan_normals(ctx):
+    """zero-area triangles give NaN normals that fall back to the 0.15 ambient floor (render.c:151-155)"""
+    g = load_golden("tess_exact_hits.npz")
+    grids = [g["gx"], g["gy"], g["gz"]]
+    scene = scenes.scene(200, 150)
+    img, want, depth, odepth, _ = _render_both(ctx, scene, [g["field"]], grids, [dict(threshold=1.0, color=(200, 200, 200))], [])
+    _assert_image(img, want)
+    assert np.array_equal(depth, odepth)
+
+
+def test_dropin_contour3d_execute_host_buffers(ctx, tmp_path):
+    """the public entry point, host double arrays in, PPM file out; config 1 in miniature"""
+    g = load_golden("frame_sines24.npz")
+    grids = [g["gx"], g["gy"], g["gz"]]
+    out = str(tmp_path / "out.ppm")
+    rc = api.execute(g["scene"], grids, [np.ascontiguousarray(g["field"], dtype=np.float64)], g["contours"], g["lines"], out)
+    assert rc == 0
+    raw = open(out, "rb").read()
+    h, w, _ = g["image"].shape
+    assert raw.startswith(f"P6\n{w} {h}\n255\n".encode())
+    _assert_image(api.read_ppm(out), g["image"])
+
+
+def test_dropin_rejects_what_it_cannot_honour(ctx, tmp_path, capfd):
+    g = load_golden("frame_gyroid32.npz")
+    grids = [g["gx"], g["gy"], g["gz"]]
+    arr = np.ascontiguousarray(g["field"], dtype=np.float64)
+    bad_line = [dict(edges=((0, 0, 0), (1, 1, 1)), nitems=1, width=1.0)]
+    rc = api.execute(g["scene"], grids, [arr], g["contours"], bad_line, str(tmp_path / "x.ppm"))
+    assert rc == 1                                   # nitems < 2 is an error in the reference too (line.c:144-147)
+    assert "[CONTOUR3D ERROR]" in capfd.readouterr().err
+    rc = api.execute(g["scene"], grids, [arr], g["contours"], [], str(tmp_path / "no" / "such" / "dir" / "x.ppm"))
+    assert rc == 1                                   # fopen failure (output.c:126-130)
+
+
+def test_demo_config1_md5(ctx, tmp_path):
+    """BASELINE config 1: the reference's built-in demo; the PPM must have the reference's md5"""
+    demo_case = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "demo_case")
+    if not os.path.exists(demo_case):
+        pytest.skip("oracle/_ref/demo_case not built")
+    import subprocess
+
+    case = str(tmp_path / "demo.bin")
+    subprocess.run([demo_case, case], check=True)
+    scene, grids, fields, contours, lines = casefile.read_case(case)
+    out = str(tmp_path / "demo.ppm")
+    rc = api.execute(scene, grids, fields, contours, lines, out)
+    assert rc == 0
+    golden = json.load(open(os.path.join(GOLDEN, "demo_md5.json")))["md5"]
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == golden["a.out ranks=1"]
+
+
+def test_full_size_properties_512(ctx):
+    """config 2 at full size (gyroid 512^3 fp32, generated on the device): size-independent checks"""
+    n = 512
+    f = ctx.field((n, n, n), dtype=np.float32).synthesize(0)
+    try:
+        thr = float(np.float32(0.1))
+        entries = ctx.sweep(f, thr, rendered_only=True)
+        # every entry is unique, inside the rendered range, and its corner bits are a cut pattern
+        cubes = entries >> np.uint64(8)
+        code = (entries & np.uint64(255)).astype(np.int64)
+        assert len(np.unique(cubes)) == len(cubes)
+        assert ((code != 0) & (code != 255)).all()
+        c = n - 1
+        i, j, k = cubes % c, (cubes // c) % c, cubes // (c * c)
+        for v in (i, j, k):
+            assert v.min() >= 1 and v.max() <= n - 3
+        # idempotence: a second sweep gives the same set
+        assert np.array_equal(np.sort(entries), np.sort(ctx.sweep(f, thr, rendered_only=True)))
+        # cross-check a slab against the oracle on the downloaded bits
+        host = f.download_ext()
+        sub = host[100:108, 200:232, 64:200]
+        g = scenes.uniform_grids(n, n, n)
+        ocodes, ocounts = oracle.case_codes(sub, [g[0][64:200], g[1][200:232], g[2][100:108]], thr)
+        sel = (k >= 100) & (k < 107) & (j >= 200) & (j < 231) & (i >= 64) & (i < 199)
+        assert sel.sum() == int((ocounts > 0).sum())
+        # frame renders and is deterministic
+        scene = scenes.scene(1920, 1080)
+        cs = [dict(field=f, grids=g, threshold=thr, color=(255, 200, 100))]
+        a = ctx.render(scene, cs, [])
+        b = ctx.render(scene, cs, [])
+        assert np.array_equal(a, b)
+        assert (a.reshape(-1, 3).max(axis=1) > 0).mean() > 0.2
+    finally:
+        f.destroy()

@@ -1,0 +1,120 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from contour3d_b200 import api, casefile, scenes
+
+
+def test_library_exports_every_declared_symbol():
+    declared = set()
+    for header in ("contour3d_b200.h", "contour3d.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b(c3d_[a-z0-9_]+|contour3d_execute)\s*\(", text))
+    declared = {d for d in declared if not d.endswith("_t")}
+    assert declared, "no declarations found"
+    L = api.lib()
+    missing = [name for name in sorted(declared) if not hasattr(L, name)]
+    assert not missing, missing
+    assert set(api.EXPORTS) == declared, set(api.EXPORTS) ^ declared
+
+
+def test_version_string():
+    assert b"sm_100a" in api.lib().c3d_version()
+
+
+def test_public_struct_layout_matches_reference_abi():
+    # sizes probed from the reference on x86-64 SysV
+    assert C.sizeof(api.ContourObj) == 88
+    assert C.sizeof(api.LineObj) == 80
+    assert C.sizeof(api.Color) == 3
+    assert C.sizeof(api.Vector) == 24
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.C3DError):
+        api.Context()
+
+
+@pytest.mark.parametrize("n,p", [(10, 3), (128, 8), (1024, 8), (7, 7), (100, 1)])
+def test_block_decomposition_matches_simpledecomp_rule(n, p):
+    # mysize = (glsize + rank) / nprocs, offset = prefix sum (sdecomp/kernel.c:89,111-116)
+    total = 0
+    for r in range(p):
+        d = api.make_decomp((1, 1, p), r)
+        my, off = api.decomp_local(d, (n, n, n))
+        assert my[2] == (n + r) // p and off[2] == total
+        assert my[0] == n and off[0] == 0
+        total += my[2]
+    assert total == n
+
+
+def test_cartesian_neighbours_row_major_z_fastest():
+    d = api.make_decomp((1, 3, 2), 3)  # coords (y, z) = (1, 1)
+    assert list(d.myrank) == [0, 1, 1]
+    assert [list(x) for x in d.neighbours] == [[-1, -1], [1, 5], [2, -1]]
+    with pytest.raises(api.C3DError):
+        api.make_decomp((2, 1, 1), 0)  # x is never split
+
+
+def test_sdecomp_standin_getters():
+    info = api.sdecomp_construct((0, 0, 0))
+    assert info.value
+
+
+def test_casefile_roundtrip(tmp_path):
+    f = scenes.gyroid(8)
+    g = scenes.uniform_grids(8, 8, 8)
+    sc = scenes.scene(64, 48, bg=(1, 2, 3))
+    cs = [dict(field=0, threshold=0.25, color=(9, 8, 7))]
+    ls = scenes.box_lines(nitems=5, width=1.5)
+    p = str(tmp_path / "c.bin")
+    casefile.write_case(p, sc, g, [f], cs, ls)
+    sc2, g2, f2, cs2, ls2 = casefile.read_case(p)
+    assert np.array_equal(f2[0], f) and all(np.array_equal(a, b) for a, b in zip(g, g2))
+    assert sc2["width"] == 64 and sc2["bg"] == (1, 2, 3) and cs2 == cs
+    assert ls2[3]["nitems"] == 5 and ls2[3]["width"] == 1.5
+
+
+def test_case_tables_agree_with_oracle_counts():
+    """the product's 256-entry case table (c3d_tables.h) against the oracle's per-tetra classification"""
+    from oracle import oracle
+
+    # enumerate all 256 corner patterns as 2x2x2 fields
+    lut = np.array([0, 1, 1, 2, 1, 2, 2, 1, 1, 2, 2, 1, 2, 1, 1, 0])
+    for code in range(256):
+        f = np.array([(code >> n) & 1 for n in range(8)], dtype=np.float64).reshape(2, 2, 2)
+        codes, counts = oracle.case_codes(f, [np.arange(2.0)] * 3, 0.5)
+        total = sum(lut[(int(codes[0, 0, 0]) >> (4 * n)) & 15] for n in range(6))
+        assert total == int(counts[0, 0, 0])
+    src = open(os.path.join(ROOT, "contour3d_b200", "csrc", "c3d_tables.h")).read()
+    assert "c3d_tables_build" in src
+
+
+def test_minimpi_fork_mode_bcast_and_reduce(tmp_path):
+    """compat/minimpi: 3 forked ranks agree on a broadcast and a max-allreduce"""
+    src = tmp_path / "t.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <mpi.h>\n'
+        "int main(void){MPI_Init(NULL,NULL);int r,n;MPI_Comm_rank(MPI_COMM_WORLD,&r);MPI_Comm_size(MPI_COMM_WORLD,&n);"
+        "int v=r==0?42:0;MPI_Bcast(&v,1,MPI_INT,0,MPI_COMM_WORLD);double m=r;MPI_Allreduce(MPI_IN_PLACE,&m,1,MPI_DOUBLE,MPI_MAX,MPI_COMM_WORLD);"
+        'if(v!=42||m!=n-1)return 1;if(r==0)printf("ok %d\\n",n);MPI_Finalize();return 0;}\n'
+    )
+    exe = tmp_path / "t"
+    mm = os.path.join(ROOT, "compat", "minimpi")
+    subprocess.run(["gcc", "-std=gnu11", "-I", mm, str(src), os.path.join(mm, "minimpi.c"), "-o", str(exe), "-lpthread", "-lrt"], check=True)
+    env = dict(os.environ, MINIMPI_NP="3")
+    for k in ("RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run([str(exe)], env=env, capture_output=True, text=True, check=True).stdout
+    assert out.strip() == "ok 3"

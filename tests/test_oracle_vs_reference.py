@@ -1,0 +1,64 @@
+"""CPU: pin the oracle restatement to the UNMODIFIED reference (oracle/_ref).
+
+Skipped when oracle/_ref is absent (it is built from /root/reference by
+oracle/Makefile in the development container and travels to the GPU box as
+prebuilt binaries; nothing here reads /root/reference at run time)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_records_equal, image_diff
+from contour3d_b200 import casefile, scenes
+from contour3d_b200.api import read_ppm
+from oracle import oracle, reference
+
+pytestmark = pytest.mark.skipif(not reference.available(), reason="oracle/_ref not built")
+
+
+@pytest.mark.parametrize("shape,thr,seed", [((9, 8, 7), 0.05, 0), ((16, 16, 16), -0.3, 1), ((5, 21, 6), 0.2, 2), ((4, 4, 4), 0.0, 3)])
+def test_stage_level_triangles(shape, thr, seed):
+    rng = np.random.default_rng(seed)
+    nz, ny, nx = shape
+    grids = [np.sort(rng.uniform(-0.5, 0.5, n)) for n in (nx, ny, nz)]
+    field = rng.normal(size=shape) * 0.3
+    assert_records_equal(oracle.tessellate(field, grids, thr)[0], reference.tessellate(field, grids, thr), str(shape))
+
+
+def test_stage_level_smooth_field():
+    f, g = scenes.sines(20)
+    assert_records_equal(oracle.tessellate(f, g, 0.1)[0], reference.tessellate(f, g, 0.1), "sines20")
+
+
+def test_demo_md5_pins_the_toolchain(tmp_path):
+    """config 1: the reference's own a.out, the case-file path and the oracle all give the same image"""
+    golden = json.load(open(os.path.join(GOLDEN, "demo_md5.json")))["md5"]
+    case = str(tmp_path / "demo32.bin")
+    reference.write_demo_case(case, 32, 320, 240)
+    out = str(tmp_path / "ref.ppm")
+    reference.run_case(case, out, ranks=2)
+    md5_ref = hashlib.md5(open(out, "rb").read()).hexdigest()
+    assert md5_ref == golden["ref_driver(demo_case 32 320 240)"]
+    scene, grids, fields, contours, lines = casefile.read_case(case)
+    cs = [dict(field=fields[c["field"]], grids=grids, threshold=c["threshold"], color=c["color"]) for c in contours]
+    rgb, _, _ = oracle.frame(scene, cs, lines, nthreads=2)
+    mine = str(tmp_path / "oracle.ppm")
+    oracle.write_ppm(mine, rgb)
+    assert hashlib.md5(open(mine, "rb").read()).hexdigest() == md5_ref
+
+
+@pytest.mark.parametrize("ranks,dims", [(1, None), (2, (1, 2, 1)), (4, (1, 1, 4)), (6, (1, 3, 2))])
+def test_reference_is_decomposition_invariant_and_matches_oracle(tmp_path, ranks, dims):
+    f, g = scenes.sines(28, seed=11)
+    scene = scenes.scene(200, 150)
+    contours = [dict(field=0, threshold=0.2, color=(255, 128, 0)), dict(field=0, threshold=-0.2, color=(0, 128, 255))]
+    lines = scenes.box_lines(nitems=16, width=3.0)
+    case, out = str(tmp_path / "c.bin"), str(tmp_path / "o.ppm")
+    casefile.write_case(case, scene, g, [f], contours, lines)
+    reference.run_case(case, out, ranks=ranks, dims=dims)
+    cs = [dict(field=f, grids=g, threshold=c["threshold"], color=c["color"]) for c in contours]
+    rgb, _, _ = oracle.frame(scene, cs, lines, nthreads=1)
+    frac, worst = image_diff(read_ppm(out), rgb[::-1])
+    assert frac == 0.0, (frac, worst)
