@@ -95,6 +95,21 @@ __device__ __forceinline__ V3 cut_edge(const Cube &c, const double thr, const un
   return v_add(p0, v_mul(factor, v_sub(p1, p0)));
 }
 
+/* the same vertex straight from global memory (no register-indexed cube copy):
+   used where a thread needs one triangle of a cube, not all of them */
+__device__ __forceinline__ V3 cut_edge_global(const FieldView &f, const long long i, const long long j, const long long k,
+                                              const double thr, const unsigned int tail, const unsigned int head) {
+  const long long base = k * f.sz + j * f.sy + i;
+  const double v0 = ld_value(f, base + (tail & 1u) + ((tail >> 1) & 1u) * f.sy + (tail >> 2) * f.sz);
+  const double v1 = ld_value(f, base + (head & 1u) + ((head >> 1) & 1u) * f.sy + (head >> 2) * f.sz);
+  const V3 p0 = V3{__ldg(f.g[0] + i + (tail & 1u)), __ldg(f.g[1] + j + ((tail >> 1) & 1u)), __ldg(f.g[2] + k + (tail >> 2))};
+  const double dv = r_sub(v1, v0);
+  if (fabs(dv) < 1.e-8) return p0;
+  const double factor = r_div(r_sub(thr, v0), dv);
+  const V3 p1 = V3{__ldg(f.g[0] + i + (head & 1u)), __ldg(f.g[1] + j + ((head >> 1) & 1u)), __ldg(f.g[2] + k + (head >> 2))};
+  return v_add(p0, v_mul(factor, v_sub(p1, p0)));
+}
+
 __device__ __forceinline__ void triangle_vertices(const Cube &c, const double thr, const unsigned int pairs, V3 v[3]) {
 #pragma unroll
   for (int m = 0; m < 3; m++) {
@@ -183,9 +198,12 @@ __device__ __forceinline__ bool project(const Cam &c, const V3 p, V3 &out) {
   return true;
 }
 
-/* a projected triangle prepared for per-pixel tests (render.c:74-115) */
+/* a projected triangle prepared for per-pixel tests (render.c:74-115).
+   The differences (b - a) of the three edge functions are per-triangle
+   constants of render.c:38-46; hoisting them changes no rounding. */
 struct Tri2D {
   V3 q[3];
+  double ey[3], ex[3];     /* edge m: a = q[(m+1)%3], b = q[(m+2)%3]; ey = b.y - a.y, ex = b.x - a.x */
   double area_inv;
   long long imin, imax, jmin, jmax;
 };
@@ -193,11 +211,6 @@ struct Tri2D {
 __device__ __forceinline__ long long clamp_ll(const long long lo, const long long hi, const long long v) {
   const long long m = v < lo ? lo : v;
   return hi < m ? hi : m;
-}
-
-__device__ __forceinline__ double edge_fn(const V3 &a, const V3 &b, const double px, const double py) {
-  /* render.c:38-46 */
-  return r_sub(r_mul(r_sub(px, a.x), r_sub(b.y, a.y)), r_mul(r_sub(py, a.y), r_sub(b.x, a.x)));
 }
 
 __device__ __forceinline__ bool setup_triangle(const Cam &c, const V3 v[3], Tri2D &t) {
@@ -218,18 +231,31 @@ __device__ __forceinline__ bool setup_triangle(const Cam &c, const V3 v[3], Tri2
   t.imax = clamp_ll(0, c.w - 1, xmax);
   t.jmin = clamp_ll(0, c.h - 1, ymin);
   t.jmax = clamp_ll(0, c.h - 1, ymax);
-  const double area = edge_fn(t.q[0], t.q[1], t.q[2].x, t.q[2].y);
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const V3 &a = t.q[(m + 1) % 3], &b = t.q[(m + 2) % 3];
+    t.ey[m] = r_sub(b.y, a.y);
+    t.ex[m] = r_sub(b.x, a.x);
+  }
+  /* area = edge_function(v0, v1, v2), render.c:102: a = q0, b = q1 (edge 2), evaluated at q2 */
+  const double area = r_sub(r_mul(r_sub(t.q[2].x, t.q[0].x), t.ey[2]), r_mul(r_sub(t.q[2].y, t.q[0].y), t.ex[2]));
   t.area_inv = r_div(1., area < 0. ? fmin(area, -1.e-16) : fmax(area, +1.e-16));
   return true;
 }
 
-/* barycentric weights of pixel (i, j); false when outside (render.c:94-115) */
-__device__ __forceinline__ bool pixel_weights(const Cam &c, const Tri2D &t, const long long i, const long long j, double w[3]) {
-  const double px = r_sub(r_div(r_add((double)i, 0.5), c.W), 0.5);
-  const double py = r_sub(r_div(r_add((double)j, 0.5), c.H), 0.5);
-  w[0] = r_mul(t.area_inv, edge_fn(t.q[1], t.q[2], px, py));
-  w[1] = r_mul(t.area_inv, edge_fn(t.q[2], t.q[0], px, py));
-  w[2] = r_mul(t.area_inv, edge_fn(t.q[0], t.q[1], px, py));
+/* pixel-centre coordinate, render.c:94-98 (tabulated per screen size by k_pixel_tables) */
+__device__ __forceinline__ double pixel_centre(const long long i, const double n) {
+  return r_sub(r_div(r_add((double)i, 0.5), n), 0.5);
+}
+
+/* barycentric weights at screen position (px, py); false when outside (render.c:94-115) */
+__device__ __forceinline__ bool pixel_weights(const Tri2D &t, const double px, const double py, double w[3]) {
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const V3 &a = t.q[(m + 1) % 3];
+    /* edge_function(a, b, p), render.c:38-46 */
+    w[m] = r_mul(t.area_inv, r_sub(r_mul(r_sub(px, a.x), t.ey[m]), r_mul(r_sub(py, a.y), t.ex[m])));
+  }
   const double slack = -1.e-8;
   return !(w[0] < slack || w[1] < slack || w[2] < slack);
 }
@@ -237,4 +263,32 @@ __device__ __forceinline__ bool pixel_weights(const Cam &c, const Tri2D &t, cons
 /* harmonic depth, render.c:120-124 */
 __device__ __forceinline__ double pixel_depth(const Tri2D &t, const double w[3]) {
   return r_div(1., r_add(r_add(r_div(w[0], t.q[0].z), r_div(w[1], t.q[1].z)), r_div(w[2], t.q[2].z)));
+}
+
+/* 128-bit compare-and-swap on a z-buffer entry (ATOMG.E.CAS.128) */
+__device__ __forceinline__ Pixel cas_pixel(Pixel *addr, const Pixel expect, const Pixel desired) {
+  Pixel old;
+  asm volatile(
+      "{\n\t.reg .b128 c, n, d;\n\t"
+      "mov.b128 c, {%2, %3};\n\t"
+      "mov.b128 n, {%4, %5};\n\t"
+      "atom.global.cas.b128 d, [%6], c, n;\n\t"
+      "mov.b128 {%0, %1}, d;\n\t}"
+      : "=l"(old.depth), "=l"(old.key)
+      : "l"(expect.depth), "l"(expect.key), "l"(desired.depth), "l"(desired.key), "l"(addr)
+      : "memory");
+  return old;
+}
+
+/* canvas[pix] = lexicographic max(canvas[pix], (o, key)): the reference's
+   sequential "if (dist < stored) skip; else overwrite" (render.c:125-132)
+   made independent of the order in which fragments arrive */
+__device__ __forceinline__ void submit_fragment(Pixel *slot, const unsigned long long o, const unsigned long long key) {
+  const ulonglong2 seen = __ldcg(reinterpret_cast<const ulonglong2 *>(slot));   /* a hint (L2); the CAS decides */
+  Pixel cur{seen.x, seen.y};
+  while (o > cur.depth || (o == cur.depth && key > cur.key)) {
+    const Pixel prev = cas_pixel(slot, cur, Pixel{o, key});
+    if (prev.depth == cur.depth && prev.key == cur.key) break;
+    cur = prev;
+  }
 }

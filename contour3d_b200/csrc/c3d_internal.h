@@ -46,33 +46,61 @@ struct LineDev {
   unsigned char color[3];
 };
 
-/* 64-bit winner key: object index + 1 in the top 16 bits, primitive below.
-   contours: primitive = cube * 16 + triangle; lines: primitive = segment.
+/* z-buffer entry: order-preserving integer image of the fp64 depth + winner key.
+   One 128-bit compare-and-swap keeps the pair consistent, so the raster needs a
+   single pass: the lexicographic maximum of (depth, key) is exactly "nearest
+   wins, later in drawing order wins ties" (render.c:125-132). */
+struct __align__(16) Pixel { unsigned long long depth, key; };
+
+/* 64-bit winner key: object index + 1 in the top 12 bits, primitive below.
+   contours: primitive = k:16 | j:16 | i:16 | triangle:4 (cube indices on the
+   extended local array); lines: primitive = segment.
    Larger key = later in the reference's drawing order (contour, k, j, i, t;
    then lines), which is what wins a depth tie (render.c:125-132). */
-#define C3D_KEY_OBJ_SHIFT 48
+#define C3D_KEY_OBJ_SHIFT 52
 #define C3D_KEY_PRIM_MASK ((1ull << C3D_KEY_OBJ_SHIFT) - 1ull)
+#define C3D_MAX_AXIS 65535ll      /* cubes per direction that fit the 16-bit fields */
+
+/* active-cube list entry: code:8 | i:16 | j:16 | k:16 | object:4 */
+#define C3D_ENTRY(obj, i, j, k, code) \
+  (((unsigned long long)(obj) << 56) | ((unsigned long long)(k) << 40) | ((unsigned long long)(j) << 24) | ((unsigned long long)(i) << 8) | (unsigned long long)(code))
+#define C3D_ENTRY_CODE(e) ((unsigned int)((e) & 255ull))
+#define C3D_ENTRY_I(e) ((long long)(((e) >> 8) & 65535ull))
+#define C3D_ENTRY_J(e) ((long long)(((e) >> 24) & 65535ull))
+#define C3D_ENTRY_K(e) ((long long)(((e) >> 40) & 65535ull))
+#define C3D_ENTRY_OBJ(e) ((unsigned int)((e) >> 56) & 15u)
+
+#define C3D_MAX_OBJECTS 16
 
 struct SweepRange { long long lo[3], hi[3]; }; /* inclusive cube ranges to emit */
+
+/* everything the raster / shading kernels need, passed by value (constant bank) */
+struct FrameParams {
+  Cam cam;
+  DevTables tab;
+  const double *px, *py;     /* pixel-centre coordinates, render.c:94-98, tabulated once per screen size */
+  unsigned int ncontours;
+  FieldView view[C3D_MAX_OBJECTS];
+};
 
 #if defined(__cplusplus)
 extern "C" {
 #endif
 
 /* launchers (c3d_kernels.cu); all asynchronous on `s`, return cudaError_t as int */
-int c3d_k_clear(unsigned long long *depth, unsigned long long *key, size_t npix, cudaStream_t s);
-int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned long long *list, unsigned long long *count,
+int c3d_k_clear(Pixel *canvas, size_t npix, cudaStream_t s);
+int c3d_k_pixel_tables(double *px, double *py, long long w, long long h, cudaStream_t s);
+int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int obj, unsigned long long *list, unsigned long long *count,
                 unsigned long long capacity, int sm_count, cudaStream_t s);
-int c3d_k_raster(int pass, const FieldView *f, const Cam *c, const DevTables *t, const unsigned long long *list,
-                 const unsigned long long *count, unsigned long long capacity, unsigned long long obj,
-                 unsigned long long *depth, unsigned long long *key, int sm_count, cudaStream_t s);
-int c3d_k_lines(int pass, const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines, unsigned long long first_obj,
-                unsigned long long *depth, unsigned long long *key, cudaStream_t s);
-int c3d_k_shade(const Cam *c, const DevTables *t, const FieldView *contours_dev, size_t ncontours, const LineDev *lines_dev,
-                const unsigned long long *depth_local, const unsigned long long *depth_global, const unsigned long long *key,
+int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const unsigned long long *count, unsigned long long capacity,
+                 Pixel *canvas, int sm_count, cudaStream_t s);
+int c3d_k_lines(const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines, unsigned long long first_obj,
+                Pixel *canvas, cudaStream_t s);
+int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t npix, cudaStream_t s);
+int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
                 unsigned int *rgba, size_t npix, cudaStream_t s);
 int c3d_k_pack(const unsigned int *rgba, const unsigned char bg[3], long long w, long long h, unsigned char *out, cudaStream_t s);
-int c3d_k_depth_to_double(const unsigned long long *depth, double *out, size_t npix, cudaStream_t s);
+int c3d_k_canvas_split(const Pixel *canvas, double *depth, unsigned long long *key, size_t npix, cudaStream_t s);
 int c3d_k_case_codes(const FieldView *f, const DevTables *t, unsigned int *codes, unsigned char *counts, cudaStream_t s);
 int c3d_k_emit(const FieldView *f, const DevTables *t, const unsigned long long *list, unsigned long long nlist,
                unsigned long long *cursor, unsigned long long capacity, void *records, cudaStream_t s);

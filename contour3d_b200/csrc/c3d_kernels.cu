@@ -19,19 +19,32 @@
 
 /* ------------------------------------------------------------------ clear */
 
-__global__ void k_clear(unsigned long long *depth, unsigned long long *key, const size_t npix) {
+__global__ void k_clear(Pixel *__restrict__ canvas, const size_t npix) {
   /* every pixel starts at depth -DBL_MAX with no winner (src/contour3d/main.c:95-103) */
-  const unsigned long long empty = ord_of(-DBL_MAX);
+  const ulonglong2 empty = make_ulonglong2(ord_of(-DBL_MAX), 0ull);
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
-    depth[p] = empty;
-    key[p] = 0ull;
+    reinterpret_cast<ulonglong2 *>(canvas)[p] = empty;
   }
 }
 
-extern "C" int c3d_k_clear(unsigned long long *depth, unsigned long long *key, size_t npix, cudaStream_t s) {
+extern "C" int c3d_k_clear(Pixel *canvas, size_t npix, cudaStream_t s) {
   const int threads = 256;
   const int blocks = (int)((npix + threads - 1) / threads < 148 * 16 ? (npix + threads - 1) / threads : 148 * 16);
-  k_clear<<<blocks > 0 ? blocks : 1, threads, 0, s>>>(depth, key, npix);
+  k_clear<<<blocks > 0 ? blocks : 1, threads, 0, s>>>(canvas, npix);
+  return (int)cudaGetLastError();
+}
+
+/* pixel-centre coordinates of every column and row (render.c:94-98), once per screen size */
+__global__ void k_pixel_tables(double *__restrict__ px, double *__restrict__ py, const long long w, const long long h) {
+  const double W = (double)w, H = (double)h;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < w + h; q += (long long)gridDim.x * blockDim.x) {
+    if (q < w) px[q] = pixel_centre(q, W);
+    else py[q - w] = pixel_centre(q - w, H);
+  }
+}
+
+extern "C" int c3d_k_pixel_tables(double *px, double *py, long long w, long long h, cudaStream_t s) {
+  k_pixel_tables<<<64, 256, 0, s>>>(px, py, w, h);
   return (int)cudaGetLastError();
 }
 
@@ -43,7 +56,7 @@ struct SweepParams {
   float thr_ge;
   double thr;
   long long ilo, ihi, jlo, jhi, klo, khi;   /* inclusive cube ranges to emit */
-  long long cx, cy;                         /* cube-grid extents for the linear cube index */
+  unsigned int obj;                         /* contour object the entries are tagged with */
   int nxseg, nytile, nzchunk, zc;
   unsigned long long ntiles;
   unsigned long long *list, *count, capacity;
@@ -198,8 +211,7 @@ __global__ void __launch_bounds__(256) k_sweep(const SweepParams p) {
           const unsigned int l0 = (unsigned int)(lower >> (5 * r)) & 31u, l1 = (unsigned int)(lower >> (5 * r + 5)) & 31u;
           const unsigned int u0 = (unsigned int)(upper >> (5 * r)) & 31u, u1 = (unsigned int)(upper >> (5 * r + 5)) & 31u;
           const unsigned int code = ((l0 >> c) & 3u) | (((l1 >> c) & 3u) << 2) | (((u0 >> c) & 3u) << 4) | (((u1 >> c) & 3u) << 6);
-          const unsigned long long cube = (unsigned long long)((k * p.cy + (j0 + r)) * p.cx + (x0 + c));
-          if (at < p.capacity) p.list[at] = (cube << 8) | code;
+          if (at < p.capacity) p.list[at] = C3D_ENTRY(p.obj, x0 + c, j0 + r, k, code);
           at++;
         }
       }
@@ -208,7 +220,7 @@ __global__ void __launch_bounds__(256) k_sweep(const SweepParams p) {
   }
 }
 
-extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned long long *list, unsigned long long *count,
+extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int obj, unsigned long long *list, unsigned long long *count,
                            unsigned long long capacity, int sm_count, cudaStream_t s) {
   SweepParams p;
   p.data = f->data;
@@ -218,7 +230,7 @@ extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned lon
   p.ilo = r->lo[0]; p.ihi = r->hi[0];
   p.jlo = r->lo[1]; p.jhi = r->hi[1];
   p.klo = r->lo[2]; p.khi = r->hi[2];
-  p.cx = f->n[0] - 1; p.cy = f->n[1] - 1;
+  p.obj = obj;
   p.list = list; p.count = count; p.capacity = capacity;
   if (p.ihi < p.ilo || p.jhi < p.jlo || p.khi < p.klo) return 0;
   const int ty = 4 == f->elem_bytes ? 8 : 4;
@@ -252,74 +264,104 @@ extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned lon
 /* ----------------------------------------------------------------- raster */
 
 /*
- * One thread per active cube (grid-stride over the compact list): rebuild the
- * cube's triangles from the field (positions are never stored), project,
- * walk the +-1 pixel bounding box (render.c:81-89).
- *   PASS 1: atomicMax of the order-preserving 64-bit image of the fp64 depth.
- *   PASS 2: pixels where this triangle's depth EQUALS the final depth take
- *           atomicMax of its key -> "later in drawing order wins ties"
- *           (render.c:125-132) without depending on atomic ordering.
+ * One pass over the frame's active-cube list (all contour objects mixed).
+ *
+ * Load balance: a warp takes 32 cubes, and spreads their 1..12 triangles over
+ * its lanes (prefix sum + one REDUX per round), so every lane rasterises ONE
+ * triangle at a time whatever the case mix.  A triangle is rebuilt from the
+ * field (positions are never stored), projected, and its +-1 pixel bounding
+ * box (render.c:81-89) is walked in 8x8 pixel tiles in two phases: phase A
+ * evaluates only the three edge functions and collects the covered pixels in
+ * a 64-bit mask, phase B computes depth and submits the few that are covered.
+ * That keeps the divergent depth/atomic path off the common "outside" case.
+ *
+ * Z-buffer: one 128-bit CAS per surviving fragment on (ord(depth), key); see
+ * submit_fragment().
  */
-template <int PASS>
-__global__ void __launch_bounds__(128) k_raster(const FieldView f, const Cam cam, const DevTables tab,
-                                                const unsigned long long *__restrict__ list,
-                                                const unsigned long long *__restrict__ count, const unsigned long long capacity,
-                                                const unsigned long long obj, unsigned long long *__restrict__ depth,
-                                                unsigned long long *__restrict__ key) {
-  unsigned long long n = *count;
-  if (n > capacity) n = capacity;
-  const long long cx = f.n[0] - 1, cy = f.n[1] - 1;
-  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-       idx += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned long long entry = __ldg(list + idx);
-    const unsigned int code = (unsigned int)(entry & 255ull);
-    const unsigned long long cube = entry >> 8;
-    const long long i = (long long)(cube % (unsigned long long)cx);
-    const long long j = (long long)((cube / (unsigned long long)cx) % (unsigned long long)cy);
-    const long long k = (long long)(cube / ((unsigned long long)cx * (unsigned long long)cy));
-    Cube c;
-    load_cube(f, i, j, k, c);
-    const unsigned int ntri = __ldg(tab.count + code);
-    for (unsigned int s = 0; s < ntri; s++) {
-      V3 v[3];
-      triangle_vertices(c, f.thr, __ldg(tab.pairs + code * C3D_MAX_TRIS + s), v);
-      Tri2D t;
-      if (!setup_triangle(cam, v, t)) continue;
-      const unsigned long long mykey = ((obj + 1ull) << C3D_KEY_OBJ_SHIFT) | (cube * 16ull + s);
-      for (long long pj = t.jmin; pj <= t.jmax; pj++) {
-        for (long long pi = t.imin; pi <= t.imax; pi++) {
+__device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsigned long long entry, const unsigned int s,
+                                                Pixel *__restrict__ canvas) {
+  const unsigned int obj = C3D_ENTRY_OBJ(entry), code = C3D_ENTRY_CODE(entry);
+  const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
+  const FieldView &f = p.view[obj];
+  const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
+  V3 v[3];
+#pragma unroll
+  for (int m = 0; m < 3; m++) v[m] = cut_edge_global(f, i, j, k, f.thr, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+  Tri2D t;
+  if (!setup_triangle(p.cam, v, t)) return;
+  const unsigned long long mykey = ((unsigned long long)(obj + 1u) << C3D_KEY_OBJ_SHIFT)
+                                 | ((unsigned long long)k << 36) | ((unsigned long long)j << 20) | ((unsigned long long)i << 4) | s;
+  for (long long j0 = t.jmin; j0 <= t.jmax; j0 += 8) {
+    const int nj = (int)(t.jmax - j0 < 7 ? t.jmax - j0 : 7);
+    for (long long i0 = t.imin; i0 <= t.imax; i0 += 8) {
+      const int ni = (int)(t.imax - i0 < 7 ? t.imax - i0 : 7);
+      unsigned long long covered = 0ull;
+      for (int dj = 0; dj <= nj; dj++) {
+        const double py = __ldg(p.py + j0 + dj);
+        for (int di = 0; di <= ni; di++) {
           double w[3];
-          if (!pixel_weights(cam, t, pi, pj, w)) continue;
-          const unsigned long long o = ord_of(pixel_depth(t, w));
-          const long long pix = pj * cam.w + pi;
-          if (1 == PASS) {
-            if (o >= depth[pix]) atomicMax(depth + pix, o);
-          } else {
-            if (o == depth[pix]) atomicMax(key + pix, mykey);
-          }
+          if (pixel_weights(t, __ldg(p.px + i0 + di), py, w)) covered |= 1ull << (dj * 8 + di);
         }
+      }
+      while (covered) {
+        const int bit = __ffsll((long long)covered) - 1;
+        covered &= covered - 1ull;
+        const long long pi = i0 + (bit & 7), pj = j0 + (bit >> 3);
+        double w[3];
+        pixel_weights(t, __ldg(p.px + pi), __ldg(p.py + pj), w);
+        submit_fragment(canvas + pj * p.cam.w + pi, ord_of(pixel_depth(t, w)), mykey);
       }
     }
   }
 }
 
-extern "C" int c3d_k_raster(int pass, const FieldView *f, const Cam *c, const DevTables *t, const unsigned long long *list,
-                            const unsigned long long *count, unsigned long long capacity, unsigned long long obj,
-                            unsigned long long *depth, unsigned long long *key, int sm_count, cudaStream_t s) {
-  const int threads = 128;
-  const int blocks = sm_count * 8;
-  if (1 == pass) k_raster<1><<<blocks, threads, 0, s>>>(*f, *c, *t, list, count, capacity, obj, depth, key);
-  else k_raster<2><<<blocks, threads, 0, s>>>(*f, *c, *t, list, count, capacity, obj, depth, key);
+__global__ void __launch_bounds__(128) k_raster(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ list,
+                                                const unsigned long long *__restrict__ count, const unsigned long long capacity,
+                                                Pixel *__restrict__ canvas) {
+  unsigned long long n = *count;
+  if (n > capacity) n = capacity;
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned long long warp = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+  for (unsigned long long base = warp * 32ull; base < n; base += nwarps * 32ull) {
+    unsigned long long entry = 0ull;
+    unsigned int ntri = 0u;
+    if (base + lane < n) {
+      entry = __ldg(list + base + lane);
+      ntri = __ldg(p.tab.count + C3D_ENTRY_CODE(entry));
+    }
+    unsigned int incl = ntri;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned int up = __shfl_up_sync(C3D_FULL_MASK, incl, d);
+      if (lane >= (unsigned int)d) incl += up;
+    }
+    const unsigned int total = __shfl_sync(C3D_FULL_MASK, incl, 31);
+    const unsigned int excl = incl - ntri;
+    for (unsigned int t0 = 0; t0 < total; t0 += 32u) {
+      /* source cube of triangle t0 + lane: the last cube whose first triangle is <= it */
+      const bool starts_here = ntri > 0u && excl >= t0 && excl < t0 + 32u;
+      const unsigned int starts = __reduce_or_sync(C3D_FULL_MASK, starts_here ? 1u << (excl - t0) : 0u);
+      const unsigned int before = __popc(__ballot_sync(C3D_FULL_MASK, ntri > 0u && excl < t0));
+      const unsigned int src = (before + __popc(starts & (0xffffffffu >> (31u - lane))) - 1u) & 31u;
+      const unsigned long long e = __shfl_sync(C3D_FULL_MASK, entry, src);
+      const unsigned int first = __shfl_sync(C3D_FULL_MASK, excl, src);
+      if (t0 + lane < total) raster_triangle(p, e, t0 + lane - first, canvas);
+    }
+  }
+}
+
+extern "C" int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const unsigned long long *count, unsigned long long capacity,
+                            Pixel *canvas, int sm_count, cudaStream_t s) {
+  k_raster<<<sm_count * 8, 128, 0, s>>>(*p, list, count, capacity, canvas);
   return (int)cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------ lines */
 
 /* one CTA per segment; draw_line_between_two_points, line.c:26-118 */
-template <int PASS>
 __global__ void __launch_bounds__(128) k_lines(const Cam cam, const LineDev *__restrict__ lines, const unsigned int nlines,
-                                               const unsigned long long first_obj, unsigned long long *__restrict__ depth,
-                                               unsigned long long *__restrict__ key) {
+                                               const unsigned long long first_obj, Pixel *__restrict__ canvas) {
   const unsigned long long seg_global = blockIdx.x;
   unsigned int l = 0;
   while (l + 1 < nlines && seg_global >= lines[l + 1].first_segment) l++;
@@ -355,27 +397,32 @@ __global__ void __launch_bounds__(128) k_lines(const Cam cam, const LineDev *__r
     if (ln.half_width_sq < dist2) continue;
     const double param = r_div(r_mul(-1., r_add(r_mul(dx, r_sub(p0.x, fi)), r_mul(dy, r_sub(p0.y, fj)))), len2);
     const double dist = r_div(1., r_add(r_div(param, p1.z), r_div(r_sub(1., param), p0.z)));
-    const unsigned long long o = ord_of(dist);
-    const long long pix = j * cam.w + i;
-    if (1 == PASS) {
-      if (o >= depth[pix]) atomicMax(depth + pix, o);
-    } else {
-      if (o == depth[pix]) atomicMax(key + pix, mykey);
-    }
+    submit_fragment(canvas + j * cam.w + i, ord_of(dist), mykey);
   }
 }
 
-extern "C" int c3d_k_lines(int pass, const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines,
-                           unsigned long long first_obj, unsigned long long *depth, unsigned long long *key, cudaStream_t s) {
+extern "C" int c3d_k_lines(const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines, unsigned long long first_obj,
+                           Pixel *canvas, cudaStream_t s) {
   if (0 == nlines) return 0;
   const unsigned long long total = lines_host[nlines - 1].first_segment + lines_host[nlines - 1].nsegments;
   if (0 == total) return 0;
-  if (1 == pass) k_lines<1><<<(unsigned int)total, 128, 0, s>>>(*c, lines_dev, (unsigned int)nlines, first_obj, depth, key);
-  else k_lines<2><<<(unsigned int)total, 128, 0, s>>>(*c, lines_dev, (unsigned int)nlines, first_obj, depth, key);
+  k_lines<<<(unsigned int)total, 128, 0, s>>>(*c, lines_dev, (unsigned int)nlines, first_obj, canvas);
   return (int)cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------ shade */
+
+/* depth plane of the canvas, contiguous, for the cross-rank ncclMax (output.c:10-30) */
+__global__ void k_depth_extract(const Pixel *__restrict__ canvas, unsigned long long *__restrict__ depth, const size_t npix) {
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+    depth[p] = canvas[p].depth;
+  }
+}
+
+extern "C" int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t npix, cudaStream_t s) {
+  k_depth_extract<<<148 * 8, 256, 0, s>>>(canvas, depth, npix);
+  return (int)cudaGetLastError();
+}
 
 /*
  * Deferred shading: one thread per pixel.  Only the winning triangle of a
@@ -385,48 +432,42 @@ extern "C" int c3d_k_lines(int pass, const Cam *c, const LineDev *lines_dev, con
  * Output: 0xFF000000 | b << 16 | g << 8 | r, or 0 where this rank has nothing
  * to contribute (background, or not the global winner).
  */
-__global__ void __launch_bounds__(128) k_shade(const Cam cam, const DevTables tab, const FieldView *__restrict__ contours,
-                                               const unsigned int ncontours, const LineDev *__restrict__ lines,
-                                               const unsigned long long *__restrict__ depth_local,
-                                               const unsigned long long *__restrict__ depth_global,
-                                               const unsigned long long *__restrict__ key, unsigned int *__restrict__ rgba,
-                                               const size_t npix) {
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FrameParams p, const LineDev *__restrict__ lines,
+                                               const Pixel *__restrict__ canvas, const unsigned long long *__restrict__ depth_global,
+                                               unsigned int *__restrict__ rgba, const size_t npix) {
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
-  const unsigned long long mykey = key[pix];
+  const ulonglong2 mine = *reinterpret_cast<const ulonglong2 *>(canvas + pix);
+  const unsigned long long mykey = mine.y;
   unsigned int out = 0u;
-  if (0ull != mykey && (nullptr == depth_global || depth_local[pix] == depth_global[pix])) {
+  if (0ull != mykey && (nullptr == depth_global || mine.x == depth_global[pix])) {
     const unsigned int obj = (unsigned int)(mykey >> C3D_KEY_OBJ_SHIFT) - 1u;
     const unsigned long long prim = mykey & C3D_KEY_PRIM_MASK;
-    if (obj >= ncontours) {
-      const LineDev &ln = lines[obj - ncontours];
+    if (obj >= p.ncontours) {
+      const LineDev &ln = lines[obj - p.ncontours];
       out = 0xFF000000u | ((unsigned int)ln.color[2] << 16) | ((unsigned int)ln.color[1] << 8) | ln.color[0];
     } else {
-      const FieldView f = contours[obj];
-      const unsigned long long cube = prim >> 4;
+      const FieldView &f = p.view[obj];
       const unsigned int s = (unsigned int)(prim & 15ull);
-      const long long cx = f.n[0] - 1, cy = f.n[1] - 1;
-      const long long i = (long long)(cube % (unsigned long long)cx);
-      const long long j = (long long)((cube / (unsigned long long)cx) % (unsigned long long)cy);
-      const long long k = (long long)(cube / ((unsigned long long)cx * (unsigned long long)cy));
+      const long long i = (long long)((prim >> 4) & 65535ull), j = (long long)((prim >> 20) & 65535ull), k = (long long)((prim >> 36) & 65535ull);
       Cube c;
       load_cube(f, i, j, k, c);
       const unsigned int code = corner_code(c, f.thr);
       V3 v[3];
-      triangle_vertices(c, f.thr, __ldg(tab.pairs + code * C3D_MAX_TRIS + s), v);
+      triangle_vertices(c, f.thr, __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s), v);
       Tri2D t;
       double w[3] = {0., 0., 0.};
-      if (setup_triangle(cam, v, t)) {
-        pixel_weights(cam, t, (long long)(pix % (size_t)cam.w), (long long)(pix / (size_t)cam.w), w);
+      if (setup_triangle(p.cam, v, t)) {
+        pixel_weights(t, __ldg(p.px + (long long)(pix % (size_t)p.cam.w)), __ldg(p.py + (long long)(pix / (size_t)p.cam.w)), w);
       }
-      const unsigned int edges = __ldg(tab.edges + code * C3D_MAX_TRIS + s);
+      const unsigned int edges = __ldg(p.tab.edges + code * C3D_MAX_TRIS + s);
       V3 vn[3];
       for (int m = 0; m < 3; m++) {
-        vn[m] = vertex_normal(f, tab, i, j, k, (edges >> (5 * m)) & 31u);
+        vn[m] = vertex_normal(f, p.tab, i, j, k, (edges >> (5 * m)) & 31u);
       }
       /* w0*n0 + (w1*n1 + w2*n2), render.c:137-146 */
       const V3 nrm = v_unit(v_add(v_mul(w[0], vn[0]), v_add(v_mul(w[1], vn[1]), v_mul(w[2], vn[2]))));
-      const double factor = fmax(0.15, fabs(v_dot(nrm, v_of(cam.light))));
+      const double factor = fmax(0.15, fabs(v_dot(nrm, v_of(p.cam.light))));
       const unsigned int r = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[0])) & 255u;
       const unsigned int g = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[1])) & 255u;
       const unsigned int b = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[2])) & 255u;
@@ -436,12 +477,11 @@ __global__ void __launch_bounds__(128) k_shade(const Cam cam, const DevTables ta
   rgba[pix] = out;
 }
 
-extern "C" int c3d_k_shade(const Cam *c, const DevTables *t, const FieldView *contours_dev, size_t ncontours, const LineDev *lines_dev,
-                           const unsigned long long *depth_local, const unsigned long long *depth_global,
-                           const unsigned long long *key, unsigned int *rgba, size_t npix, cudaStream_t s) {
+extern "C" int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
+                           unsigned int *rgba, size_t npix, cudaStream_t s) {
   const int threads = 128;
   const unsigned int blocks = (unsigned int)((npix + threads - 1) / threads);
-  k_shade<<<blocks, threads, 0, s>>>(*c, *t, contours_dev, (unsigned int)ncontours, lines_dev, depth_local, depth_global, key, rgba, npix);
+  k_shade<<<blocks, threads, 0, s>>>(*p, lines_dev, canvas, depth_global, rgba, npix);
   return (int)cudaGetLastError();
 }
 
@@ -470,14 +510,15 @@ extern "C" int c3d_k_pack(const unsigned int *rgba, const unsigned char bg[3], l
   return (int)cudaGetLastError();
 }
 
-__global__ void k_depth_to_double(const unsigned long long *__restrict__ depth, double *__restrict__ out, const size_t npix) {
+__global__ void k_canvas_split(const Pixel *__restrict__ canvas, double *__restrict__ depth, unsigned long long *__restrict__ key, const size_t npix) {
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
-    out[p] = ord_to_double(depth[p]);
+    if (depth) depth[p] = ord_to_double(canvas[p].depth);
+    if (key) key[p] = canvas[p].key;
   }
 }
 
-extern "C" int c3d_k_depth_to_double(const unsigned long long *depth, double *out, size_t npix, cudaStream_t s) {
-  k_depth_to_double<<<148 * 8, 256, 0, s>>>(depth, out, npix);
+extern "C" int c3d_k_canvas_split(const Pixel *canvas, double *depth, unsigned long long *key, size_t npix, cudaStream_t s) {
+  k_canvas_split<<<148 * 8, 256, 0, s>>>(canvas, depth, key, npix);
   return (int)cudaGetLastError();
 }
 
@@ -519,11 +560,9 @@ __global__ void __launch_bounds__(128) k_emit(const FieldView f, const DevTables
   for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nlist;
        idx += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long entry = list[idx];
-    const unsigned int code = (unsigned int)(entry & 255ull);
-    const unsigned long long cube = entry >> 8;
-    const long long i = (long long)(cube % (unsigned long long)cx);
-    const long long j = (long long)((cube / (unsigned long long)cx) % (unsigned long long)cy);
-    const long long k = (long long)(cube / ((unsigned long long)cx * (unsigned long long)cy));
+    const unsigned int code = C3D_ENTRY_CODE(entry);
+    const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
+    const unsigned long long cube = (unsigned long long)((k * cy + j) * cx + i);
     const unsigned int ntri = __ldg(tab.count + code);
     const unsigned long long at = atomicAdd(cursor, (unsigned long long)ntri);
     /* the reference smooths cubes 1..m-3 of every direction only (normal.c:54-55, contour/main.c:71,92-93) */

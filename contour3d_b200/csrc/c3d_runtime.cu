@@ -23,7 +23,6 @@
 #include "contour3d_b200.h"
 #include "c3d_internal.h"
 
-#define C3D_MAX_OBJECTS 16
 #define C3D_STR__(x) #x
 #define C3D_STR_(x) C3D_STR__(x)
 
@@ -113,11 +112,14 @@ struct c3d_context {
   DevTables tab;
   /* canvases */
   size_t npix_cap;
-  unsigned long long *depth, *key, *depth_global;
+  Pixel *canvas;                                   /* (depth, winner key) per pixel */
+  unsigned long long *depth_local, *depth_global;  /* multi-rank only: contiguous depth planes for ncclMax */
+  double *pixel_xy;                                /* pixel-centre tables: width + height doubles */
+  size_t table_w, table_h;
   unsigned int *rgba;
   unsigned char *ppm_dev, *ppm_host;
   size_t width, height;
-  /* active-cube lists: one region per contour object */
+  /* active-cube list of the frame (all contour objects, tagged) */
   unsigned long long *list;
   size_t list_cap;
   unsigned long long *counts_dev, *counts_host;
@@ -204,7 +206,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
   cudaFree(ctx->table_mem);
-  cudaFree(ctx->depth); cudaFree(ctx->key); cudaFree(ctx->depth_global); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
+  cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->pixel_xy); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
   if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
   cudaFree(ctx->list); cudaFree(ctx->counts_dev);
   if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
@@ -280,7 +282,11 @@ extern "C" int c3d_field_create(c3d_context_t *ctx, const c3d_decomp_t *decomp, 
     /* two extra points towards every neighbour, none at the domain boundary (contour/extend.c:216-252) */
     const size_t lo = decomp->myrank[d] > 0 ? 2 : 0;
     const size_t hi = decomp->myrank[d] < decomp->nprocs[d] - 1 ? 2 : 0;
-    if ((lo || hi) && f->mysizes[d] < 2) { free(f); return c3d_error("local size %zu in direction %d is too small for a 2-point halo", f->mysizes[d], d); }
+    if ((lo || hi) && f->mysizes[d] < 2) {
+      const size_t have = f->mysizes[d];
+      free(f);
+      return c3d_error("local size %zu in direction %d is too small for a 2-point halo", have, d);
+    }
     f->lo[d] = lo;
     f->ext[d] = f->mysizes[d] + lo + hi;
     f->ext_off[d] = f->offsets[d] - lo;
@@ -479,17 +485,28 @@ static void rendered_range(const FieldView *v, const int rendered_only, SweepRan
 static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
   const size_t npix = w * h;
   if (npix > ctx->npix_cap) {
-    cudaFree(ctx->depth); cudaFree(ctx->key); cudaFree(ctx->depth_global); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
+    cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
     if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
-    ctx->depth = ctx->key = ctx->depth_global = NULL; ctx->rgba = NULL; ctx->ppm_dev = NULL; ctx->ppm_host = NULL;
+    ctx->canvas = NULL; ctx->depth_local = ctx->depth_global = NULL; ctx->rgba = NULL; ctx->ppm_dev = NULL; ctx->ppm_host = NULL;
     ctx->npix_cap = 0;
-    CUDA_OK(cudaMalloc(&ctx->depth, npix * 8));
-    CUDA_OK(cudaMalloc(&ctx->key, npix * 8));
-    if (ctx->size > 1) CUDA_OK(cudaMalloc(&ctx->depth_global, npix * 8));
+    CUDA_OK(cudaMalloc(&ctx->canvas, npix * sizeof(Pixel)));
+    if (ctx->size > 1) {
+      CUDA_OK(cudaMalloc(&ctx->depth_local, npix * 8));
+      CUDA_OK(cudaMalloc(&ctx->depth_global, npix * 8));
+    }
     CUDA_OK(cudaMalloc(&ctx->rgba, npix * 4));
     CUDA_OK(cudaMalloc(&ctx->ppm_dev, npix * 3));
     CUDA_OK(cudaMallocHost(&ctx->ppm_host, npix * 3));
     ctx->npix_cap = npix;
+  }
+  if (w != ctx->table_w || h != ctx->table_h) {
+    cudaFree(ctx->pixel_xy);
+    ctx->pixel_xy = NULL;
+    ctx->table_w = ctx->table_h = 0;
+    CUDA_OK(cudaMalloc(&ctx->pixel_xy, (w + h) * sizeof(double)));
+    LAUNCH_OK(c3d_k_pixel_tables(ctx->pixel_xy, ctx->pixel_xy + w, (long long)w, (long long)h, ctx->stream));
+    ctx->table_w = w;
+    ctx->table_h = h;
   }
   ctx->width = w;
   ctx->height = h;
@@ -552,16 +569,25 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     if (0 != ensure_bytes((void **)&ctx->grids_dev, &cap, (grid_elems + 8) * sizeof(double))) return 1;
     ctx->grids_cap = cap / sizeof(double);
   }
-  FieldView views[C3D_MAX_OBJECTS];
+  FrameParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.cam = cam;
+  fp.tab = ctx->tab;
+  fp.px = ctx->pixel_xy;
+  fp.py = ctx->pixel_xy + scene->width;
+  fp.ncontours = (unsigned int)nc;
+  FieldView *views = fp.view;
   {
     double *slot = ctx->grids_dev;
     for (size_t n = 0; n < nc; n++) {
       const c3d_field *f = contours[n].field;
+      for (int d = 0; d < 3; d++) {
+        if ((long long)f->ext[d] - 1 > C3D_MAX_AXIS) return c3d_error("extended array too large in direction %d (%zu points)", d, f->ext[d]);
+      }
       if (0 != make_view(ctx, f, contours[n].grids, contours[n].threshold, contours[n].color, slot, &views[n])) return 1;
       slot += f->ext[0] + f->ext[1] + f->ext[2];
     }
   }
-  if (nc > 0) CUDA_OK(cudaMemcpyAsync(ctx->views_dev, views, nc * sizeof(FieldView), cudaMemcpyHostToDevice, s));
   std::vector<LineDev> hl(nl);
   {
     unsigned long long first = 0;
@@ -588,7 +614,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     }
     if (nl > 0) CUDA_OK(cudaMemcpyAsync(ctx->lines_dev, hl.data(), nl * sizeof(LineDev), cudaMemcpyHostToDevice, s));
   }
-  /* work lists: equal share of the list buffer per contour object */
+  /* work list of the frame: every contour object appends its active cubes */
   if (nc > 0 && 0 == ctx->list_cap) {
     size_t want = 0;
     for (size_t n = 0; n < nc; n++) {
@@ -599,47 +625,43 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     CUDA_OK(cudaMalloc(&ctx->list, want * 8));
     ctx->list_cap = want;
   }
-  const size_t share = nc > 0 ? ctx->list_cap / nc : 0;
   CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, (C3D_MAX_OBJECTS + 2) * sizeof(unsigned long long), s));
-  LAUNCH_OK(c3d_k_clear(ctx->depth, ctx->key, npix, s));
+  LAUNCH_OK(c3d_k_clear(ctx->canvas, npix, s));
   launches += 1;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_CLEAR], s));
-  /* 1. classification sweeps */
+  /* 1. classification sweeps: counts_dev[0] is the shared cursor, counts_dev[1 + n] the cursor after object n */
   for (size_t n = 0; n < nc; n++) {
     CUDA_OK(cudaEventRecord(ctx->ev_sweep[n], s));
     SweepRange r;
     rendered_range(&views[n], 1, &r);
-    LAUNCH_OK(c3d_k_sweep(&views[n], &r, ctx->list + n * share, ctx->counts_dev + n, share, ctx->sm_count, s));
+    LAUNCH_OK(c3d_k_sweep(&views[n], &r, (unsigned int)n, ctx->list, ctx->counts_dev, ctx->list_cap, ctx->sm_count, s));
+    CUDA_OK(cudaMemcpyAsync(ctx->counts_dev + 1 + n, ctx->counts_dev, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
     launches += 1;
   }
   CUDA_OK(cudaEventRecord(ctx->ev_sweep[nc], s));
   CUDA_OK(cudaEventRecord(ctx->ev[EV_SWEEP], s));
-  /* 2. depth pass: contours in order, then lines (src/contour3d/main.c:105-129) */
-  for (size_t n = 0; n < nc; n++) {
-    LAUNCH_OK(c3d_k_raster(1, &views[n], &cam, &ctx->tab, ctx->list + n * share, ctx->counts_dev + n, share, n, ctx->depth, ctx->key, ctx->sm_count, s));
+  /* 2. tessellate + rasterise every active cube, contours in one launch (src/contour3d/main.c:105-117) */
+  if (nc > 0) {
+    LAUNCH_OK(c3d_k_raster(&fp, ctx->list, ctx->counts_dev, ctx->list_cap, ctx->canvas, ctx->sm_count, s));
     launches += 1;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_RASTER], s));
-  LAUNCH_OK(c3d_k_lines(1, &cam, ctx->lines_dev, hl.data(), nl, nc, ctx->depth, ctx->key, s));
+  /* 3. lines: drawn after the contours in the reference (main.c:119-129); their keys are larger, so they win ties */
+  LAUNCH_OK(c3d_k_lines(&cam, ctx->lines_dev, hl.data(), nl, nc, ctx->canvas, s));
   if (nl > 0) launches += 1;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_LINES], s));
-  /* 3. winner pass: among the primitives that reach the final depth, the last in drawing order */
-  for (size_t n = 0; n < nc; n++) {
-    LAUNCH_OK(c3d_k_raster(2, &views[n], &cam, &ctx->tab, ctx->list + n * share, ctx->counts_dev + n, share, n, ctx->depth, ctx->key, ctx->sm_count, s));
-    launches += 1;
-  }
-  LAUNCH_OK(c3d_k_lines(2, &cam, ctx->lines_dev, hl.data(), nl, nc, ctx->depth, ctx->key, s));
-  if (nl > 0) launches += 1;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_RESOLVE], s));
   /* 4. nearest depth across ranks (replaces the depth half of MPI_Reduce, output.c:10-30,82) */
   const unsigned long long *depth_global = NULL;
   if (ctx->size > 1) {
-    NCCL_OK(g_nccl.AllReduce(ctx->depth, ctx->depth_global, npix, ncclUint64, ncclMax, ctx->comm, s));
+    LAUNCH_OK(c3d_k_depth_extract(ctx->canvas, ctx->depth_local, npix, s));
+    launches += 1;
+    NCCL_OK(g_nccl.AllReduce(ctx->depth_local, ctx->depth_global, npix, ncclUint64, ncclMax, ctx->comm, s));
     depth_global = ctx->depth_global;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
   /* 5. shade only what survived */
-  LAUNCH_OK(c3d_k_shade(&cam, &ctx->tab, ctx->views_dev, nc, ctx->lines_dev, ctx->depth, depth_global, ctx->key, ctx->rgba, npix, s));
+  LAUNCH_OK(c3d_k_shade(&fp, ctx->lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, s));
   launches += 1;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
   /* 6. colours to the writer (the colour half of the reference's reduce) */
@@ -658,16 +680,13 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   CUDA_OK(cudaEventRecord(ctx->ev[EV_DOWNLOAD], s));
   CUDA_OK(cudaStreamSynchronize(s));
   /* capacity policy: a list that overflowed is grown and the frame is redone */
-  size_t need = 0;
-  for (size_t n = 0; n < nc; n++) {
-    if (ctx->counts_host[n] > share) *overflow = true;
-    need = std::max<size_t>(need, (size_t)ctx->counts_host[n]);
-  }
-  if (*overflow) {
+  const size_t need = (size_t)ctx->counts_host[0];
+  if (need > ctx->list_cap) {
+    *overflow = true;
     cudaFree(ctx->list);
     ctx->list = NULL;
     ctx->list_cap = 0;
-    const size_t want = (need + need / 4 + 1024) * nc;
+    const size_t want = need + need / 4 + 1024;
     const cudaError_t err = cudaMalloc(&ctx->list, want * 8);
     if (cudaSuccess != err) return c3d_error("failed to grow the active-cube list to %zu entries: %s", want, cudaGetErrorString(err));
     ctx->list_cap = want;
@@ -692,7 +711,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   t->launches = launches;
   for (size_t n = 0; n < nc && n < 16; n++) {
     cudaEventElapsedTime(&t->sweep_each[n], ctx->ev_sweep[n], ctx->ev_sweep[n + 1]);
-    t->active_cubes[n] = ctx->counts_host[n];
+    t->active_cubes[n] = ctx->counts_host[1 + n] - (n > 0 ? ctx->counts_host[n] : 0ull);
     const c3d_field *f = contours[n].field;
     t->sweep_bytes[n] = (uint64_t)f->ext[0] * f->ext[1] * f->ext[2] * (uint64_t)f->elem_bytes;
   }
@@ -719,7 +738,7 @@ extern "C" int c3d_frame_render(c3d_context_t *ctx, const c3d_scene_t *scene, si
   if (nc > 0 && NULL == contours) return c3d_error("contour objects are missing");
   if (nl > 0 && NULL == lines) return c3d_error("line objects are missing");
   if (0 == scene->width || 0 == scene->height) return c3d_error("empty screen (%zu x %zu)", scene->width, scene->height);
-  if (nc + nl >= 65535) return c3d_error("too many objects (%zu)", nc + nl);
+  if (nc + nl >= 4095) return c3d_error("too many objects (%zu)", nc + nl);
   for (size_t n = 0; n < nc; n++) {
     if (NULL == contours[n].field) return c3d_error("contour object %zu has no field", n);
   }
@@ -744,18 +763,16 @@ extern "C" int c3d_frame_canvas(c3d_context_t *ctx, double *host_depth, uint64_t
   const size_t npix = ctx->width * ctx->height;
   if (0 == npix) return c3d_error("no frame has been rendered yet");
   CUDA_OK(cudaSetDevice(ctx->device));
-  if (host_depth) {
-    double *tmp = NULL;
-    CUDA_OK(cudaMalloc(&tmp, npix * sizeof(double)));
-    LAUNCH_OK(c3d_k_depth_to_double(ctx->depth, tmp, npix, ctx->stream));
-    CUDA_OK(cudaMemcpyAsync(host_depth, tmp, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    CUDA_OK(cudaFree(tmp));
-  }
-  if (host_key) {
-    CUDA_OK(cudaMemcpyAsync(host_key, ctx->key, npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  }
+  double *tmp_depth = NULL;
+  unsigned long long *tmp_key = NULL;
+  if (host_depth) CUDA_OK(cudaMalloc(&tmp_depth, npix * sizeof(double)));
+  if (host_key) CUDA_OK(cudaMalloc(&tmp_key, npix * 8));
+  LAUNCH_OK(c3d_k_canvas_split(ctx->canvas, tmp_depth, tmp_key, npix, ctx->stream));
+  if (host_depth) CUDA_OK(cudaMemcpyAsync(host_depth, tmp_depth, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (host_key) CUDA_OK(cudaMemcpyAsync(host_key, tmp_key, npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(tmp_depth);
+  cudaFree(tmp_key);
   return 0;
 }
 
@@ -805,7 +822,7 @@ static int sweep_to_device(c3d_context *ctx, const FieldView *v, const int rende
   for (int attempt = 0; attempt < 3; attempt++) {
     CUDA_OK(cudaMalloc(list, cap * 8));
     CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, 8, ctx->stream));
-    LAUNCH_OK(c3d_k_sweep(v, &r, *list, ctx->counts_dev, cap, ctx->sm_count, ctx->stream));
+    LAUNCH_OK(c3d_k_sweep(v, &r, 0u, *list, ctx->counts_dev, cap, ctx->sm_count, ctx->stream));
     CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
     *count = ctx->counts_host[0];
@@ -830,6 +847,13 @@ extern "C" int c3d_sweep(c3d_context_t *ctx, const c3d_field_t *f, double thresh
   if (take > 0 && NULL != host_entries) {
     CUDA_OK(cudaMemcpyAsync(host_entries, list, take * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    /* device entries carry (i, j, k); the C-ABI documents the flat cube index */
+    const unsigned long long cx = (unsigned long long)(f->ext[0] - 1), cy = (unsigned long long)(f->ext[1] - 1);
+    for (size_t q = 0; q < take; q++) {
+      const unsigned long long e = host_entries[q];
+      const unsigned long long cube = ((unsigned long long)C3D_ENTRY_K(e) * cy + (unsigned long long)C3D_ENTRY_J(e)) * cx + (unsigned long long)C3D_ENTRY_I(e);
+      host_entries[q] = (cube << 8) | C3D_ENTRY_CODE(e);
+    }
   }
   cudaFree(list);
   return 0;
