@@ -227,7 +227,7 @@ def ours(args):
             launches += t["launches"]
             sweep_ms += t["sweep_each"]
             sweep_bytes += t["sweep_bytes"]
-            for k in ("halo", "clear", "sweep", "raster", "lines", "resolve", "reduce", "shade", "pack", "download", "total"):
+            for k in ("halo", "clear", "sweep", "expand", "raster", "lines", "resolve", "reduce", "shade", "pack", "download", "total"):
                 stage_sum[k] = stage_sum.get(k, 0.0) + t[k]
         end.record(stream)
         barrier()
@@ -253,7 +253,7 @@ def ours(args):
     tfile = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tfile):
         traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
-    roofline = {"kernel": "k_sweep<float,8,true>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"kernel": f"k_sweep_tiles<float,{t['sweep_thresholds'][0]},16> (one pass classifies {t['sweep_thresholds'][0]} iso-values)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": float(np.mean(sweep_bytes)), "ms_per_launch": sweep_avg_ms,
                 "share_of_step": stage_sum["sweep"] / stage_sum["total"]}
 

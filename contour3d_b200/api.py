@@ -64,23 +64,24 @@ class LineDesc(C.Structure):
 
 
 class Timings(C.Structure):
-    _fields_ = [
-        ("upload", C.c_float), ("halo", C.c_float), ("clear", C.c_float), ("sweep", C.c_float), ("raster", C.c_float),
-        ("lines", C.c_float), ("resolve", C.c_float), ("reduce", C.c_float), ("shade", C.c_float), ("pack", C.c_float),
-        ("download", C.c_float), ("total", C.c_float),
+    _STAGES = ("upload", "halo", "clear", "sweep", "expand", "raster", "lines", "resolve", "reduce", "shade", "pack", "download", "total")
+    _fields_ = [(k, C.c_float) for k in _STAGES] + [
         ("sweep_each", C.c_float * 16),
-        ("active_cubes", C.c_uint64 * 16),
         ("sweep_bytes", C.c_uint64 * 16),
+        ("sweep_thresholds", C.c_uint32 * 16),
+        ("active_cubes", C.c_uint64 * 16),
+        ("nsweeps", C.c_uint32),
         ("ncontours", C.c_uint32),
         ("launches", C.c_uint32),
     ]
 
     def as_dict(self):
-        n = int(self.ncontours)
-        d = {k: float(getattr(self, k)) for k in ("upload", "halo", "clear", "sweep", "raster", "lines", "resolve", "reduce", "shade", "pack", "download", "total")}
-        d["sweep_each"] = [float(self.sweep_each[i]) for i in range(n)]
+        n, m = int(self.ncontours), int(self.nsweeps)
+        d = {k: float(getattr(self, k)) for k in self._STAGES}
+        d["sweep_each"] = [float(self.sweep_each[i]) for i in range(m)]
+        d["sweep_bytes"] = [int(self.sweep_bytes[i]) for i in range(m)]
+        d["sweep_thresholds"] = [int(self.sweep_thresholds[i]) for i in range(m)]
         d["active_cubes"] = [int(self.active_cubes[i]) for i in range(n)]
-        d["sweep_bytes"] = [int(self.sweep_bytes[i]) for i in range(n)]
         d["launches"] = int(self.launches)
         return d
 

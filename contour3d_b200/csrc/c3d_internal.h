@@ -71,6 +71,7 @@ struct __align__(16) Pixel { unsigned long long depth, key; };
 #define C3D_ENTRY_OBJ(e) ((unsigned int)((e) >> 56) & 15u)
 
 #define C3D_MAX_OBJECTS 16
+#define C3D_SWEEP_MAX_THR 4        /* iso-values of one array classified by a single sweep launch */
 
 struct SweepRange { long long lo[3], hi[3]; }; /* inclusive cube ranges to emit */
 
@@ -92,6 +93,14 @@ int c3d_k_clear(Pixel *canvas, size_t npix, cudaStream_t s);
 int c3d_k_pixel_tables(double *px, double *py, long long w, long long h, cudaStream_t s);
 int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int obj, unsigned long long *list, unsigned long long *count,
                 unsigned long long capacity, int sm_count, cudaStream_t s);
+/* tiled bulk-copy sweep (c3d_sweep.cu): needs 16-byte aligned rows; up to C3D_SWEEP_MAX_THR iso-values per launch */
+int c3d_k_sweep_tiles_ok(const FieldView *f);
+int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nthr, const double *thr, const float *thr_ge, const unsigned int *obj,
+                      unsigned int *tile_cursor, void *records, unsigned long long *count, unsigned long long capacity,
+                      int sm_count, cudaStream_t s);
+int c3d_k_expand(const void *records, const unsigned long long *nrecords, unsigned long long rec_capacity, unsigned long long *list,
+                 unsigned long long *count, unsigned long long capacity, unsigned long long *per_object, unsigned int nobjects,
+                 int sm_count, cudaStream_t s);
 int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const unsigned long long *count, unsigned long long capacity,
                  Pixel *canvas, int sm_count, cudaStream_t s);
 int c3d_k_lines(const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines, unsigned long long first_obj,

@@ -101,7 +101,8 @@ struct c3d_field {
   bool halo_valid;
 };
 
-enum { EV_START, EV_HALO, EV_CLEAR, EV_SWEEP, EV_RASTER, EV_LINES, EV_RESOLVE, EV_REDUCE0, EV_SHADE, EV_REDUCE1, EV_PACK, EV_DOWNLOAD, EV_COUNT };
+enum { CNT_LIST = 0, CNT_REC = 1, CNT_OBJ = 2, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
+enum { EV_START, EV_HALO, EV_CLEAR, EV_SWEEP, EV_EXPAND, EV_RASTER, EV_LINES, EV_RESOLVE, EV_REDUCE0, EV_SHADE, EV_REDUCE1, EV_PACK, EV_DOWNLOAD, EV_COUNT };
 
 struct c3d_context {
   int device, rank, size, sm_count;
@@ -122,6 +123,11 @@ struct c3d_context {
   /* active-cube list of the frame (all contour objects, tagged) */
   unsigned long long *list;
   size_t list_cap;
+  void *records;                 /* 32-byte patch records written by the tiled sweep */
+  size_t rec_cap;
+  unsigned int *tile_cursor;
+  /* counters: [CNT_LIST] list cursor, [CNT_REC] record cursor, [CNT_OBJ + n] cut cubes of object n (expand),
+     [CNT_SNAP + m] list cursor after direct-sweep launch m */
   unsigned long long *counts_dev, *counts_host;
   /* per-frame descriptors */
   FieldView *views_dev;
@@ -185,8 +191,9 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   ctx->tab.pairs = (const uint32_t *)(tb + offsetof(c3d_tables_t, pairs));
   ctx->tab.emask = (const uint32_t *)(tb + offsetof(c3d_tables_t, emask));
   ctx->tab.edges = (const uint32_t *)(tb + offsetof(c3d_tables_t, edges));
-  CUDA_OK(cudaMalloc(&ctx->counts_dev, (C3D_MAX_OBJECTS + 2) * sizeof(unsigned long long)));
-  CUDA_OK(cudaMallocHost(&ctx->counts_host, (C3D_MAX_OBJECTS + 2) * sizeof(unsigned long long)));
+  CUDA_OK(cudaMalloc(&ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long)));
+  CUDA_OK(cudaMallocHost(&ctx->counts_host, CNT_TOTAL * sizeof(unsigned long long)));
+  CUDA_OK(cudaMalloc(&ctx->tile_cursor, sizeof(unsigned int)));
   CUDA_OK(cudaMalloc(&ctx->views_dev, C3D_MAX_OBJECTS * sizeof(FieldView)));
   if (comm_size > 1) {
     if (NULL == nccl_id128) return c3d_error("c3d_context_create: %d ranks need an NCCL unique id", comm_size);
@@ -208,7 +215,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   cudaFree(ctx->table_mem);
   cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->pixel_xy); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
   if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
-  cudaFree(ctx->list); cudaFree(ctx->counts_dev);
+  cudaFree(ctx->list); cudaFree(ctx->records); cudaFree(ctx->tile_cursor); cudaFree(ctx->counts_dev);
   if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
   cudaFree(ctx->views_dev); cudaFree(ctx->lines_dev); cudaFree(ctx->grids_dev); cudaFree(ctx->halo_buf);
   for (int e = 0; e < EV_COUNT; e++) cudaEventDestroy(ctx->ev[e]);
@@ -614,7 +621,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     }
     if (nl > 0) CUDA_OK(cudaMemcpyAsync(ctx->lines_dev, hl.data(), nl * sizeof(LineDev), cudaMemcpyHostToDevice, s));
   }
-  /* work list of the frame: every contour object appends its active cubes */
+  /* work buffers of the frame: patch records from the tiled sweeps, then one list entry per cut cube */
   if (nc > 0 && 0 == ctx->list_cap) {
     size_t want = 0;
     for (size_t n = 0; n < nc; n++) {
@@ -625,24 +632,73 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     CUDA_OK(cudaMalloc(&ctx->list, want * 8));
     ctx->list_cap = want;
   }
-  CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, (C3D_MAX_OBJECTS + 2) * sizeof(unsigned long long), s));
+  if (nc > 0 && 0 == ctx->rec_cap) {
+    const size_t want = std::max<size_t>(1u << 18, ctx->list_cap / 4);
+    CUDA_OK(cudaMalloc(&ctx->records, want * 32));
+    ctx->rec_cap = want;
+  }
+  CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, CNT_TOTAL * sizeof(unsigned long long), s));
   LAUNCH_OK(c3d_k_clear(ctx->canvas, npix, s));
   launches += 1;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_CLEAR], s));
-  /* 1. classification sweeps: counts_dev[0] is the shared cursor, counts_dev[1 + n] the cursor after object n */
-  for (size_t n = 0; n < nc; n++) {
-    CUDA_OK(cudaEventRecord(ctx->ev_sweep[n], s));
-    SweepRange r;
-    rendered_range(&views[n], 1, &r);
-    LAUNCH_OK(c3d_k_sweep(&views[n], &r, (unsigned int)n, ctx->list, ctx->counts_dev, ctx->list_cap, ctx->sm_count, s));
-    CUDA_OK(cudaMemcpyAsync(ctx->counts_dev + 1 + n, ctx->counts_dev, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+  /* 1. classification sweeps: contour objects that share an array share ONE pass over it (up to
+        C3D_SWEEP_MAX_THR iso-values per launch); arrays whose rows are not 16-byte aligned take the
+        direct kernel, one launch per object */
+  uint32_t nsweeps = 0;
+  uint32_t sweep_nthr[C3D_MAX_OBJECTS];
+  uint64_t sweep_bytes[C3D_MAX_OBJECTS];
+  int snap_of[C3D_MAX_OBJECTS];
+  bool used_records = false;
+  uint32_t ndirect = 0;
+  {
+    bool done[C3D_MAX_OBJECTS] = {false};
+    for (size_t n = 0; n < nc; n++) {
+      if (done[n]) continue;
+      const c3d_field *f = contours[n].field;
+      SweepRange r;
+      rendered_range(&views[n], 1, &r);
+      const uint64_t bytes = (uint64_t)f->ext[0] * f->ext[1] * f->ext[2] * (uint64_t)f->elem_bytes;
+      if (c3d_k_sweep_tiles_ok(&views[n])) {
+        double thr[C3D_SWEEP_MAX_THR];
+        float thr_ge[C3D_SWEEP_MAX_THR];
+        unsigned int obj[C3D_SWEEP_MAX_THR];
+        int cnt = 0;
+        for (size_t m = n; m < nc && cnt < C3D_SWEEP_MAX_THR; m++) {
+          if (done[m] || contours[m].field != contours[n].field) continue;
+          thr[cnt] = views[m].thr; thr_ge[cnt] = views[m].thr_ge; obj[cnt] = (unsigned int)m;
+          snap_of[m] = -1;
+          done[m] = true;
+          cnt++;
+        }
+        CUDA_OK(cudaEventRecord(ctx->ev_sweep[nsweeps], s));
+        LAUNCH_OK(c3d_k_sweep_tiles(&views[n], &r, cnt, thr, thr_ge, obj, ctx->tile_cursor, ctx->records, ctx->counts_dev + CNT_REC,
+                                    ctx->rec_cap, ctx->sm_count, s));
+        sweep_nthr[nsweeps] = (uint32_t)cnt;
+        used_records = true;
+      } else {
+        done[n] = true;
+        CUDA_OK(cudaEventRecord(ctx->ev_sweep[nsweeps], s));
+        LAUNCH_OK(c3d_k_sweep(&views[n], &r, (unsigned int)n, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->sm_count, s));
+        CUDA_OK(cudaMemcpyAsync(ctx->counts_dev + CNT_SNAP + 1 + ndirect, ctx->counts_dev + CNT_LIST, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        snap_of[n] = (int)ndirect++;
+        sweep_nthr[nsweeps] = 1;
+      }
+      sweep_bytes[nsweeps] = bytes;
+      nsweeps++;
+      launches += 1;
+    }
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev_sweep[nsweeps], s));
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_SWEEP], s));
+  if (used_records) {
+    LAUNCH_OK(c3d_k_expand(ctx->records, ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap,
+                           ctx->counts_dev + CNT_OBJ, (unsigned int)nc, ctx->sm_count, s));
     launches += 1;
   }
-  CUDA_OK(cudaEventRecord(ctx->ev_sweep[nc], s));
-  CUDA_OK(cudaEventRecord(ctx->ev[EV_SWEEP], s));
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_EXPAND], s));
   /* 2. tessellate + rasterise every active cube, contours in one launch (src/contour3d/main.c:105-117) */
   if (nc > 0) {
-    LAUNCH_OK(c3d_k_raster(&fp, ctx->list, ctx->counts_dev, ctx->list_cap, ctx->canvas, ctx->sm_count, s));
+    LAUNCH_OK(c3d_k_raster(&fp, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->canvas, ctx->sm_count, s));
     launches += 1;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_RASTER], s));
@@ -676,21 +732,33 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   CUDA_OK(cudaEventRecord(ctx->ev[EV_PACK], s));
   const bool want_host = (0 == ctx->rank) && (NULL != host_rgb || NULL != fname);
   if (want_host) CUDA_OK(cudaMemcpyAsync(ctx->ppm_host, ctx->ppm_dev, 3 * npix, cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, (C3D_MAX_OBJECTS + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaEventRecord(ctx->ev[EV_DOWNLOAD], s));
   CUDA_OK(cudaStreamSynchronize(s));
-  /* capacity policy: a list that overflowed is grown and the frame is redone */
-  const size_t need = (size_t)ctx->counts_host[0];
-  if (need > ctx->list_cap) {
-    *overflow = true;
-    cudaFree(ctx->list);
-    ctx->list = NULL;
-    ctx->list_cap = 0;
-    const size_t want = need + need / 4 + 1024;
-    const cudaError_t err = cudaMalloc(&ctx->list, want * 8);
-    if (cudaSuccess != err) return c3d_error("failed to grow the active-cube list to %zu entries: %s", want, cudaGetErrorString(err));
-    ctx->list_cap = want;
-    return 0;
+  /* capacity policy: a buffer that overflowed is grown and the frame is redone */
+  {
+    const size_t need_rec = (size_t)ctx->counts_host[CNT_REC], need_list = (size_t)ctx->counts_host[CNT_LIST];
+    if (need_rec > ctx->rec_cap) {
+      *overflow = true;
+      cudaFree(ctx->records);
+      ctx->records = NULL;
+      ctx->rec_cap = 0;
+      const size_t want = need_rec + need_rec / 4 + 1024;
+      const cudaError_t err = cudaMalloc(&ctx->records, want * 32);
+      if (cudaSuccess != err) return c3d_error("failed to grow the sweep record buffer to %zu entries: %s", want, cudaGetErrorString(err));
+      ctx->rec_cap = want;
+    }
+    if (need_list > ctx->list_cap) {
+      *overflow = true;
+      cudaFree(ctx->list);
+      ctx->list = NULL;
+      ctx->list_cap = 0;
+      const size_t want = need_list + need_list / 4 + 1024;
+      const cudaError_t err = cudaMalloc(&ctx->list, want * 8);
+      if (cudaSuccess != err) return c3d_error("failed to grow the active-cube list to %zu entries: %s", want, cudaGetErrorString(err));
+      ctx->list_cap = want;
+    }
+    if (*overflow) return 0;
   }
   /* timings */
   c3d_timings_t *t = &ctx->last;
@@ -699,7 +767,8 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   t->halo = ms(EV_START, EV_HALO);
   t->clear = ms(EV_HALO, EV_CLEAR);
   t->sweep = ms(EV_CLEAR, EV_SWEEP);
-  t->raster = ms(EV_SWEEP, EV_RASTER);
+  t->expand = ms(EV_SWEEP, EV_EXPAND);
+  t->raster = ms(EV_EXPAND, EV_RASTER);
   t->lines = ms(EV_RASTER, EV_LINES);
   t->resolve = ms(EV_LINES, EV_RESOLVE);
   t->reduce = ms(EV_RESOLVE, EV_REDUCE0) + ms(EV_SHADE, EV_REDUCE1);
@@ -709,11 +778,15 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   t->total = ms(EV_START, EV_DOWNLOAD);
   t->ncontours = (uint32_t)nc;
   t->launches = launches;
-  for (size_t n = 0; n < nc && n < 16; n++) {
-    cudaEventElapsedTime(&t->sweep_each[n], ctx->ev_sweep[n], ctx->ev_sweep[n + 1]);
-    t->active_cubes[n] = ctx->counts_host[1 + n] - (n > 0 ? ctx->counts_host[n] : 0ull);
-    const c3d_field *f = contours[n].field;
-    t->sweep_bytes[n] = (uint64_t)f->ext[0] * f->ext[1] * f->ext[2] * (uint64_t)f->elem_bytes;
+  t->nsweeps = nsweeps;
+  for (uint32_t m = 0; m < nsweeps; m++) {
+    cudaEventElapsedTime(&t->sweep_each[m], ctx->ev_sweep[m], ctx->ev_sweep[m + 1]);
+    t->sweep_bytes[m] = sweep_bytes[m];
+    t->sweep_thresholds[m] = sweep_nthr[m];
+  }
+  for (size_t n = 0; n < nc; n++) {
+    t->active_cubes[n] = ctx->counts_host[CNT_OBJ + n];
+    if (snap_of[n] >= 0) t->active_cubes[n] += ctx->counts_host[CNT_SNAP + 1 + snap_of[n]] - ctx->counts_host[CNT_SNAP + snap_of[n]];
   }
   if (want_host) {
     if (NULL != host_rgb) memcpy(host_rgb, ctx->ppm_host, 3 * npix);
@@ -818,20 +891,34 @@ extern "C" int c3d_case_codes(c3d_context_t *ctx, const c3d_field_t *f, double t
 static int sweep_to_device(c3d_context *ctx, const FieldView *v, const int rendered_only, unsigned long long **list, unsigned long long *count) {
   SweepRange r;
   rendered_range(v, rendered_only, &r);
-  size_t cap = 1u << 20;
-  for (int attempt = 0; attempt < 3; attempt++) {
+  size_t cap = 1u << 20, rec_cap = 1u << 18;
+  const bool tiles = 0 != c3d_k_sweep_tiles_ok(v);
+  for (int attempt = 0; attempt < 4; attempt++) {
+    void *records = NULL;
     CUDA_OK(cudaMalloc(list, cap * 8));
-    CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, 8, ctx->stream));
-    LAUNCH_OK(c3d_k_sweep(v, &r, 0u, *list, ctx->counts_dev, cap, ctx->sm_count, ctx->stream));
-    CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, CNT_TOTAL * sizeof(unsigned long long), ctx->stream));
+    if (tiles) {
+      const unsigned int obj = 0u;
+      CUDA_OK(cudaMalloc(&records, rec_cap * 32));
+      LAUNCH_OK(c3d_k_sweep_tiles(v, &r, 1, &v->thr, &v->thr_ge, &obj, ctx->tile_cursor, records, ctx->counts_dev + CNT_REC, rec_cap,
+                                  ctx->sm_count, ctx->stream));
+      LAUNCH_OK(c3d_k_expand(records, ctx->counts_dev + CNT_REC, rec_cap, *list, ctx->counts_dev + CNT_LIST, cap, ctx->counts_dev + CNT_OBJ, 1u,
+                             ctx->sm_count, ctx->stream));
+    } else {
+      LAUNCH_OK(c3d_k_sweep(v, &r, 0u, *list, ctx->counts_dev + CNT_LIST, cap, ctx->sm_count, ctx->stream));
+    }
+    CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    *count = ctx->counts_host[0];
-    if (*count <= cap) return 0;
+    if (records) CUDA_OK(cudaFree(records));
+    *count = ctx->counts_host[CNT_LIST];
+    const size_t nrec = (size_t)ctx->counts_host[CNT_REC];
+    if (*count <= cap && nrec <= rec_cap) return 0;
     CUDA_OK(cudaFree(*list));
     *list = NULL;
-    cap = (size_t)*count + 1024;
+    if (*count > cap) cap = (size_t)*count + 1024;
+    if (nrec > rec_cap) rec_cap = nrec + 1024;
   }
-  return c3d_error("sweep list did not converge");
+  return c3d_error("sweep buffers did not converge");
 }
 
 extern "C" int c3d_sweep(c3d_context_t *ctx, const c3d_field_t *f, double threshold, int rendered_only, size_t capacity,

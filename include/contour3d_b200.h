@@ -79,12 +79,14 @@ typedef struct {
 
 /* per-stage device times of the last frame, milliseconds (CUDA events) */
 typedef struct {
-  float upload, halo, clear, sweep, raster, lines, resolve, reduce, shade, pack, download, total;
-  float sweep_each[16];       /* per contour object */
-  uint64_t active_cubes[16];  /* per contour object, rendered range */
-  uint64_t sweep_bytes[16];   /* algorithmic bytes of each sweep launch */
+  float upload, halo, clear, sweep, expand, raster, lines, resolve, reduce, shade, pack, download, total;
+  float sweep_each[16];          /* per sweep launch */
+  uint64_t sweep_bytes[16];      /* algorithmic bytes of each sweep launch (elem_bytes x points of the extended array) */
+  uint32_t sweep_thresholds[16]; /* iso-values classified by each sweep launch */
+  uint64_t active_cubes[16];     /* per contour object, rendered range */
+  uint32_t nsweeps;
   uint32_t ncontours;
-  uint32_t launches;          /* kernels launched by this library in the frame */
+  uint32_t launches;             /* kernels launched by this library in the frame */
 } c3d_timings_t;
 
 /* ---- life cycle ---- */
