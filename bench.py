@@ -275,7 +275,7 @@ def ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "stages_ms": {k: v / args.steps for k, v in stage_sum.items()},
-            "active_cubes": active,
+            "active_cubes": active, "culled_cubes": t["culled_cubes"],
         }
         print(json.dumps(line))
     barrier()

@@ -70,6 +70,7 @@ class Timings(C.Structure):
         ("sweep_bytes", C.c_uint64 * 16),
         ("sweep_thresholds", C.c_uint32 * 16),
         ("active_cubes", C.c_uint64 * 16),
+        ("culled_cubes", C.c_uint64),
         ("nsweeps", C.c_uint32),
         ("ncontours", C.c_uint32),
         ("launches", C.c_uint32),
@@ -82,6 +83,7 @@ class Timings(C.Structure):
         d["sweep_bytes"] = [int(self.sweep_bytes[i]) for i in range(m)]
         d["sweep_thresholds"] = [int(self.sweep_thresholds[i]) for i in range(m)]
         d["active_cubes"] = [int(self.active_cubes[i]) for i in range(n)]
+        d["culled_cubes"] = int(self.culled_cubes)
         d["launches"] = int(self.launches)
         return d
 

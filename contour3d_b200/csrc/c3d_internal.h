@@ -71,13 +71,25 @@ struct __align__(16) Pixel { unsigned long long depth, key; };
 #define C3D_ENTRY_OBJ(e) ((unsigned int)((e) >> 56) & 15u)
 
 #define C3D_MAX_OBJECTS 16
+#define C3D_DEPTH_BUCKETS 2048        /* view-depth slabs of the front-to-back ordering (multiple of 1024) */
 #define C3D_SWEEP_MAX_THR 4        /* iso-values of one array classified by a single sweep launch */
 
 struct SweepRange { long long lo[3], hi[3]; }; /* inclusive cube ranges to emit */
 
+/* fp32 copy of the projection (project.c:28-65) for the conservative occlusion test of whole cubes:
+   sx = ax + t * (ray . lxs), sy = ay + t * (ray . lys), t = c / (n . ray), ray = p - cam */
+struct CullCam {
+  float cam[3], n[3], lxs[3], lys[3];
+  float ax, ay, c;
+  float W, H;
+  int w, h;
+  int enabled;
+};
+
 /* everything the raster / shading kernels need, passed by value (constant bank) */
 struct FrameParams {
   Cam cam;
+  CullCam cull;
   DevTables tab;
   const double *px, *py;     /* pixel-centre coordinates, render.c:94-98, tabulated once per screen size */
   unsigned int ncontours;
@@ -96,13 +108,15 @@ int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int obj, unsig
 /* tiled bulk-copy sweep (c3d_sweep.cu): needs 16-byte aligned rows; up to C3D_SWEEP_MAX_THR iso-values per launch */
 int c3d_k_sweep_tiles_ok(const FieldView *f);
 int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nthr, const double *thr, const float *thr_ge, const unsigned int *obj,
-                      unsigned int *tile_cursor, void *records, unsigned long long *count, unsigned long long capacity,
+                      const int flip[3], unsigned int *tile_cursor, void *records, unsigned long long *count, unsigned long long capacity,
                       int sm_count, cudaStream_t s);
-int c3d_k_expand(const void *records, const unsigned long long *nrecords, unsigned long long rec_capacity, unsigned long long *list,
-                 unsigned long long *count, unsigned long long capacity, unsigned long long *per_object, unsigned int nobjects,
-                 int sm_count, cudaStream_t s);
+/* sorted != 0: counting sort of the entries by view depth, nearest first (needs fp->cull and the range of n.(p - cam)) */
+int c3d_k_expand(const FrameParams *fp, int sorted, float near_depth, float far_depth,
+                 const void *records, const unsigned long long *nrecords, unsigned long long rec_capacity, unsigned long long *list,
+                 unsigned long long *count, unsigned long long capacity, unsigned int *histogram, unsigned long long *cursors,
+                 unsigned long long *per_object, unsigned int nobjects, int sm_count, cudaStream_t s);
 int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const unsigned long long *count, unsigned long long capacity,
-                 Pixel *canvas, int sm_count, cudaStream_t s);
+                 Pixel *canvas, unsigned long long *culled, int sm_count, cudaStream_t s);
 int c3d_k_lines(const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines, unsigned long long first_obj,
                 Pixel *canvas, cudaStream_t s);
 int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t npix, cudaStream_t s);

@@ -315,21 +315,88 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
   }
 }
 
+/*
+ * Conservative occlusion test of a whole cube against the z-buffer as it
+ * stands: true only when every pixel any of the cube's triangles could touch
+ * already holds a depth strictly nearer than anything inside the cube.  Such
+ * a cube cannot change the image (depths only grow, render.c:125-132), so its
+ * triangles are never built.  The test runs in fp32 with margins far above the
+ * fp32 error (0.25 pixel, 1e-4 relative depth); anything doubtful is kept.
+ * With a depth complexity of ~20 most cubes of a turbulent field are hidden.
+ */
+__device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned long long entry, const Pixel *__restrict__ canvas) {
+  const CullCam &q = p.cull;
+  const FieldView &f = p.view[C3D_ENTRY_OBJ(entry)];
+  const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
+  float an[2], al[2], am[2], bn[2], bl[2], bm[2], cn[2], cl[2], cm[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const float rx = (float)__ldg(f.g[0] + i + e) - q.cam[0];
+    const float ry = (float)__ldg(f.g[1] + j + e) - q.cam[1];
+    const float rz = (float)__ldg(f.g[2] + k + e) - q.cam[2];
+    an[e] = q.n[0] * rx; al[e] = q.lxs[0] * rx; am[e] = q.lys[0] * rx;
+    bn[e] = q.n[1] * ry; bl[e] = q.lxs[1] * ry; bm[e] = q.lys[1] * ry;
+    cn[e] = q.n[2] * rz; cl[e] = q.lxs[2] * rz; cm[e] = q.lys[2] * rz;
+  }
+  float xlo = 3.e38f, xhi = -3.e38f, ylo = 3.e38f, yhi = -3.e38f, znear = -3.e38f, tlo = 3.e38f, thi = -3.e38f;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int a = c & 1, b = (c >> 1) & 1, d = c >> 2;
+    const float nr = an[a] + bn[b] + cn[d];
+    const float t = __fdividef(q.c, nr);
+    const float sx = q.ax + t * (al[a] + bl[b] + cl[d]);
+    const float sy = q.ay + t * (am[a] + bm[b] + cm[d]);
+    xlo = fminf(xlo, sx); xhi = fmaxf(xhi, sx);
+    ylo = fminf(ylo, sy); yhi = fmaxf(yhi, sy);
+    znear = fmaxf(znear, nr);
+    tlo = fminf(tlo, t); thi = fmaxf(thi, t);
+  }
+  /* every corner strictly beyond the screen plane as seen from the camera (project.c:44-46 accepts 0 < t < 1;
+     then all n.ray share the sign of c and the cube projects inside the hull of its corners), else the
+     bounds mean nothing and the cube is kept */
+  if (!(tlo > 1.e-4f && thi < 0.9999f)) return false;
+  /* a fragment exists only where a PIXEL CENTRE lies inside a triangle (render.c:94-115; the +-1 pixel box of
+     render.c:81-89 is just the search range), and every triangle lies inside the hull of the corners:
+     the pixels to look at are those whose centre (i + 0.5) / W - 0.5 falls within the bounds, +- 0.05 pixel */
+  const float fx0 = (0.5f + xlo) * q.W - 0.55f, fx1 = (0.5f + xhi) * q.W - 0.45f;
+  const float fy0 = (0.5f + ylo) * q.H - 0.55f, fy1 = (0.5f + yhi) * q.H - 0.45f;
+  if (!(fx0 > -1.e6f && fx1 < 1.e6f && fy0 > -1.e6f && fy1 < 1.e6f)) return false;
+  const int imin = max(0, (int)ceilf(fx0)), imax = min(q.w - 1, (int)floorf(fx1));
+  const int jmin = max(0, (int)ceilf(fy0)), jmax = min(q.h - 1, (int)floorf(fy1));
+  if (imax < imin || jmax < jmin) return true;                 /* no pixel centre inside: nothing to draw */
+  if ((imax - imin + 1) * (jmax - jmin + 1) > 64) return false;
+  const double zcap = (double)znear + (1.e-4 * fabs((double)znear) + 1.e-6);
+  const unsigned long long limit = ord_of(zcap);
+  for (int pj = jmin; pj <= jmax; pj++) {
+    const unsigned long long *row = reinterpret_cast<const unsigned long long *>(canvas + (long long)pj * q.w);
+    for (int pi = imin; pi <= imax; pi++) {
+      if (__ldcg(row + 2 * pi) <= limit) return false;
+    }
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(128) k_raster(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ list,
                                                 const unsigned long long *__restrict__ count, const unsigned long long capacity,
-                                                Pixel *__restrict__ canvas) {
+                                                Pixel *__restrict__ canvas, unsigned long long *__restrict__ culled) {
+  __shared__ unsigned long long s_entry[4][32];
+  __shared__ unsigned int s_first[4][32];
   unsigned long long n = *count;
   if (n > capacity) n = capacity;
-  const unsigned int lane = threadIdx.x & 31u;
-  const unsigned long long warp = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned int lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const unsigned long long warp = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + wid;
   const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+  unsigned int hidden_total = 0u;
   for (unsigned long long base = warp * 32ull; base < n; base += nwarps * 32ull) {
     unsigned long long entry = 0ull;
     unsigned int ntri = 0u;
     if (base + lane < n) {
       entry = __ldg(list + base + lane);
       ntri = __ldg(p.tab.count + C3D_ENTRY_CODE(entry));
+      if (p.cull.enabled && cube_hidden(p, entry, canvas)) ntri = 0u;
     }
+    const unsigned int alive = __ballot_sync(C3D_FULL_MASK, ntri > 0u);
+    hidden_total += __popc(__ballot_sync(C3D_FULL_MASK, base + lane < n)) - __popc(alive);
     unsigned int incl = ntri;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -338,22 +405,29 @@ __global__ void __launch_bounds__(128) k_raster(const __grid_constant__ FramePar
     }
     const unsigned int total = __shfl_sync(C3D_FULL_MASK, incl, 31);
     const unsigned int excl = incl - ntri;
+    /* surviving cubes, compacted: slot r = r-th surviving lane */
+    __syncwarp();
+    if (ntri > 0u) {
+      const unsigned int slot = __popc(alive & ((1u << lane) - 1u));
+      s_entry[wid][slot] = entry;
+      s_first[wid][slot] = excl;
+    }
+    __syncwarp();
     for (unsigned int t0 = 0; t0 < total; t0 += 32u) {
-      /* source cube of triangle t0 + lane: the last cube whose first triangle is <= it */
+      /* source cube of triangle t0 + lane: the last surviving cube whose first triangle is <= it */
       const bool starts_here = ntri > 0u && excl >= t0 && excl < t0 + 32u;
       const unsigned int starts = __reduce_or_sync(C3D_FULL_MASK, starts_here ? 1u << (excl - t0) : 0u);
       const unsigned int before = __popc(__ballot_sync(C3D_FULL_MASK, ntri > 0u && excl < t0));
       const unsigned int src = (before + __popc(starts & (0xffffffffu >> (31u - lane))) - 1u) & 31u;
-      const unsigned long long e = __shfl_sync(C3D_FULL_MASK, entry, src);
-      const unsigned int first = __shfl_sync(C3D_FULL_MASK, excl, src);
-      if (t0 + lane < total) raster_triangle(p, e, t0 + lane - first, canvas);
+      if (t0 + lane < total) raster_triangle(p, s_entry[wid][src], t0 + lane - s_first[wid][src], canvas);
     }
   }
+  if (0u == lane && hidden_total > 0u && nullptr != culled) atomicAdd(culled, (unsigned long long)hidden_total);
 }
 
 extern "C" int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const unsigned long long *count, unsigned long long capacity,
-                            Pixel *canvas, int sm_count, cudaStream_t s) {
-  k_raster<<<sm_count * 8, 128, 0, s>>>(*p, list, count, capacity, canvas);
+                            Pixel *canvas, unsigned long long *culled, int sm_count, cudaStream_t s) {
+  k_raster<<<sm_count * 8, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
   return (int)cudaGetLastError();
 }
 

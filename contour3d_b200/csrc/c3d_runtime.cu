@@ -101,7 +101,7 @@ struct c3d_field {
   bool halo_valid;
 };
 
-enum { CNT_LIST = 0, CNT_REC = 1, CNT_OBJ = 2, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
+enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_OBJ = 3, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
 enum { EV_START, EV_HALO, EV_CLEAR, EV_SWEEP, EV_EXPAND, EV_RASTER, EV_LINES, EV_RESOLVE, EV_REDUCE0, EV_SHADE, EV_REDUCE1, EV_PACK, EV_DOWNLOAD, EV_COUNT };
 
 struct c3d_context {
@@ -126,6 +126,8 @@ struct c3d_context {
   void *records;                 /* 32-byte patch records written by the tiled sweep */
   size_t rec_cap;
   unsigned int *tile_cursor;
+  unsigned int *bucket_hist;             /* C3D_DEPTH_BUCKETS counters + cursors of the depth ordering */
+  unsigned long long *bucket_cursors;
   /* counters: [CNT_LIST] list cursor, [CNT_REC] record cursor, [CNT_OBJ + n] cut cubes of object n (expand),
      [CNT_SNAP + m] list cursor after direct-sweep launch m */
   unsigned long long *counts_dev, *counts_host;
@@ -194,6 +196,8 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   CUDA_OK(cudaMalloc(&ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long)));
   CUDA_OK(cudaMallocHost(&ctx->counts_host, CNT_TOTAL * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->tile_cursor, sizeof(unsigned int)));
+  CUDA_OK(cudaMalloc(&ctx->bucket_hist, C3D_DEPTH_BUCKETS * sizeof(unsigned int)));
+  CUDA_OK(cudaMalloc(&ctx->bucket_cursors, C3D_DEPTH_BUCKETS * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->views_dev, C3D_MAX_OBJECTS * sizeof(FieldView)));
   if (comm_size > 1) {
     if (NULL == nccl_id128) return c3d_error("c3d_context_create: %d ranks need an NCCL unique id", comm_size);
@@ -215,7 +219,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   cudaFree(ctx->table_mem);
   cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->pixel_xy); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
   if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
-  cudaFree(ctx->list); cudaFree(ctx->records); cudaFree(ctx->tile_cursor); cudaFree(ctx->counts_dev);
+  cudaFree(ctx->list); cudaFree(ctx->records); cudaFree(ctx->tile_cursor); cudaFree(ctx->bucket_hist); cudaFree(ctx->bucket_cursors); cudaFree(ctx->counts_dev);
   if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
   cudaFree(ctx->views_dev); cudaFree(ctx->lines_dev); cudaFree(ctx->grids_dev); cudaFree(ctx->halo_buf);
   for (int e = 0; e < EV_COUNT; e++) cudaEventDestroy(ctx->ev[e]);
@@ -547,6 +551,29 @@ static void make_cam(const c3d_scene_t *s, Cam *c) {
   c->h = (long long)s->height;
 }
 
+/* fp32 projection constants of cube_hidden() (c3d_kernels.cu) */
+static void make_cull(const Cam *c, CullCam *q) {
+  const double cx = (c->cam[0] - c->center[0]) * c->lx[0] + (c->cam[1] - c->center[1]) * c->lx[1] + (c->cam[2] - c->center[2]) * c->lx[2];
+  const double cy = (c->cam[0] - c->center[0]) * c->ly[0] + (c->cam[1] - c->center[1]) * c->ly[1] + (c->cam[2] - c->center[2]) * c->ly[2];
+  for (int d = 0; d < 3; d++) {
+    q->cam[d] = (float)c->cam[d];
+    q->n[d] = (float)c->normal[d];
+    q->lxs[d] = (float)(c->lx[d] / c->lxlx);
+    q->lys[d] = (float)(c->ly[d] / c->lyly);
+  }
+  q->ax = (float)(cx / c->lxlx);
+  q->ay = (float)(cy / c->lyly);
+  q->c = (float)(c->d - c->nc);
+  q->W = (float)c->W;
+  q->H = (float)c->H;
+  q->w = (int)c->w;
+  q->h = (int)c->h;
+  const char *env = getenv("CONTOUR3D_NO_CULL");
+  const bool off = NULL != env && '\0' != *env && '0' != *env;
+  /* needs finite, non-degenerate constants and a screen that fits the int / float arithmetic of the test */
+  q->enabled = !off && fabs(c->d - c->nc) > 1.e-9 && isfinite(q->ax) && isfinite(q->ay) && c->w < (1 << 20) && c->h < (1 << 20);
+}
+
 static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t nc, const c3d_contour_t *contours,
                       const size_t nl, const c3d_line_t *lines, uint8_t *host_rgb, const char *fname, bool *overflow) {
   *overflow = false;
@@ -579,6 +606,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   FrameParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.cam = cam;
+  make_cull(&cam, &fp.cull);
   fp.tab = ctx->tab;
   fp.px = ctx->pixel_xy;
   fp.py = ctx->pixel_xy + scene->width;
@@ -671,7 +699,13 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
           cnt++;
         }
         CUDA_OK(cudaEventRecord(ctx->ev_sweep[nsweeps], s));
-        LAUNCH_OK(c3d_k_sweep_tiles(&views[n], &r, cnt, thr, thr_ge, obj, ctx->tile_cursor, ctx->records, ctx->counts_dev + CNT_REC,
+        /* front-to-back for this camera: start at the end of each axis the camera is nearer to */
+        int flip[3];
+        for (int d = 0; d < 3; d++) {
+          const double lo = contours[n].grids[d][f->ext_off[d]], hi = contours[n].grids[d][f->ext_off[d] + f->ext[d] - 1];
+          flip[d] = fabs(cam.cam[d] - hi) < fabs(cam.cam[d] - lo) ? 1 : 0;
+        }
+        LAUNCH_OK(c3d_k_sweep_tiles(&views[n], &r, cnt, thr, thr_ge, obj, flip, ctx->tile_cursor, ctx->records, ctx->counts_dev + CNT_REC,
                                     ctx->rec_cap, ctx->sm_count, s));
         sweep_nthr[nsweeps] = (uint32_t)cnt;
         used_records = true;
@@ -691,14 +725,30 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   CUDA_OK(cudaEventRecord(ctx->ev_sweep[nsweeps], s));
   CUDA_OK(cudaEventRecord(ctx->ev[EV_SWEEP], s));
   if (used_records) {
-    LAUNCH_OK(c3d_k_expand(ctx->records, ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap,
+    /* range of the view depth n.(p - cam) over the corners of every array: the slabs of the front-to-back order */
+    double near_depth = -DBL_MAX, far_depth = DBL_MAX;
+    for (size_t n = 0; n < nc; n++) {
+      const c3d_field *f = contours[n].field;
+      for (int c = 0; c < 8; c++) {
+        double depth = 0.;
+        for (int d = 0; d < 3; d++) {
+          const size_t at = f->ext_off[d] + (((c >> d) & 1) ? f->ext[d] - 1 : 0);
+          depth += cam.normal[d] * (contours[n].grids[d][at] - cam.cam[d]);
+        }
+        near_depth = std::max(near_depth, depth);
+        far_depth = std::min(far_depth, depth);
+      }
+    }
+    const int sorted = fp.cull.enabled && near_depth > far_depth;
+    LAUNCH_OK(c3d_k_expand(&fp, sorted, (float)near_depth, (float)far_depth, ctx->records, ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->list,
+                           ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->bucket_hist, ctx->bucket_cursors,
                            ctx->counts_dev + CNT_OBJ, (unsigned int)nc, ctx->sm_count, s));
-    launches += 1;
+    launches += sorted ? 3 : 1;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_EXPAND], s));
   /* 2. tessellate + rasterise every active cube, contours in one launch (src/contour3d/main.c:105-117) */
   if (nc > 0) {
-    LAUNCH_OK(c3d_k_raster(&fp, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->canvas, ctx->sm_count, s));
+    LAUNCH_OK(c3d_k_raster(&fp, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->canvas, ctx->counts_dev + CNT_CULLED, ctx->sm_count, s));
     launches += 1;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_RASTER], s));
@@ -779,6 +829,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   t->ncontours = (uint32_t)nc;
   t->launches = launches;
   t->nsweeps = nsweeps;
+  t->culled_cubes = ctx->counts_host[CNT_CULLED];
   for (uint32_t m = 0; m < nsweeps; m++) {
     cudaEventElapsedTime(&t->sweep_each[m], ctx->ev_sweep[m], ctx->ev_sweep[m + 1]);
     t->sweep_bytes[m] = sweep_bytes[m];
@@ -900,10 +951,17 @@ static int sweep_to_device(c3d_context *ctx, const FieldView *v, const int rende
     if (tiles) {
       const unsigned int obj = 0u;
       CUDA_OK(cudaMalloc(&records, rec_cap * 32));
-      LAUNCH_OK(c3d_k_sweep_tiles(v, &r, 1, &v->thr, &v->thr_ge, &obj, ctx->tile_cursor, records, ctx->counts_dev + CNT_REC, rec_cap,
+      /* the result is a set, so any visiting order will do: alternate them so that the stage-level parity
+         tests cover both marching directions */
+      static int turn = 0;
+      const int flip[3] = {turn & 1, (turn >> 1) & 1, (turn >> 2) & 1};
+      turn = (turn + 3) & 7;
+      LAUNCH_OK(c3d_k_sweep_tiles(v, &r, 1, &v->thr, &v->thr_ge, &obj, flip, ctx->tile_cursor, records, ctx->counts_dev + CNT_REC, rec_cap,
                                   ctx->sm_count, ctx->stream));
-      LAUNCH_OK(c3d_k_expand(records, ctx->counts_dev + CNT_REC, rec_cap, *list, ctx->counts_dev + CNT_LIST, cap, ctx->counts_dev + CNT_OBJ, 1u,
-                             ctx->sm_count, ctx->stream));
+      FrameParams none;
+      memset(&none, 0, sizeof(none));
+      LAUNCH_OK(c3d_k_expand(&none, 0, 0.f, 0.f, records, ctx->counts_dev + CNT_REC, rec_cap, *list, ctx->counts_dev + CNT_LIST, cap,
+                             ctx->bucket_hist, ctx->bucket_cursors, ctx->counts_dev + CNT_OBJ, 1u, ctx->sm_count, ctx->stream));
     } else {
       LAUNCH_OK(c3d_k_sweep(v, &r, 0u, *list, ctx->counts_dev + CNT_LIST, cap, ctx->sm_count, ctx->stream));
     }

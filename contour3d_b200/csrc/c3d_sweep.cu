@@ -13,8 +13,8 @@
  *    through `zc` planes; tiles are handed out by an atomic cursor;
  *  - rows travel HBM -> shared memory as 1-D bulk async copies
  *    (cp.async.bulk ... mbarrier::complete_tx::bytes, SASS UBLKCP) into a
- *    warp-private ring of SW_SLOTS slots of 8 rows, so SW_SLOTS x 4 KiB per
- *    warp are always in flight and no register is tied up by a load;
+ *    warp-private ring of 3-4 slots of 8 rows, so 12-16 KiB per warp are
+ *    always in flight and no register is tied up by a load;
  *  - a lane reads its 4 points of a row with one LDS.128 and folds
  *    `thr < v` of the 4 points into bit 4r+c of a 32-bit word per iso-value
  *    (8 rows x 4 points; FSET + LOP3 each), so one word describes 32 points;
@@ -35,7 +35,6 @@
 #include <stdint.h>
 #include "c3d_internal.h"
 
-#define SW_SLOTS 3          /* ring depth per warp */
 #define SW_ROWS 8           /* rows per slot = rows per 32-bit word */
 #define SW_GROUPS 4         /* row groups per tile: 32 point rows, 31 cube rows */
 #define SW_XCUBES 124       /* cubes per tile row (lane 31 only supplies the x+1 neighbour) */
@@ -61,6 +60,7 @@ struct TileSweepParams {
   unsigned int obj[C3D_SWEEP_MAX_THR];
   long long ilo, ihi, jlo, jhi, klo, khi;   /* inclusive cube ranges to report */
   int nxt, nyt, nzc, zc;
+  int flip[3];                       /* visit tiles (and planes) from the high end of the axis: front-to-back for the camera */
   unsigned int ntiles;
   unsigned int *tile_cursor;
   SweepRecord *records;
@@ -95,10 +95,38 @@ __device__ __forceinline__ void bulk_g2s(const uint32_t dst, const void *src, co
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-/* `threshold < value` (triangulate.c:176-179): fp32 fields compare against the smallest float above the
-   threshold, which is the same predicate exactly; NaN is "not above" in both forms */
-__device__ __forceinline__ bool above(const float v, const float thr_ge) { return v >= thr_ge; }
-__device__ __forceinline__ bool above(const double v, const double thr) { return thr < v; }
+/*
+ * Per-iso-value accumulator of one row group: bit 4r+c <=> point c of row r is
+ * above the iso-value, i.e. `threshold < value` (triangulate.c:176-179).
+ *
+ * fp32 fields compare against the smallest float above the threshold, which is
+ * the same predicate exactly (NaN is "not above" in both forms).  The ALU pipe
+ * (16 lanes/clk/SMSP: FSETP, LOP3, SHF) is the scarce resource of this kernel,
+ * so the float version spends one ALU op (FSET.BF -> 1.0f / 0.0f) and one
+ * FMA-pipe op (FFMA with the bit weight; sums of distinct powers of two below
+ * 2^16 are exact in fp32) per point instead of two ALU ops.
+ */
+template <typename T> struct GroupBits;
+template <> struct GroupBits<float> {
+  float lo, hi;               /* rows 0-3 / rows 4-7, weights 2^(4(r&3)+c) */
+  __device__ __forceinline__ void clear() { lo = 0.f; hi = 0.f; }
+  template <int R, int C> __device__ __forceinline__ void add(const float v, const float thr_ge) {
+    float one;
+    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(one) : "f"(v), "f"(thr_ge));
+    constexpr float weight = (float)(1u << (4 * (R & 3) + C));
+    if (R < 4) lo = fmaf(one, weight, lo);
+    else hi = fmaf(one, weight, hi);
+  }
+  __device__ __forceinline__ unsigned int word() const { return __float2uint_rz(lo) | (__float2uint_rz(hi) << 16); }
+};
+template <> struct GroupBits<double> {
+  unsigned int w;
+  __device__ __forceinline__ void clear() { w = 0u; }
+  template <int R, int C> __device__ __forceinline__ void add(const double v, const double thr) {
+    if (thr < v) w |= 1u << (4 * R + C);
+  }
+  __device__ __forceinline__ unsigned int word() const { return w; }
+};
 
 template <typename T> struct Thr;
 template <> struct Thr<float> {
@@ -106,6 +134,11 @@ template <> struct Thr<float> {
 };
 template <> struct Thr<double> {
   __device__ static __forceinline__ double get(const TileSweepParams &p, const int t) { return p.thr[t]; }
+};
+
+template <typename T, int NT, int R> struct RowFold {
+  /* rows R..7 of a slot, unrolled at compile time */
+  __device__ static __forceinline__ void run(const T *rows, const unsigned int lane, const TileSweepParams &p, GroupBits<T> (&acc)[NT]);
 };
 
 template <typename T> struct Quad4 { T a, b, c, d; };
@@ -119,13 +152,29 @@ __device__ __forceinline__ Quad4<double> lds_quad(const double *row, const unsig
   return Quad4<double>{lo.x, lo.y, hi.x, hi.y};
 }
 
+template <typename T, int NT, int R>
+__device__ __forceinline__ void RowFold<T, NT, R>::run(const T *rows, const unsigned int lane, const TileSweepParams &p, GroupBits<T> (&acc)[NT]) {
+  if constexpr (R < SW_ROWS) {
+    const Quad4<T> v = lds_quad(rows + R * 128, lane);
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      const auto thr = Thr<T>::get(p, t);
+      acc[t].template add<R, 0>(v.a, thr);
+      acc[t].template add<R, 1>(v.b, thr);
+      acc[t].template add<R, 2>(v.c, thr);
+      acc[t].template add<R, 3>(v.d, thr);
+    }
+    RowFold<T, NT, R + 1>::run(rows, lane, p, acc);
+  }
+}
+
 /*
  * One warp = one tile at a time.  Shared memory per warp:
  *   ring   SW_SLOTS x SW_ROWS rows x 128 points
  *   stage  SW_STAGE records
  *   bars   SW_SLOTS mbarriers
  */
-template <typename T, int NT, int WARPS>
+template <typename T, int NT, int WARPS, int SW_SLOTS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_constant__ TileSweepParams p) {
   constexpr unsigned int ROWB = 128u * sizeof(T);
   constexpr unsigned int SLOTB = SW_ROWS * ROWB;
@@ -166,9 +215,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
     if (0u == lane) tile = atomicAdd(p.tile_cursor, 1u);
     tile = __shfl_sync(SW_FULL, tile, 0);
     if (tile >= p.ntiles) break;
-    const int xt = (int)(tile % (unsigned int)p.nxt);
-    const int yt = (int)((tile / (unsigned int)p.nxt) % (unsigned int)p.nyt);
-    const int zt = (int)(tile / ((unsigned int)p.nxt * (unsigned int)p.nyt));
+    int xt = (int)(tile % (unsigned int)p.nxt);
+    int yt = (int)((tile / (unsigned int)p.nxt) % (unsigned int)p.nyt);
+    int zt = (int)(tile / ((unsigned int)p.nxt * (unsigned int)p.nyt));
+    /* tiles are handed out (and their records appended) in this order, which the raster follows: nearest
+       tiles first lets its occlusion test drop most of what lies behind */
+    if (p.flip[0]) xt = p.nxt - 1 - xt;
+    if (p.flip[1]) yt = p.nyt - 1 - yt;
+    if (p.flip[2]) zt = p.nzc - 1 - zt;
     const long long x0 = (long long)xt * SW_XCUBES;
     const long long j0 = p.jlo + (long long)yt * SW_YCUBES;
     const long long k0 = p.klo + (long long)zt * p.zc;
@@ -215,7 +269,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
       if (0u == lane) mbar_expect_tx(bar, (uint32_t)rows * xbytes);
       __syncwarp();
       if ((int)lane < rows) {
-        const T *src = base + (k0 + ipl) * p.sz + (j0 + SW_ROWS * ig + (long long)lane) * p.sy + x0;
+        const long long plane = p.flip[2] ? k1 + 1 - ipl : k0 + ipl;
+        const T *src = base + plane * p.sz + (j0 + SW_ROWS * ig + (long long)lane) * p.sy + x0;
         bulk_g2s(ring_s + islot * SLOTB + lane * ROWB, src, xbytes, bar);
       }
       issued++;
@@ -231,29 +286,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
       for (int g = 0; g < SW_GROUPS; g++) { LP[t][g] = 0u; LQ[t][g] = 0u; }
     }
 
+    unsigned int UP[NT][SW_GROUPS], UQ[NT][SW_GROUPS];     /* upper plane, being assembled */
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+#pragma unroll
+      for (int g = 0; g < SW_GROUPS; g++) { UP[t][g] = 0u; UQ[t][g] = 0u; }
+    }
     for (int pl = 0; pl < nplanes; pl++) {
-      unsigned int UP[NT][SW_GROUPS], UQ[NT][SW_GROUPS];
-#pragma unroll
+      /* the row-group loop is kept rolled (the body is large: 8 rows x 4 points x NT iso-values); each new
+         group enters at index 3 and the older ones slide down, so after four turns UP[t][g] is group g */
+#pragma unroll 1
       for (int g = 0; g < SW_GROUPS; g++) {
-        unsigned int acc[NT];
+        GroupBits<T> acc[NT];
 #pragma unroll
-        for (int t = 0; t < NT; t++) acc[t] = 0u;
+        for (int t = 0; t < NT; t++) acc[t].clear();
         if (g < ng) {
           mbar_wait(bars_s + 8u * cslot, cphase);
-          const T *rows = reinterpret_cast<const T *>(ring + cslot * SLOTB);
-#pragma unroll
-          for (int r = 0; r < SW_ROWS; r++) {
-            const Quad4<T> v = lds_quad(rows + r * 128, lane);
-#pragma unroll
-            for (int t = 0; t < NT; t++) {
-              const auto thr = Thr<T>::get(p, t);
-              /* FSETP + predicated LOP3 per point */
-              if (above(v.a, thr)) acc[t] |= 1u << (4 * r + 0);
-              if (above(v.b, thr)) acc[t] |= 1u << (4 * r + 1);
-              if (above(v.c, thr)) acc[t] |= 1u << (4 * r + 2);
-              if (above(v.d, thr)) acc[t] |= 1u << (4 * r + 3);
-            }
-          }
+          RowFold<T, NT, 0>::run(reinterpret_cast<const T *>(ring + cslot * SLOTB), lane, p, acc);
           /* the slot is free again: refill it SW_SLOTS steps ahead */
           fence_proxy_async();
           __syncwarp();
@@ -262,45 +311,63 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
         }
 #pragma unroll
         for (int t = 0; t < NT; t++) {
-          const unsigned int right = __shfl_down_sync(SW_FULL, acc[t], 1);
-          UP[t][g] = acc[t];
-          UQ[t][g] = ((acc[t] >> 1) & 0x77777777u) | ((right << 3) & 0x88888888u);
+          const unsigned int w = acc[t].word();
+          const unsigned int right = __shfl_down_sync(SW_FULL, w, 1);
+#pragma unroll
+          for (int h = 0; h + 1 < SW_GROUPS; h++) { UP[t][h] = UP[t][h + 1]; UQ[t][h] = UQ[t][h + 1]; }
+          UP[t][SW_GROUPS - 1] = w;
+          UQ[t][SW_GROUPS - 1] = ((w >> 1) & 0x77777777u) | ((right << 3) & 0x88888888u);
         }
       }
       if (pl > 0) {
-        const long long k = k0 + pl - 1;
+        /* marching down, the plane just read is the cubes' lower face and the previous one their upper face */
+        const bool down = 0 != p.flip[2];
+        const long long k = down ? k1 + 1 - pl : k0 + pl - 1;
+        /* OR / AND over the 8 corners of each of my 32 cubes per group and iso-value */
+        unsigned int active[NT][SW_GROUPS], some = 0u;
 #pragma unroll
         for (int t = 0; t < NT; t++) {
+          unsigned int c_or[SW_GROUPS], c_and[SW_GROUPS];
 #pragma unroll
           for (int g = 0; g < SW_GROUPS; g++) {
-            /* OR / AND over the 8 corners of each of my 32 cubes */
-            const unsigned int lo_or = LP[t][g] | LQ[t][g], lo_and = LP[t][g] & LQ[t][g];
-            const unsigned int up_or = UP[t][g] | UQ[t][g], up_and = UP[t][g] & UQ[t][g];
-            const unsigned int z_or = lo_or | up_or, z_and = lo_and & up_and;
-            unsigned int nz_or = 0u, nz_and = 0u;             /* first row of the next group */
-            if (g + 1 < SW_GROUPS) {
-              nz_or = LP[t][g + 1] | LQ[t][g + 1] | UP[t][g + 1] | UQ[t][g + 1];
-              nz_and = LP[t][g + 1] & LQ[t][g + 1] & UP[t][g + 1] & UQ[t][g + 1];
-            }
-            const unsigned int any = z_or | __funnelshift_r(z_or, nz_or, 4);
-            const unsigned int all = z_and & __funnelshift_r(z_and, nz_and, 4);
-            const unsigned int active = any & ~all & valid[g];
-            const unsigned int who = __ballot_sync(SW_FULL, 0u != active);
-            if (0u != who) {
-              const unsigned int cnt = __popc(who);
-              if (fill + cnt > SW_STAGE) flush();
-              if (0u != active) {
-                unsigned int row8 = 0u;
-                if (g + 1 < SW_GROUPS) {
-                  row8 = (LP[t][g + 1] & 15u) | ((LQ[t][g + 1] & 15u) << 4) | ((UP[t][g + 1] & 15u) << 8) | ((UQ[t][g + 1] & 15u) << 12);
+            c_or[g] = LP[t][g] | LQ[t][g] | UP[t][g] | UQ[t][g];
+            c_and[g] = LP[t][g] & LQ[t][g] & UP[t][g] & UQ[t][g];
+          }
+#pragma unroll
+          for (int g = 0; g < SW_GROUPS; g++) {
+            const unsigned int n_or = g + 1 < SW_GROUPS ? c_or[g + 1] : 0u, n_and = g + 1 < SW_GROUPS ? c_and[g + 1] : 0u;
+            const unsigned int any = c_or[g] | __funnelshift_r(c_or[g], n_or, 4);      /* rows r and r+1 */
+            const unsigned int all = c_and[g] & __funnelshift_r(c_and[g], n_and, 4);
+            active[t][g] = any & ~all & valid[g];
+            some |= active[t][g];
+          }
+        }
+        if (__any_sync(SW_FULL, 0u != some)) {
+#pragma unroll
+          for (int t = 0; t < NT; t++) {
+#pragma unroll
+            for (int g = 0; g < SW_GROUPS; g++) {
+              const unsigned int who = __ballot_sync(SW_FULL, 0u != active[t][g]);
+              if (0u != who) {
+                const unsigned int cnt = __popc(who);
+                if (fill + cnt > SW_STAGE) flush();
+                if (0u != active[t][g]) {
+                  const unsigned int bp = down ? UP[t][g] : LP[t][g], bq = down ? UQ[t][g] : LQ[t][g];   /* z = k */
+                  const unsigned int tp = down ? LP[t][g] : UP[t][g], tq = down ? LQ[t][g] : UQ[t][g];   /* z = k + 1 */
+                  unsigned int row8 = 0u;
+                  if (g + 1 < SW_GROUPS) {
+                    const unsigned int bp8 = down ? UP[t][g + 1] : LP[t][g + 1], bq8 = down ? UQ[t][g + 1] : LQ[t][g + 1];
+                    const unsigned int tp8 = down ? LP[t][g + 1] : UP[t][g + 1], tq8 = down ? LQ[t][g + 1] : UQ[t][g + 1];
+                    row8 = (bp8 & 15u) | ((bq8 & 15u) << 4) | ((tp8 & 15u) << 8) | ((tq8 & 15u) << 12);
+                  }
+                  const unsigned int at = fill + __popc(who & ((1u << lane) - 1u));
+                  uint4 *dst = reinterpret_cast<uint4 *>(stage + at);
+                  dst[0] = make_uint4(bp, bq, tp, tq);
+                  dst[1] = make_uint4(active[t][g], row8, (unsigned int)(x0 + 4 * (long long)lane) | ((unsigned int)(j0 + SW_ROWS * g) << 16),
+                                      (unsigned int)k | (p.obj[t] << 16));
                 }
-                const unsigned int at = fill + __popc(who & ((1u << lane) - 1u));
-                uint4 *dst = reinterpret_cast<uint4 *>(stage + at);
-                dst[0] = make_uint4(LP[t][g], LQ[t][g], UP[t][g], UQ[t][g]);
-                dst[1] = make_uint4(active, row8, (unsigned int)(x0 + 4 * (long long)lane) | ((unsigned int)(j0 + SW_ROWS * g) << 16),
-                                    (unsigned int)k | (p.obj[t] << 16));
+                fill += cnt;
               }
-              fill += cnt;
             }
           }
         }
@@ -320,10 +387,78 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
 /*
  * records -> one list entry per cut cube: code:8 | i:16 | j:16 | k:16 | object:4
  * (corner numbering bit0 = +x, bit1 = +y, bit2 = +z, triangulate.c:15-19).
+ *
+ * SORTED: the entries are written nearest-first as a counting sort by view
+ * depth (C3D_DEPTH_BUCKETS slabs perpendicular to the screen normal).  The
+ * image does not depend on the order; the raster's occlusion test does: drawn
+ * front to back, most cubes behind the first surfaces are dropped before any
+ * triangle is built.  k_bucket_count histograms the records, k_bucket_scan
+ * turns the histogram into cursors, k_expand<true> scatters.
  */
-__global__ void __launch_bounds__(256) k_expand(const SweepRecord *__restrict__ records, const unsigned long long *__restrict__ nrecords,
+struct DepthOrder {
+  float near_depth, scale;          /* bucket = (near_depth - n.(p - cam)) * scale, clamped */
+};
+
+__device__ __forceinline__ unsigned int depth_bucket(const FrameParams &p, const DepthOrder &o, const unsigned int obj, const unsigned int x,
+                                                     const unsigned int j, const unsigned int k) {
+  const FieldView &f = p.view[obj];
+  const float rx = (float)__ldg(f.g[0] + x) - p.cull.cam[0];
+  const float ry = (float)__ldg(f.g[1] + j) - p.cull.cam[1];
+  const float rz = (float)__ldg(f.g[2] + k) - p.cull.cam[2];
+  const float nr = p.cull.n[0] * rx + p.cull.n[1] * ry + p.cull.n[2] * rz;
+  const float b = (o.near_depth - nr) * o.scale;
+  return (unsigned int)fminf(fmaxf(b, 0.f), (float)(C3D_DEPTH_BUCKETS - 1));    /* NaN -> 0 */
+}
+
+__global__ void __launch_bounds__(256) k_bucket_count(const __grid_constant__ FrameParams p, const DepthOrder o,
+                                                      const SweepRecord *__restrict__ records, const unsigned long long *__restrict__ nrecords,
+                                                      const unsigned long long rec_capacity, unsigned int *__restrict__ histogram) {
+  __shared__ unsigned int local[C3D_DEPTH_BUCKETS];
+  for (unsigned int b = threadIdx.x; b < C3D_DEPTH_BUCKETS; b += blockDim.x) local[b] = 0u;
+  __syncthreads();
+  unsigned long long n = *nrecords;
+  if (n > rec_capacity) n = rec_capacity;
+  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(records) + 2ull * q + 1ull);
+    atomicAdd(local + depth_bucket(p, o, b.w >> 16, b.z & 65535u, b.z >> 16, b.w & 65535u), (unsigned int)__popc(b.x));
+  }
+  __syncthreads();
+  for (unsigned int b = threadIdx.x; b < C3D_DEPTH_BUCKETS; b += blockDim.x) {
+    if (0u != local[b]) atomicAdd(histogram + b, local[b]);
+  }
+}
+
+/* one block: histogram -> start offsets behind what the list already holds; the list cursor moves past all buckets */
+__global__ void __launch_bounds__(1024) k_bucket_scan(const unsigned int *__restrict__ histogram, unsigned long long *__restrict__ cursors,
+                                                      unsigned long long *__restrict__ count) {
+  __shared__ unsigned long long part[1024];
+  constexpr unsigned int PER = C3D_DEPTH_BUCKETS / 1024;
+  unsigned long long mine = 0ull;
+  for (unsigned int q = 0; q < PER; q++) mine += histogram[threadIdx.x * PER + q];
+  part[threadIdx.x] = mine;
+  __syncthreads();
+  for (unsigned int d = 1; d < 1024; d <<= 1) {
+    const unsigned long long add = threadIdx.x >= d ? part[threadIdx.x - d] : 0ull;
+    __syncthreads();
+    part[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const unsigned long long first = *count;
+  unsigned long long at = first + part[threadIdx.x] - mine;
+  for (unsigned int q = 0; q < PER; q++) {
+    cursors[threadIdx.x * PER + q] = at;
+    at += histogram[threadIdx.x * PER + q];
+  }
+  __syncthreads();
+  if (1023u == threadIdx.x) *count = first + part[1023];
+}
+
+template <bool SORTED>
+__global__ void __launch_bounds__(256) k_expand(const __grid_constant__ FrameParams p, const DepthOrder o,
+                                                const SweepRecord *__restrict__ records, const unsigned long long *__restrict__ nrecords,
                                                 const unsigned long long rec_capacity, unsigned long long *__restrict__ list,
                                                 unsigned long long *__restrict__ count, const unsigned long long capacity,
+                                                unsigned long long *__restrict__ cursors,
                                                 unsigned long long *__restrict__ per_object, const unsigned int nobjects) {
   unsigned long long n = *nrecords;
   if (n > rec_capacity) n = rec_capacity;
@@ -339,25 +474,29 @@ __global__ void __launch_bounds__(256) k_expand(const SweepRecord *__restrict__ 
     }
     unsigned int active = b.x;
     const unsigned int mine = __popc(active);
-    unsigned int incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned int up = __shfl_up_sync(SW_FULL, incl, d);
-      if (lane >= (unsigned int)d) incl += up;
-    }
-    const unsigned int total = __shfl_sync(SW_FULL, incl, 31);
-    if (0u == total) continue;
+    const unsigned int x = b.z & 65535u, j = b.z >> 16, k = b.w & 65535u, obj = b.w >> 16;
     unsigned long long at = 0ull;
-    if (0u == lane) at = atomicAdd(count, (unsigned long long)total);
-    at = __shfl_sync(SW_FULL, at, 0) + (incl - mine);
+    if (SORTED) {
+      if (0u != mine) at = atomicAdd(cursors + depth_bucket(p, o, obj, x, j, k), (unsigned long long)mine);
+    } else {
+      unsigned int incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int up = __shfl_up_sync(SW_FULL, incl, d);
+        if (lane >= (unsigned int)d) incl += up;
+      }
+      const unsigned int total = __shfl_sync(SW_FULL, incl, 31);
+      if (0u == total) continue;
+      if (0u == lane) at = atomicAdd(count, (unsigned long long)total);
+      at = __shfl_sync(SW_FULL, at, 0) + (incl - mine);
+    }
     /* rows 0..8 of the four bit planes */
     const unsigned long long pl = a.x | ((unsigned long long)(b.y & 15u) << 32), ql = a.y | ((unsigned long long)((b.y >> 4) & 15u) << 32);
     const unsigned long long pu = a.z | ((unsigned long long)((b.y >> 8) & 15u) << 32), qu = a.w | ((unsigned long long)((b.y >> 12) & 15u) << 32);
-    const unsigned int x = b.z & 65535u, j = b.z >> 16, k = b.w & 65535u, obj = b.w >> 16;
     /* statistics: cut cubes per contour object */
-    for (unsigned int o = 0; o < nobjects; o++) {
-      const unsigned int sum = __reduce_add_sync(SW_FULL, obj == o ? mine : 0u);
-      if (0u == lane && 0u != sum) atomicAdd(per_object + o, (unsigned long long)sum);
+    for (unsigned int ob = 0; ob < nobjects; ob++) {
+      const unsigned int sum = __reduce_add_sync(SW_FULL, obj == ob ? mine : 0u);
+      if (0u == lane && 0u != sum) atomicAdd(per_object + ob, (unsigned long long)sum);
     }
     while (active) {
       const int bit = __ffs((int)active) - 1;
@@ -374,15 +513,15 @@ __global__ void __launch_bounds__(256) k_expand(const SweepRecord *__restrict__ 
 
 /* ---------------------------------------------------------------- launchers */
 
-template <typename T, int NT, int WARPS>
+template <typename T, int NT, int WARPS, int SW_SLOTS>
 static int launch_tiles(const TileSweepParams &p, const int sm_count, cudaStream_t s) {
   const size_t smem = (size_t)WARPS * (SW_SLOTS * SW_ROWS * 128 * sizeof(T) + SW_STAGE * sizeof(SweepRecord) + SW_SLOTS * 8);
   /* per device, so not cached in a static */
-  const cudaError_t err = cudaFuncSetAttribute(k_sweep_tiles<T, NT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const cudaError_t err = cudaFuncSetAttribute(k_sweep_tiles<T, NT, WARPS, SW_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (cudaSuccess != err) return (int)err;
   const unsigned int need = (p.ntiles + WARPS - 1) / WARPS;
   const unsigned int blocks = need < (unsigned int)sm_count ? need : (unsigned int)sm_count;
-  k_sweep_tiles<T, NT, WARPS><<<blocks, WARPS * 32, smem, s>>>(p);
+  k_sweep_tiles<T, NT, WARPS, SW_SLOTS><<<blocks, WARPS * 32, smem, s>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -392,7 +531,7 @@ extern "C" int c3d_k_sweep_tiles_ok(const FieldView *f) {
 }
 
 extern "C" int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nthr, const double *thr, const float *thr_ge, const unsigned int *obj,
-                                 unsigned int *tile_cursor, void *records, unsigned long long *count, unsigned long long capacity,
+                                 const int flip[3], unsigned int *tile_cursor, void *records, unsigned long long *count, unsigned long long capacity,
                                  int sm_count, cudaStream_t s) {
   if (nthr < 1 || nthr > C3D_SWEEP_MAX_THR) return (int)cudaErrorInvalidValue;
   TileSweepParams p;
@@ -404,6 +543,7 @@ extern "C" int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nt
     const int u = t < nthr ? t : 0;
     p.thr[t] = thr[u]; p.thr_ge[t] = thr_ge[u]; p.obj[t] = obj[u];
   }
+  for (int d = 0; d < 3; d++) p.flip[d] = (NULL != flip && 0 != flip[d]) ? 1 : 0;
   p.ilo = r->lo[0]; p.ihi = r->hi[0];
   p.jlo = r->lo[1]; p.jhi = r->hi[1];
   p.klo = r->lo[2]; p.khi = r->hi[2];
@@ -412,7 +552,7 @@ extern "C" int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nt
   p.nyt = (int)((p.jhi - p.jlo + SW_YCUBES) / SW_YCUBES);
   const long long nk = p.khi - p.klo + 1;
   /* planes per tile: enough tiles for ~6 per resident warp (dynamic hand-out evens the tail), at most 1/32 z re-reads */
-  const int warps = 4 == f->elem_bytes ? 16 : 8;
+  const int warps = 4 == f->elem_bytes ? (nthr >= 3 ? 12 : 16) : 8;
   const long long per_chunk = (long long)p.nxt * p.nyt;
   const long long want_tiles = 6ll * warps * sm_count;
   long long chunks = (want_tiles + per_chunk - 1) / per_chunk;
@@ -430,23 +570,36 @@ extern "C" int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nt
   if (cudaSuccess != err) return (int)err;
   if (4 == f->elem_bytes) {
     switch (nthr) {
-      case 1: return launch_tiles<float, 1, 16>(p, sm_count, s);
-      case 2: return launch_tiles<float, 2, 16>(p, sm_count, s);
-      case 3: return launch_tiles<float, 3, 16>(p, sm_count, s);
-      default: return launch_tiles<float, 4, 16>(p, sm_count, s);
+      case 1: return launch_tiles<float, 1, 16, 3>(p, sm_count, s);
+      case 2: return launch_tiles<float, 2, 16, 3>(p, sm_count, s);
+      case 3: return launch_tiles<float, 3, 12, 4>(p, sm_count, s);
+      default: return launch_tiles<float, 4, 12, 4>(p, sm_count, s);
     }
   }
   switch (nthr) {
-    case 1: return launch_tiles<double, 1, 8>(p, sm_count, s);
-    case 2: return launch_tiles<double, 2, 8>(p, sm_count, s);
-    case 3: return launch_tiles<double, 3, 8>(p, sm_count, s);
-    default: return launch_tiles<double, 4, 8>(p, sm_count, s);
+    case 1: return launch_tiles<double, 1, 8, 3>(p, sm_count, s);
+    case 2: return launch_tiles<double, 2, 8, 3>(p, sm_count, s);
+    case 3: return launch_tiles<double, 3, 8, 3>(p, sm_count, s);
+    default: return launch_tiles<double, 4, 8, 3>(p, sm_count, s);
   }
 }
 
-extern "C" int c3d_k_expand(const void *records, const unsigned long long *nrecords, unsigned long long rec_capacity, unsigned long long *list,
-                            unsigned long long *count, unsigned long long capacity, unsigned long long *per_object, unsigned int nobjects,
-                            int sm_count, cudaStream_t s) {
-  k_expand<<<sm_count * 8, 256, 0, s>>>(static_cast<const SweepRecord *>(records), nrecords, rec_capacity, list, count, capacity, per_object, nobjects);
+extern "C" int c3d_k_expand(const FrameParams *fp, int sorted, float near_depth, float far_depth,
+                            const void *records, const unsigned long long *nrecords, unsigned long long rec_capacity, unsigned long long *list,
+                            unsigned long long *count, unsigned long long capacity, unsigned int *histogram, unsigned long long *cursors,
+                            unsigned long long *per_object, unsigned int nobjects, int sm_count, cudaStream_t s) {
+  const SweepRecord *rec = static_cast<const SweepRecord *>(records);
+  DepthOrder o;
+  o.near_depth = near_depth;
+  o.scale = (near_depth > far_depth) ? (float)C3D_DEPTH_BUCKETS / (near_depth - far_depth) : 0.f;
+  if (sorted) {
+    const cudaError_t err = cudaMemsetAsync(histogram, 0, C3D_DEPTH_BUCKETS * sizeof(unsigned int), s);
+    if (cudaSuccess != err) return (int)err;
+    k_bucket_count<<<sm_count * 4, 256, 0, s>>>(*fp, o, rec, nrecords, rec_capacity, histogram);
+    k_bucket_scan<<<1, 1024, 0, s>>>(histogram, cursors, count);
+    k_expand<true><<<sm_count * 8, 256, 0, s>>>(*fp, o, rec, nrecords, rec_capacity, list, count, capacity, cursors, per_object, nobjects);
+  } else {
+    k_expand<false><<<sm_count * 8, 256, 0, s>>>(*fp, o, rec, nrecords, rec_capacity, list, count, capacity, cursors, per_object, nobjects);
+  }
   return (int)cudaGetLastError();
 }

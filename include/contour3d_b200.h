@@ -84,6 +84,7 @@ typedef struct {
   uint64_t sweep_bytes[16];      /* algorithmic bytes of each sweep launch (elem_bytes x points of the extended array) */
   uint32_t sweep_thresholds[16]; /* iso-values classified by each sweep launch */
   uint64_t active_cubes[16];     /* per contour object, rendered range */
+  uint64_t culled_cubes;         /* cut cubes the raster skipped because the z-buffer already hid them */
   uint32_t nsweeps;
   uint32_t ncontours;
   uint32_t launches;             /* kernels launched by this library in the frame */
