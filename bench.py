@@ -55,12 +55,24 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.lines, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+
+            def pump():
+                for line in self.proc.stdout:
+                    self.lines.append((time.time(), line))
+
+            self.thread = threading.Thread(target=pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
@@ -74,7 +86,9 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], 0, set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.lines:
+        inside = [l for (ts, l) in self.lines if self.t0 is not None and self.t1 is not None and self.t0 - 0.02 <= ts <= self.t1 + 0.05]
+        window = "timed region" if inside else "warm-up + timed region"
+        for line in (inside or [l for (_, l) in self.lines]):
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -86,7 +100,7 @@ class ClockSampler:
             for name, flag in zip(names, parts[3:7]):
                 if flag.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def sample_case(field_crop: np.ndarray, size: int, width: int, height: int, path: str):
@@ -107,7 +121,7 @@ def run_reference_on(case: str, steps: int, warmup: int, cores: int):
 
     ranks = max(1, cores)
     out = os.path.join(os.path.dirname(case), "ref.ppm")
-    res = reference.run_case(case, out, ranks=ranks, dims=(1, ranks, 1), repeat=warmup + steps)
+    res = reference.run_case(case, out, ranks=ranks, dims=(1, ranks, 1), repeat=steps, warmup=warmup)
     return res
 
 
@@ -213,13 +227,14 @@ def ours(args):
         ctx.synchronize()
 
     # ---- device-resident arm ----
-    for _ in range(args.warmup):
-        ctx.render(scene, contours, lines, want_rgb=False)
     stage_sum, launches = {}, 0
     sweep_ms, sweep_bytes = [], []
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:          # nvidia-smi needs ~0.2 s to start: it runs through the warm-up too
+        for _ in range(args.warmup):
+            ctx.render(scene, contours, lines, want_rgb=False)
+        barrier()
+        clocks.mark_start()
         start.record(stream)
         for _ in range(args.steps):
             ctx.render(scene, contours, lines, want_rgb=False)
@@ -231,6 +246,8 @@ def ours(args):
                 stage_sum[k] = stage_sum.get(k, 0.0) + t[k]
         end.record(stream)
         barrier()
+        clocks.mark_end()
+        time.sleep(0.05)
     elapsed_ms = start.elapsed_time(end)
     tt = torch.tensor([elapsed_ms], device="cuda")
     if world > 1:
@@ -253,7 +270,7 @@ def ours(args):
     tfile = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tfile):
         traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
-    roofline = {"kernel": f"k_sweep_tiles<float,{t['sweep_thresholds'][0]},16> (one pass classifies {t['sweep_thresholds'][0]} iso-values)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"kernel": f"k_sweep_tiles<float,{t['sweep_thresholds'][0]},...> (c3d_sweep.cu; one pass classifies {t['sweep_thresholds'][0]} iso-values)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": float(np.mean(sweep_bytes)), "ms_per_launch": sweep_avg_ms,
                 "share_of_step": stage_sum["sweep"] / stage_sum["total"]}
 
@@ -325,7 +342,7 @@ def e2e_arm(args, ctx, field, grids, scene, lines, rank, world, barrier):
     voxels = size ** 3 * len(ISOVALUES)
     return {"value": voxels * steps / dt / 1e9, "unit": "Gvoxel/s", "frames_per_s": steps / dt, "ms_per_step": dt / steps * 1e3, "steps": steps,
             "h2d_bytes_per_step": int(host.nbytes + 3 * 8 * size), "d2h_bytes_per_step": int(3 * scene["width"] * scene["height"]) if rank == 0 else 0,
-            "path": "contour3d_execute(host double arrays, pinned) -> PPM in /dev/shm; wall clock incl. cudaMalloc/free of the field"}
+            "path": "contour3d_execute(host double arrays, pinned) -> PPM in /dev/shm; wall clock around the call, H2D of the array and D2H of the image inside"}
 
 
 def cpu_baseline(args, ctx, field, size, width, height):

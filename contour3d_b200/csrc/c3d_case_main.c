@@ -2,7 +2,7 @@
  * c3d_case_main.c -- a small MPI program around the PUBLIC API only
  * (contour3d_execute + SimpleDecomp getters): renders a "case file".
  *
- *   [MINIMPI_NP=<ranks>] c3d_case <case.bin> <out.ppm> [dim_y dim_z] [repeat]
+ *   [MINIMPI_NP=<ranks>] c3d_case <case.bin> <out.ppm> [dim_y dim_z] [repeat] [warmup]
  *
  * Because it touches nothing but include/contour3d.h it is built twice from
  * this one source: against libcontour3d_b200.so (-> contour3d_b200/c3d_case,
@@ -49,7 +49,7 @@ static double now(void) {
 
 int main(int argc, char **argv) {
   if (argc < 3) {
-    fprintf(stderr, "usage: %s case.bin out.ppm [dim_y dim_z] [repeat]\n", argv[0]);
+    fprintf(stderr, "usage: %s case.bin out.ppm [dim_y dim_z] [repeat] [warmup]\n", argv[0]);
     return 2;
   }
   MPI_Init(NULL, NULL);
@@ -63,6 +63,7 @@ int main(int argc, char **argv) {
     dims[2] = (size_t)atol(argv[4]);
   }
   const int repeat = argc >= 6 ? atoi(argv[5]) : 1;
+  const int warmup = argc >= 7 ? atoi(argv[6]) : 0;      /* untimed calls before the `repeat` timed ones */
   sdecomp_info_t *info = NULL;
   if (0 != sdecomp.construct(MPI_COMM_WORLD, 3, dims, (bool[3]){false, false, false}, &info)) return 1;
   FILE *fp = fopen(argv[1], "rb");
@@ -139,13 +140,14 @@ int main(int argc, char **argv) {
   const size_t screen[2] = {h.width, h.height};
   double best = 1.e300, sum = 0.;
   int status = 0;
-  for (int it = 0; it < repeat; it++) {
+  for (int it = -warmup; it < repeat; it++) {
     MPI_Barrier(MPI_COMM_WORLD);
     const double t0 = now();
     status |= contour3d_execute(info, &camera, &look_at, &light, screen, &center, local, &bg,
                                 h.ncontours, cobjs, h.nlines, lobjs, argv[2]);
     double dt = now() - t0;
     MPI_Allreduce(MPI_IN_PLACE, &dt, 1, MPI_DOUBLE, MPI_MAX, MPI_COMM_WORLD);
+    if (it < 0) continue;
     if (dt < best) best = dt;
     sum += dt;
   }

@@ -140,6 +140,8 @@ struct c3d_context {
   void *halo_buf;
   size_t halo_cap;
   cudaEvent_t ev[EV_COUNT];
+  cudaEvent_t ev_upload[2 * C3D_MAX_OBJECTS];   /* start/stop pairs of the uploads since the last frame */
+  int nuploads;
   cudaEvent_t ev_sweep[C3D_MAX_OBJECTS + 1];
   c3d_timings_t last;
 };
@@ -180,6 +182,7 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (int e = 0; e < EV_COUNT; e++) CUDA_OK(cudaEventCreate(&ctx->ev[e]));
   for (int e = 0; e <= C3D_MAX_OBJECTS; e++) CUDA_OK(cudaEventCreate(&ctx->ev_sweep[e]));
+  for (int e = 0; e < 2 * C3D_MAX_OBJECTS; e++) CUDA_OK(cudaEventCreate(&ctx->ev_upload[e]));
   /* case tables -> device */
   c3d_tables_t *host_tab = (c3d_tables_t *)malloc(sizeof(c3d_tables_t));
   if (NULL == host_tab) return c3d_error("out of host memory");
@@ -224,6 +227,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   cudaFree(ctx->views_dev); cudaFree(ctx->lines_dev); cudaFree(ctx->grids_dev); cudaFree(ctx->halo_buf);
   for (int e = 0; e < EV_COUNT; e++) cudaEventDestroy(ctx->ev[e]);
   for (int e = 0; e <= C3D_MAX_OBJECTS; e++) cudaEventDestroy(ctx->ev_sweep[e]);
+  for (int e = 0; e < 2 * C3D_MAX_OBJECTS; e++) cudaEventDestroy(ctx->ev_upload[e]);
   cudaStreamDestroy(ctx->stream);
   free(ctx);
   return 0;
@@ -326,15 +330,27 @@ static inline char *interior_ptr(const c3d_field *f) {
 extern "C" int c3d_field_upload(c3d_context_t *ctx, c3d_field_t *f, const void *local) {
   if (NULL == ctx || NULL == f || NULL == local) return c3d_error("c3d_field_upload: NULL argument");
   CUDA_OK(cudaSetDevice(ctx->device));
-  cudaMemcpy3DParms p;
-  memset(&p, 0, sizeof(p));
   const size_t eb = (size_t)f->elem_bytes;
-  p.srcPtr = make_cudaPitchedPtr((void *)local, f->mysizes[0] * eb, f->mysizes[0] * eb, f->mysizes[1]);
-  p.dstPtr = make_cudaPitchedPtr(f->data, f->ext[0] * eb, f->ext[0] * eb, f->ext[1]);
-  p.dstPos = make_cudaPos(f->lo[0] * eb, f->lo[1], f->lo[2]);
-  p.extent = make_cudaExtent(f->mysizes[0] * eb, f->mysizes[1], f->mysizes[2]);
-  p.kind = cudaMemcpyDefault;
-  CUDA_OK(cudaMemcpy3DAsync(&p, ctx->stream));
+  const bool timed = ctx->nuploads < C3D_MAX_OBJECTS;
+  if (timed) CUDA_OK(cudaEventRecord(ctx->ev_upload[2 * ctx->nuploads], ctx->stream));
+  if (f->mysizes[0] == f->ext[0] && f->mysizes[1] == f->ext[1]) {
+    /* x and y undivided (one rank, or z slabs): the interior is one contiguous block -> a single flat copy,
+       which runs at the link rate; the pitched 3-D form below pays per-row descriptors */
+    CUDA_OK(cudaMemcpyAsync(interior_ptr(f), local, f->mysizes[0] * f->mysizes[1] * f->mysizes[2] * eb, cudaMemcpyDefault, ctx->stream));
+  } else {
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    p.srcPtr = make_cudaPitchedPtr((void *)local, f->mysizes[0] * eb, f->mysizes[0] * eb, f->mysizes[1]);
+    p.dstPtr = make_cudaPitchedPtr(f->data, f->ext[0] * eb, f->ext[0] * eb, f->ext[1]);
+    p.dstPos = make_cudaPos(f->lo[0] * eb, f->lo[1], f->lo[2]);
+    p.extent = make_cudaExtent(f->mysizes[0] * eb, f->mysizes[1], f->mysizes[2]);
+    p.kind = cudaMemcpyDefault;
+    CUDA_OK(cudaMemcpy3DAsync(&p, ctx->stream));
+  }
+  if (timed) {
+    CUDA_OK(cudaEventRecord(ctx->ev_upload[2 * ctx->nuploads + 1], ctx->stream));
+    ctx->nuploads++;
+  }
   f->halo_valid = (1 == ctx->size);
   return 0;
 }
@@ -814,6 +830,11 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   c3d_timings_t *t = &ctx->last;
   memset(t, 0, sizeof(*t));
   auto ms = [&](int a, int b) { float v = 0.f; cudaEventElapsedTime(&v, ctx->ev[a], ctx->ev[b]); return v; };
+  for (int u = 0; u < ctx->nuploads; u++) {
+    float v = 0.f;
+    if (cudaSuccess == cudaEventElapsedTime(&v, ctx->ev_upload[2 * u], ctx->ev_upload[2 * u + 1])) t->upload += v;
+  }
+  ctx->nuploads = 0;
   t->halo = ms(EV_START, EV_HALO);
   t->clear = ms(EV_HALO, EV_CLEAR);
   t->sweep = ms(EV_CLEAR, EV_SWEEP);

@@ -31,6 +31,18 @@
 static c3d_context_t *g_ctx = NULL;
 static int g_rank = -1, g_size = -1;
 
+/* Device arrays kept between calls.  A solver calls contour3d_execute() once per output step with arrays of
+   the same shape; allocating and freeing gigabytes of device memory each time costs more than the frame.
+   The contents are never reused (every call uploads afresh), so nothing the caller can observe is retained.
+   CONTOUR3D_NO_CACHE=1 restores allocate-per-call. */
+typedef struct {
+  c3d_field_t *field;
+  size_t glsizes[CONTOUR3D_NDIMS];
+  c3d_decomp_t decomp;
+  int in_use;
+} cached_field_t;
+static cached_field_t g_cache[MAX_OBJECTS];
+
 static int log_error(const char *fmt, ...) {
   va_list args;
   va_start(args, fmt);
@@ -43,6 +55,10 @@ static int log_error(const char *fmt, ...) {
 }
 
 static void release_context(void) {
+  for (size_t n = 0; n < MAX_OBJECTS; n++) {
+    if (NULL != g_cache[n].field) c3d_field_destroy(g_ctx, g_cache[n].field);
+    memset(&g_cache[n], 0, sizeof(g_cache[n]));
+  }
   if (NULL != g_ctx) {
     c3d_context_destroy(g_ctx);
     g_ctx = NULL;
@@ -78,6 +94,53 @@ static int acquire_context(const sdecomp_info_t *info) {
   return 0;
 }
 
+static int cache_enabled(void) {
+  const char *env = getenv("CONTOUR3D_NO_CACHE");
+  return !(NULL != env && '\0' != *env && '0' != *env);
+}
+
+/* a device array of this shape: from the cache when one is free, else new (and cached when there is room) */
+static int acquire_field(const c3d_decomp_t *decomp, const size_t glsizes[CONTOUR3D_NDIMS], c3d_field_t **field, int *cached) {
+  *cached = 0;
+  if (cache_enabled()) {
+    for (size_t n = 0; n < MAX_OBJECTS; n++) {
+      cached_field_t *c = &g_cache[n];
+      if (NULL != c->field && !c->in_use && 0 == memcmp(c->glsizes, glsizes, sizeof(c->glsizes)) && 0 == memcmp(&c->decomp, decomp, sizeof(*decomp))) {
+        c->in_use = 1;
+        *field = c->field;
+        *cached = 1;
+        return 0;
+      }
+    }
+  }
+  if (0 != c3d_field_create(g_ctx, decomp, glsizes, (int)sizeof(double), field)) {
+    /* out of device memory? drop what the cache holds and try once more */
+    int dropped = 0;
+    for (size_t n = 0; n < MAX_OBJECTS; n++) {
+      if (NULL != g_cache[n].field && !g_cache[n].in_use) {
+        c3d_field_destroy(g_ctx, g_cache[n].field);
+        memset(&g_cache[n], 0, sizeof(g_cache[n]));
+        dropped = 1;
+      }
+    }
+    if (!dropped || 0 != c3d_field_create(g_ctx, decomp, glsizes, (int)sizeof(double), field)) return 1;
+  }
+  if (cache_enabled()) {
+    for (size_t n = 0; n < MAX_OBJECTS; n++) {
+      cached_field_t *c = &g_cache[n];
+      if (NULL == c->field) {
+        c->field = *field;
+        memcpy(c->glsizes, glsizes, sizeof(c->glsizes));
+        c->decomp = *decomp;
+        c->in_use = 1;
+        *cached = 1;
+        break;
+      }
+    }
+  }
+  return 0;
+}
+
 static int is_identity(contour3d_vector_t (*converter)(const contour3d_vector_t), const double probes[][3], const size_t nprobes) {
   if (NULL == converter) return 1;
   for (size_t n = 0; n < nprobes; n++) {
@@ -105,6 +168,7 @@ int contour3d_execute (
 ) {
   (void)camera_look_at; /* stored but never read by the reference either (src/contour3d/main.c:17-20) */
   c3d_field_t *fields[MAX_OBJECTS] = {NULL};
+  int cached[MAX_OBJECTS] = {0};
   c3d_contour_t contours[MAX_OBJECTS];
   c3d_line_t *lines = NULL;
   int status = 1;
@@ -172,7 +236,7 @@ int contour3d_execute (
     if (same < n) {
       contours[n].field = contours[same].field;
     } else {
-      if (0 != c3d_field_create(g_ctx, &decomp, obj->glsizes, (int)sizeof(double), &fields[n])) {
+      if (0 != acquire_field(&decomp, obj->glsizes, &fields[n], &cached[n])) {
         log_error("failed to extend domain");
         goto done;
       }
@@ -215,7 +279,16 @@ int contour3d_execute (
 done:
   /* nothing is retained after return, like the reference (contour/main.c:114-117) */
   for (size_t n = 0; n < num_contours && n < MAX_OBJECTS; n++) {
-    if (NULL != fields[n]) c3d_field_destroy(g_ctx, fields[n]);
+    if (NULL != fields[n] && !cached[n]) c3d_field_destroy(g_ctx, fields[n]);
+  }
+  for (size_t n = 0; n < MAX_OBJECTS; n++) g_cache[n].in_use = 0;
+  {
+    const char *env = getenv("CONTOUR3D_VERBOSE");
+    c3d_timings_t t;
+    if (0 == status && NULL != env && '\0' != *env && '0' != *env && 0 == c3d_frame_timings(g_ctx, &t)) {
+      fprintf(stderr, "[CONTOUR3D] upload %.2f sweep %.2f expand %.2f raster %.2f shade %.2f reduce %.2f download %.2f | device total %.2f ms\n",
+              t.upload, t.sweep, t.expand, t.raster, t.shade, t.reduce, t.download, t.upload + t.total);
+    }
   }
   free(lines);
   return status;

@@ -61,14 +61,14 @@ def tessellate(field, grids, threshold) -> np.ndarray:
     return out
 
 
-def run_case(case_path: str, out_ppm: str, ranks: int = 1, dims=None, repeat: int = 1, timeout=None) -> dict:
+def run_case(case_path: str, out_ppm: str, ranks: int = 1, dims=None, repeat: int = 1, warmup: int = 0, timeout=None) -> dict:
     """contour3d_execute of the reference on a case file, `ranks` processes (fork mode of compat/minimpi)."""
     cmd = [REF_DRIVER, case_path, out_ppm]
     if dims is not None:
         cmd += [str(dims[1]), str(dims[2])]
-        if repeat != 1:
-            cmd += [str(repeat)]
-    elif repeat != 1:
+        if repeat != 1 or warmup:
+            cmd += [str(repeat), str(warmup)]
+    elif repeat != 1 or warmup:
         raise ValueError("repeat needs explicit dims")
     env = dict(os.environ)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT", "MASTER_ADDR"):
