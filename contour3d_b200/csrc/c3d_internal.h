@@ -92,6 +92,7 @@ struct FrameParams {
   CullCam cull;
   DevTables tab;
   const double *px, *py;     /* pixel-centre coordinates, render.c:94-98, tabulated once per screen size */
+  const float *pxf, *pyf;    /* the same rounded to fp32 (conservative coverage pre-test) */
   unsigned int ncontours;
   FieldView view[C3D_MAX_OBJECTS];
 };
@@ -102,7 +103,7 @@ extern "C" {
 
 /* launchers (c3d_kernels.cu); all asynchronous on `s`, return cudaError_t as int */
 int c3d_k_clear(Pixel *canvas, size_t npix, cudaStream_t s);
-int c3d_k_pixel_tables(double *px, double *py, long long w, long long h, cudaStream_t s);
+int c3d_k_pixel_tables(double *px, double *py, float *pxf, float *pyf, long long w, long long h, cudaStream_t s);
 int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int obj, unsigned long long *list, unsigned long long *count,
                 unsigned long long capacity, int sm_count, cudaStream_t s);
 /* tiled bulk-copy sweep (c3d_sweep.cu): needs 16-byte aligned rows; up to C3D_SWEEP_MAX_THR iso-values per launch */

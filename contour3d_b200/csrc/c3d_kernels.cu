@@ -15,6 +15,7 @@
  * File:line references are to NaokiHori/Contour3D @ c66854e.
  */
 #include <float.h>
+#include <stdlib.h>
 #include "c3d_device.cuh"
 
 /* ------------------------------------------------------------------ clear */
@@ -34,17 +35,19 @@ extern "C" int c3d_k_clear(Pixel *canvas, size_t npix, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-/* pixel-centre coordinates of every column and row (render.c:94-98), once per screen size */
-__global__ void k_pixel_tables(double *__restrict__ px, double *__restrict__ py, const long long w, const long long h) {
+/* pixel-centre coordinates of every column and row (render.c:94-98), once per screen size; the float copies
+   feed the conservative fp32 coverage pre-test of the raster */
+__global__ void k_pixel_tables(double *__restrict__ px, double *__restrict__ py, float *__restrict__ pxf, float *__restrict__ pyf,
+                               const long long w, const long long h) {
   const double W = (double)w, H = (double)h;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < w + h; q += (long long)gridDim.x * blockDim.x) {
-    if (q < w) px[q] = pixel_centre(q, W);
-    else py[q - w] = pixel_centre(q - w, H);
+    if (q < w) { px[q] = pixel_centre(q, W); pxf[q] = (float)px[q]; }
+    else { py[q - w] = pixel_centre(q - w, H); pyf[q - w] = (float)py[q - w]; }
   }
 }
 
-extern "C" int c3d_k_pixel_tables(double *px, double *py, long long w, long long h, cudaStream_t s) {
-  k_pixel_tables<<<64, 256, 0, s>>>(px, py, w, h);
+extern "C" int c3d_k_pixel_tables(double *px, double *py, float *pxf, float *pyf, long long w, long long h, cudaStream_t s) {
+  k_pixel_tables<<<64, 256, 0, s>>>(px, py, pxf, pyf, w, h);
   return (int)cudaGetLastError();
 }
 
@@ -291,25 +294,53 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
   if (!setup_triangle(p.cam, v, t)) return;
   const unsigned long long mykey = ((unsigned long long)(obj + 1u) << C3D_KEY_OBJ_SHIFT)
                                  | ((unsigned long long)k << 36) | ((unsigned long long)j << 20) | ((unsigned long long)i << 4) | s;
-  for (long long j0 = t.jmin; j0 <= t.jmax; j0 += 8) {
-    const int nj = (int)(t.jmax - j0 < 7 ? t.jmax - j0 : 7);
-    for (long long i0 = t.imin; i0 <= t.imax; i0 += 8) {
-      const int ni = (int)(t.imax - i0 < 7 ? t.imax - i0 : 7);
-      unsigned long long covered = 0ull;
+  /*
+   * Coverage in two steps.  Most pixels of the +-1 pixel box are far outside the triangle, so each is first
+   * tested with the three edge functions in fp32 and dropped when one of them is below -tol, tol being a
+   * rigorous bound of the fp32 evaluation error (inputs rounded to 2^-24, four rounded operations:
+   * <= 5.01 * 2^-24 * [(|px| + |ax|) |ey| + (|py| + |ay|) |ex|], taken as 4e-7 * [...] with |px|, |py| <= 0.5)
+   * plus the reference's own slack: w < -1e-8 <=> sign(area) E < -1e-8 |area| (render.c:102-115).  A dropped
+   * pixel is therefore outside for the exact test too; everything else is decided by the exact fp64 test below.
+   */
+  float fax[3], fay[3], fex[3], fey[3], ntol[3];
+  {
+    const double sgn = t.area_inv < 0. ? -1. : 1.;
+    const double slack = 1.0001e-8 / fabs(t.area_inv);
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const V3 &a = t.q[(m + 1) % 3];
+      fax[m] = (float)a.x; fay[m] = (float)a.y;
+      fex[m] = (float)(sgn * t.ex[m]); fey[m] = (float)(sgn * t.ey[m]);
+      const double tol = 4.e-7 * ((0.5 + fabs(a.x)) * fabs(t.ey[m]) + (0.5 + fabs(a.y)) * fabs(t.ex[m])) + slack;
+      ntol[m] = -((float)tol * 1.000001f + 1.e-37f);       /* NaN / inf propagate: then nothing is dropped */
+    }
+  }
+  const int jmin = (int)t.jmin, jmax = (int)t.jmax, imin = (int)t.imin, imax = (int)t.imax;
+  for (int j0 = jmin; j0 <= jmax; j0 += 4) {
+    const int nj = min(jmax - j0, 3);
+    for (int i0 = imin; i0 <= imax; i0 += 8) {
+      const int ni = min(imax - i0, 7);
+      unsigned int maybe = 0u;
       for (int dj = 0; dj <= nj; dj++) {
-        const double py = __ldg(p.py + j0 + dj);
-        for (int di = 0; di <= ni; di++) {
-          double w[3];
-          if (pixel_weights(t, __ldg(p.px + i0 + di), py, w)) covered |= 1ull << (dj * 8 + di);
+        const float py = __ldg(p.pyf + j0 + dj);
+        const float dy0 = py - fay[0], dy1 = py - fay[1], dy2 = py - fay[2];
+        unsigned int bit = 1u << (8 * dj);
+        for (int di = 0; di <= ni; di++, bit <<= 1) {
+          const float px = __ldg(p.pxf + i0 + di);
+          const float e0 = (px - fax[0]) * fey[0] - dy0 * fex[0];
+          const float e1 = (px - fax[1]) * fey[1] - dy1 * fex[1];
+          const float e2 = (px - fax[2]) * fey[2] - dy2 * fex[2];
+          if (!(e0 < ntol[0] || e1 < ntol[1] || e2 < ntol[2])) maybe |= bit;
         }
       }
-      while (covered) {
-        const int bit = __ffsll((long long)covered) - 1;
-        covered &= covered - 1ull;
-        const long long pi = i0 + (bit & 7), pj = j0 + (bit >> 3);
+      while (maybe) {
+        const int b = __ffs((int)maybe) - 1;
+        maybe &= maybe - 1u;
+        const long long pi = i0 + (b & 7), pj = j0 + (b >> 3);
         double w[3];
-        pixel_weights(t, __ldg(p.px + pi), __ldg(p.py + pj), w);
-        submit_fragment(canvas + pj * p.cam.w + pi, ord_of(pixel_depth(t, w)), mykey);
+        if (pixel_weights(t, __ldg(p.px + pi), __ldg(p.py + pj), w)) {
+          submit_fragment(canvas + pj * p.cam.w + pi, ord_of(pixel_depth(t, w)), mykey);
+        }
       }
     }
   }
@@ -376,7 +407,8 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
   return true;
 }
 
-__global__ void __launch_bounds__(128) k_raster(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ list,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ list,
                                                 const unsigned long long *__restrict__ count, const unsigned long long capacity,
                                                 Pixel *__restrict__ canvas, unsigned long long *__restrict__ culled) {
   __shared__ unsigned long long s_entry[4][32];
@@ -427,7 +459,16 @@ __global__ void __launch_bounds__(128) k_raster(const __grid_constant__ FramePar
 
 extern "C" int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const unsigned long long *count, unsigned long long capacity,
                             Pixel *canvas, unsigned long long *culled, int sm_count, cudaStream_t s) {
-  k_raster<<<sm_count * 8, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
+  /* resident blocks per SM: the kernel is bound by dependent fp64 chains, so more warps help until spills hurt (tuned by measurement) */
+  static int occ = -1;
+  if (occ < 0) {
+    const char *env = getenv("CONTOUR3D_RASTER_OCC");
+    occ = (NULL != env && '\0' != *env) ? atoi(env) : 5;
+  }
+  if (occ >= 8) k_raster<8><<<sm_count * 16, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
+  else if (occ >= 6) k_raster<6><<<sm_count * 12, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
+  else if (occ >= 5) k_raster<5><<<sm_count * 10, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
+  else k_raster<4><<<sm_count * 8, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
   return (int)cudaGetLastError();
 }
 

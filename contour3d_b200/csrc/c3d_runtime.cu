@@ -530,8 +530,10 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
     cudaFree(ctx->pixel_xy);
     ctx->pixel_xy = NULL;
     ctx->table_w = ctx->table_h = 0;
-    CUDA_OK(cudaMalloc(&ctx->pixel_xy, (w + h) * sizeof(double)));
-    LAUNCH_OK(c3d_k_pixel_tables(ctx->pixel_xy, ctx->pixel_xy + w, (long long)w, (long long)h, ctx->stream));
+    /* doubles for w columns + h rows, then the same as floats */
+    CUDA_OK(cudaMalloc(&ctx->pixel_xy, (w + h) * (sizeof(double) + sizeof(float))));
+    float *as_float = (float *)(ctx->pixel_xy + w + h);
+    LAUNCH_OK(c3d_k_pixel_tables(ctx->pixel_xy, ctx->pixel_xy + w, as_float, as_float + w, (long long)w, (long long)h, ctx->stream));
     ctx->table_w = w;
     ctx->table_h = h;
   }
@@ -626,6 +628,8 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   fp.tab = ctx->tab;
   fp.px = ctx->pixel_xy;
   fp.py = ctx->pixel_xy + scene->width;
+  fp.pxf = (const float *)(ctx->pixel_xy + scene->width + scene->height);
+  fp.pyf = fp.pxf + scene->width;
   fp.ncontours = (unsigned int)nc;
   FieldView *views = fp.view;
   {
