@@ -71,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cc = "mpicc" if have_real_mpi() else "gcc"
     mpi_inc = [] if have_real_mpi() else ["-I", MINIMPI]
     objs = []
-    for name in ("c3d_kernels.cu", "c3d_sweep.cu", "c3d_runtime.cu"):
+    for name in ("c3d_kernels.cu", "c3d_sweep.cu", "c3d_shade.cu", "c3d_runtime.cu"):
         src = os.path.join(CSRC, name)
         obj = os.path.join(OBJ, name + ".o")
         if force or _newer(obj, [src] + headers):

@@ -126,7 +126,7 @@ __device__ __forceinline__ void face_normal(const V3 v[3], V3 &fn, double &area)
 
 /* add area * face_normal of the triangles of cube (i, j, k) that touch its
    local edge `edge`, in triangle order; average(), normal.c:6-43 */
-__device__ __noinline__ void gather_cube(const FieldView &f, const DevTables &t, const long long i, const long long j, const long long k,
+static __device__ __noinline__ void gather_cube(const FieldView &f, const DevTables &t, const long long i, const long long j, const long long k,
                                          const unsigned int edge, V3 &sum) {
   Cube c;
   load_cube(f, i, j, k, c);
@@ -146,7 +146,7 @@ __device__ __noinline__ void gather_cube(const FieldView &f, const DevTables &t,
 /* vertex normal of the vertex on edge e of cube (i, j, k): the cubes sharing
    the edge are visited in global (k, j, i) order with the edge renamed to each
    cube's local id; the 19-way branch of normal.c:78-158, then normalise (159) */
-__device__ __noinline__ V3 vertex_normal(const FieldView &f, const DevTables &t, const long long i, const long long j, const long long k,
+static __device__ __noinline__ V3 vertex_normal(const FieldView &f, const DevTables &t, const long long i, const long long j, const long long k,
                                          const unsigned int e) {
   V3 sum = V3{0., 0., 0.};
   if (e < 12u) {

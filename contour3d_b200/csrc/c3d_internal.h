@@ -15,6 +15,7 @@ struct DevTables {
   const uint32_t *pairs;
   const uint32_t *emask;
   const uint32_t *edges;
+  const uint16_t *touch;
 };
 
 /* one contour object as the kernels see it: the extended local array */
@@ -122,7 +123,8 @@ int c3d_k_lines(const Cam *c, const LineDev *lines_dev, const LineDev *lines_hos
                 Pixel *canvas, cudaStream_t s);
 int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t npix, cudaStream_t s);
 int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
-                unsigned int *rgba, size_t npix, cudaStream_t s);
+                unsigned int *rgba, size_t npix, unsigned int *work, unsigned int *nwork, unsigned long long *overflowed,
+                int sm_count, cudaStream_t s);
 int c3d_k_pack(const unsigned int *rgba, const unsigned char bg[3], long long w, long long h, unsigned char *out, cudaStream_t s);
 int c3d_k_canvas_split(const Pixel *canvas, double *depth, unsigned long long *key, size_t npix, cudaStream_t s);
 int c3d_k_case_codes(const FieldView *f, const DevTables *t, unsigned int *codes, unsigned char *counts, cudaStream_t s);

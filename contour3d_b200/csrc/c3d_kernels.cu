@@ -7,8 +7,7 @@
  *   k_raster     per-cube tessellation + projection + bounding-box raster into
  *                a 64-bit atomic z-buffer (pass 1) / winner-key buffer (pass 2)
  *   k_lines      the same two passes for poly-line segments
- *   k_shade      deferred shading of the winning primitive of every pixel
- *                (vertex normals are gathered only for winners)
+ *   (deferred shading lives in c3d_shade.cu, the tiled sweep in c3d_sweep.cu)
  *   k_pack       y-flip + RGB byte packing (PPM payload)
  *   + halo pack/unpack, debug/inspection kernels, synthetic fields
  *
@@ -536,67 +535,6 @@ __global__ void k_depth_extract(const Pixel *__restrict__ canvas, unsigned long 
 
 extern "C" int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t npix, cudaStream_t s) {
   k_depth_extract<<<148 * 8, 256, 0, s>>>(canvas, depth, npix);
-  return (int)cudaGetLastError();
-}
-
-/*
- * Deferred shading: one thread per pixel.  Only the winning triangle of a
- * pixel gets vertex normals (compute_vertex_normals, normal.c:46-165,
- * evaluated by gathering instead of three stored slices), then the
- * barycentric blend + light factor + truncation of render.c:137-159.
- * Output: 0xFF000000 | b << 16 | g << 8 | r, or 0 where this rank has nothing
- * to contribute (background, or not the global winner).
- */
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ FrameParams p, const LineDev *__restrict__ lines,
-                                               const Pixel *__restrict__ canvas, const unsigned long long *__restrict__ depth_global,
-                                               unsigned int *__restrict__ rgba, const size_t npix) {
-  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= npix) return;
-  const ulonglong2 mine = *reinterpret_cast<const ulonglong2 *>(canvas + pix);
-  const unsigned long long mykey = mine.y;
-  unsigned int out = 0u;
-  if (0ull != mykey && (nullptr == depth_global || mine.x == depth_global[pix])) {
-    const unsigned int obj = (unsigned int)(mykey >> C3D_KEY_OBJ_SHIFT) - 1u;
-    const unsigned long long prim = mykey & C3D_KEY_PRIM_MASK;
-    if (obj >= p.ncontours) {
-      const LineDev &ln = lines[obj - p.ncontours];
-      out = 0xFF000000u | ((unsigned int)ln.color[2] << 16) | ((unsigned int)ln.color[1] << 8) | ln.color[0];
-    } else {
-      const FieldView &f = p.view[obj];
-      const unsigned int s = (unsigned int)(prim & 15ull);
-      const long long i = (long long)((prim >> 4) & 65535ull), j = (long long)((prim >> 20) & 65535ull), k = (long long)((prim >> 36) & 65535ull);
-      Cube c;
-      load_cube(f, i, j, k, c);
-      const unsigned int code = corner_code(c, f.thr);
-      V3 v[3];
-      triangle_vertices(c, f.thr, __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s), v);
-      Tri2D t;
-      double w[3] = {0., 0., 0.};
-      if (setup_triangle(p.cam, v, t)) {
-        pixel_weights(t, __ldg(p.px + (long long)(pix % (size_t)p.cam.w)), __ldg(p.py + (long long)(pix / (size_t)p.cam.w)), w);
-      }
-      const unsigned int edges = __ldg(p.tab.edges + code * C3D_MAX_TRIS + s);
-      V3 vn[3];
-      for (int m = 0; m < 3; m++) {
-        vn[m] = vertex_normal(f, p.tab, i, j, k, (edges >> (5 * m)) & 31u);
-      }
-      /* w0*n0 + (w1*n1 + w2*n2), render.c:137-146 */
-      const V3 nrm = v_unit(v_add(v_mul(w[0], vn[0]), v_add(v_mul(w[1], vn[1]), v_mul(w[2], vn[2]))));
-      const double factor = fmax(0.15, fabs(v_dot(nrm, v_of(p.cam.light))));
-      const unsigned int r = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[0])) & 255u;
-      const unsigned int g = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[1])) & 255u;
-      const unsigned int b = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[2])) & 255u;
-      out = 0xFF000000u | (b << 16) | (g << 8) | r;
-    }
-  }
-  rgba[pix] = out;
-}
-
-extern "C" int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
-                           unsigned int *rgba, size_t npix, cudaStream_t s) {
-  const int threads = 128;
-  const unsigned int blocks = (unsigned int)((npix + threads - 1) / threads);
-  k_shade<<<blocks, threads, 0, s>>>(*p, lines_dev, canvas, depth_global, rgba, npix);
   return (int)cudaGetLastError();
 }
 

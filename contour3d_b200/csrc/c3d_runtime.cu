@@ -101,7 +101,7 @@ struct c3d_field {
   bool halo_valid;
 };
 
-enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_OBJ = 3, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
+enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_SHADE_SPILL = 3, CNT_OBJ = 4, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
 enum { EV_START, EV_HALO, EV_CLEAR, EV_SWEEP, EV_EXPAND, EV_RASTER, EV_LINES, EV_RESOLVE, EV_REDUCE0, EV_SHADE, EV_REDUCE1, EV_PACK, EV_DOWNLOAD, EV_COUNT };
 
 struct c3d_context {
@@ -118,6 +118,7 @@ struct c3d_context {
   double *pixel_xy;                                /* pixel-centre tables: width + height doubles */
   size_t table_w, table_h;
   unsigned int *rgba;
+  unsigned int *shade_work, *shade_nwork;          /* pixels won by a contour triangle (compacted), and their number */
   unsigned char *ppm_dev, *ppm_host;
   size_t width, height;
   /* active-cube list of the frame (all contour objects, tagged) */
@@ -196,9 +197,11 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   ctx->tab.pairs = (const uint32_t *)(tb + offsetof(c3d_tables_t, pairs));
   ctx->tab.emask = (const uint32_t *)(tb + offsetof(c3d_tables_t, emask));
   ctx->tab.edges = (const uint32_t *)(tb + offsetof(c3d_tables_t, edges));
+  ctx->tab.touch = (const uint16_t *)(tb + offsetof(c3d_tables_t, touch));
   CUDA_OK(cudaMalloc(&ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long)));
   CUDA_OK(cudaMallocHost(&ctx->counts_host, CNT_TOTAL * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->tile_cursor, sizeof(unsigned int)));
+  CUDA_OK(cudaMalloc(&ctx->shade_nwork, sizeof(unsigned int)));
   CUDA_OK(cudaMalloc(&ctx->bucket_hist, C3D_DEPTH_BUCKETS * sizeof(unsigned int)));
   CUDA_OK(cudaMalloc(&ctx->bucket_cursors, C3D_DEPTH_BUCKETS * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->views_dev, C3D_MAX_OBJECTS * sizeof(FieldView)));
@@ -220,6 +223,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
   cudaFree(ctx->table_mem);
+  cudaFree(ctx->shade_work); cudaFree(ctx->shade_nwork);
   cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->pixel_xy); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
   if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
   cudaFree(ctx->list); cudaFree(ctx->records); cudaFree(ctx->tile_cursor); cudaFree(ctx->bucket_hist); cudaFree(ctx->bucket_cursors); cudaFree(ctx->counts_dev);
@@ -513,6 +517,8 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
   const size_t npix = w * h;
   if (npix > ctx->npix_cap) {
     cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
+    cudaFree(ctx->shade_work);
+    ctx->shade_work = NULL;
     if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
     ctx->canvas = NULL; ctx->depth_local = ctx->depth_global = NULL; ctx->rgba = NULL; ctx->ppm_dev = NULL; ctx->ppm_host = NULL;
     ctx->npix_cap = 0;
@@ -522,6 +528,7 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
       CUDA_OK(cudaMalloc(&ctx->depth_global, npix * 8));
     }
     CUDA_OK(cudaMalloc(&ctx->rgba, npix * 4));
+    CUDA_OK(cudaMalloc(&ctx->shade_work, npix * 4));
     CUDA_OK(cudaMalloc(&ctx->ppm_dev, npix * 3));
     CUDA_OK(cudaMallocHost(&ctx->ppm_host, npix * 3));
     ctx->npix_cap = npix;
@@ -787,8 +794,9 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
   /* 5. shade only what survived */
-  LAUNCH_OK(c3d_k_shade(&fp, ctx->lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, s));
-  launches += 1;
+  LAUNCH_OK(c3d_k_shade(&fp, ctx->lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, ctx->shade_work, ctx->shade_nwork,
+                        ctx->counts_dev + CNT_SHADE_SPILL, ctx->sm_count, s));
+  launches += 2;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
   /* 6. colours to the writer (the colour half of the reference's reduce) */
   if (ctx->size > 1) {

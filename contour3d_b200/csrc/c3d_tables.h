@@ -12,6 +12,7 @@
  *                        3+3 bits each at bit 6m (winding reversal applied)
  *   emask[code][t]       bit e set when a vertex of triangle t sits on cube edge e (0..18)
  *   edges[code][t]       the three cube-edge ids, 5 bits each at bit 5m
+ *   touch[code][e]       bit t set when triangle t has a vertex on cube edge e (emask transposed)
  *
  * Corner numbering: bit0 = +x, bit1 = +y, bit2 = +z (triangulate.c:15-19).
  */
@@ -28,6 +29,7 @@ typedef struct {
   uint32_t pairs[256 * C3D_MAX_TRIS];
   uint32_t emask[256 * C3D_MAX_TRIS];
   uint32_t edges[256 * C3D_MAX_TRIS];
+  uint16_t touch[256 * 19];
 } c3d_tables_t;
 
 /* cube-edge id between corners a and b: 0-3 x edges (dj + 2dk), 4-7 y edges
@@ -93,6 +95,11 @@ static inline void c3d_tables_build(c3d_tables_t *t) {
     }
     t->count[code] = (uint8_t)count;
     t->code24[code] = packed;
+    for (uint32_t e = 0; e < 19; e++) {
+      uint16_t mask = 0;
+      for (uint32_t s = 0; s < count; s++) mask |= (uint16_t)(((t->emask[code * C3D_MAX_TRIS + s] >> e) & 1u) << s);
+      t->touch[code * 19 + e] = mask;
+    }
   }
 }
 
