@@ -292,7 +292,7 @@ def ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "stages_ms": {k: v / args.steps for k, v in stage_sum.items()},
-            "active_cubes": active, "culled_cubes": t["culled_cubes"],
+            "active_cubes": active, "culled_cubes": t["culled_cubes"], "culled_triangles": t["culled_triangles"], "shade_spills": t["shade_spills"],
         }
         print(json.dumps(line))
     barrier()

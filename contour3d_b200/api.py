@@ -71,6 +71,8 @@ class Timings(C.Structure):
         ("sweep_thresholds", C.c_uint32 * 16),
         ("active_cubes", C.c_uint64 * 16),
         ("culled_cubes", C.c_uint64),
+        ("culled_triangles", C.c_uint64),
+        ("shade_spills", C.c_uint64),
         ("nsweeps", C.c_uint32),
         ("ncontours", C.c_uint32),
         ("launches", C.c_uint32),
@@ -84,6 +86,8 @@ class Timings(C.Structure):
         d["sweep_thresholds"] = [int(self.sweep_thresholds[i]) for i in range(m)]
         d["active_cubes"] = [int(self.active_cubes[i]) for i in range(n)]
         d["culled_cubes"] = int(self.culled_cubes)
+        d["culled_triangles"] = int(self.culled_triangles)
+        d["shade_spills"] = int(self.shade_spills)
         d["launches"] = int(self.launches)
         return d
 

@@ -25,6 +25,7 @@ struct FieldView {
   long long n[3];          /* points in x, y, z */
   long long sy, sz;        /* row / plane strides in elements */
   const double *g[3];      /* device coordinates of exactly those points */
+  const float *gf[3];      /* the same rounded to fp32 (conservative visibility pre-tests only) */
   double thr;              /* iso value; classification is thr < value (strict) */
   float thr_ge;            /* fp32 fields: smallest float f with (double)f > thr, so thr < v <=> v >= thr_ge */
   unsigned char color[3];
@@ -62,7 +63,8 @@ struct __align__(16) Pixel { unsigned long long depth, key; };
 #define C3D_KEY_PRIM_MASK ((1ull << C3D_KEY_OBJ_SHIFT) - 1ull)
 #define C3D_MAX_AXIS 65535ll      /* cubes per direction that fit the 16-bit fields */
 
-/* active-cube list entry: code:8 | i:16 | j:16 | k:16 | object:4 */
+/* active-cube list entry: code:8 | i:16 | j:16 | k:16 | object:4 | irregular:1 (bit 60: a corner value may be
+   within rounding of the iso-value, so a triangle may have collapsed to a point; see cube_hidden) */
 #define C3D_ENTRY(obj, i, j, k, code) \
   (((unsigned long long)(obj) << 56) | ((unsigned long long)(k) << 40) | ((unsigned long long)(j) << 24) | ((unsigned long long)(i) << 8) | (unsigned long long)(code))
 #define C3D_ENTRY_CODE(e) ((unsigned int)((e) & 255ull))
@@ -70,6 +72,8 @@ struct __align__(16) Pixel { unsigned long long depth, key; };
 #define C3D_ENTRY_J(e) ((long long)(((e) >> 24) & 65535ull))
 #define C3D_ENTRY_K(e) ((long long)(((e) >> 40) & 65535ull))
 #define C3D_ENTRY_OBJ(e) ((unsigned int)((e) >> 56) & 15u)
+#define C3D_ENTRY_IRREGULAR_BIT (1ull << 60)
+#define C3D_ENTRY_IRREGULAR(e) (0ull != ((e) & C3D_ENTRY_IRREGULAR_BIT))
 
 #define C3D_MAX_OBJECTS 16
 #define C3D_DEPTH_BUCKETS 2048        /* view-depth slabs of the front-to-back ordering (multiple of 1024) */
@@ -82,6 +86,7 @@ struct SweepRange { long long lo[3], hi[3]; }; /* inclusive cube ranges to emit 
 struct CullCam {
   float cam[3], n[3], lxs[3], lys[3];
   float ax, ay, c;
+  float inv_abs_c, lx_norm, ly_norm;   /* 1 / |c|, |lxs|, |lys|: screen magnification bound of the triangle pre-test */
   float W, H;
   int w, h;
   int enabled;
@@ -125,6 +130,7 @@ int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t n
 int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
                 unsigned int *rgba, size_t npix, unsigned int *work, unsigned int *nwork, unsigned long long *overflowed,
                 int sm_count, cudaStream_t s);
+int c3d_k_to_float(const double *in, float *out, size_t n, cudaStream_t s);
 int c3d_k_pack(const unsigned int *rgba, const unsigned char bg[3], long long w, long long h, unsigned char *out, cudaStream_t s);
 int c3d_k_canvas_split(const Pixel *canvas, double *depth, unsigned long long *key, size_t npix, cudaStream_t s);
 int c3d_k_case_codes(const FieldView *f, const DevTables *t, unsigned int *codes, unsigned char *counts, cudaStream_t s);

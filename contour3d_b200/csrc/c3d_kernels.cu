@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(256) k_sweep(const SweepParams p) {
           const unsigned int l0 = (unsigned int)(lower >> (5 * r)) & 31u, l1 = (unsigned int)(lower >> (5 * r + 5)) & 31u;
           const unsigned int u0 = (unsigned int)(upper >> (5 * r)) & 31u, u1 = (unsigned int)(upper >> (5 * r + 5)) & 31u;
           const unsigned int code = ((l0 >> c) & 3u) | (((l1 >> c) & 3u) << 2) | (((u0 >> c) & 3u) << 4) | (((u1 >> c) & 3u) << 6);
-          if (at < p.capacity) p.list[at] = C3D_ENTRY(p.obj, x0 + c, j0 + r, k, code);
+          /* no patch analysis on this path: marked irregular, i.e. never skipped by the raster's visibility tests */
+          if (at < p.capacity) p.list[at] = C3D_ENTRY(p.obj, x0 + c, j0 + r, k, code) | C3D_ENTRY_IRREGULAR_BIT;
           at++;
         }
       }
@@ -345,6 +346,23 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
   }
 }
 
+/* every pixel of [ceil(x0), floor(x1)] x [ceil(y0), floor(y1)] (clipped to the screen) holds a depth above `limit`;
+   an empty range is hidden only when `empty_is_hidden` (no pixel centre can be covered); more than 64 pixels: not decided */
+__device__ __forceinline__ bool region_hidden(const Pixel *__restrict__ canvas, const CullCam &q, const float x0, const float x1,
+                                              const float y0, const float y1, const bool empty_is_hidden, const unsigned long long limit) {
+  const int imin = max(0, (int)ceilf(x0)), imax = min(q.w - 1, (int)floorf(x1));
+  const int jmin = max(0, (int)ceilf(y0)), jmax = min(q.h - 1, (int)floorf(y1));
+  if (imax < imin || jmax < jmin) return empty_is_hidden;
+  if ((imax - imin + 1) * (jmax - jmin + 1) > 64) return false;
+  for (int pj = jmin; pj <= jmax; pj++) {
+    const unsigned long long *row = reinterpret_cast<const unsigned long long *>(canvas + (long long)pj * q.w);
+    for (int pi = imin; pi <= imax; pi++) {
+      if (__ldcg(row + 2 * pi) <= limit) return false;
+    }
+  }
+  return true;
+}
+
 /*
  * Conservative occlusion test of a whole cube against the z-buffer as it
  * stands: true only when every pixel any of the cube's triangles could touch
@@ -355,15 +373,21 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
  * With a depth complexity of ~20 most cubes of a turbulent field are hidden.
  */
 __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned long long entry, const Pixel *__restrict__ canvas) {
+  /* A triangle whose vertices have collapsed onto one cube corner is drawn by the reference as a blob: the
+     clamped area (render.c:103-106) makes all three weights +-0, every pixel of the +-1 pixel box passes the
+     inside test and the depth is 1 / +-0 = +-inf -- it beats any finite depth.  Collapse needs an interpolation
+     factor within rounding of 0 or 1, i.e. a corner value (almost) equal to the iso-value; k_expand marks the
+     cubes of every 4 x 8 patch where that cannot be excluded (C3D_ENTRY_IRREGULAR) and those are never culled. */
+  if (C3D_ENTRY_IRREGULAR(entry)) return false;
   const CullCam &q = p.cull;
   const FieldView &f = p.view[C3D_ENTRY_OBJ(entry)];
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
   float an[2], al[2], am[2], bn[2], bl[2], bm[2], cn[2], cl[2], cm[2];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
-    const float rx = (float)__ldg(f.g[0] + i + e) - q.cam[0];
-    const float ry = (float)__ldg(f.g[1] + j + e) - q.cam[1];
-    const float rz = (float)__ldg(f.g[2] + k + e) - q.cam[2];
+    const float rx = __ldg(f.gf[0] + i + e) - q.cam[0];
+    const float ry = __ldg(f.gf[1] + j + e) - q.cam[1];
+    const float rz = __ldg(f.gf[2] + k + e) - q.cam[2];
     an[e] = q.n[0] * rx; al[e] = q.lxs[0] * rx; am[e] = q.lys[0] * rx;
     bn[e] = q.n[1] * ry; bl[e] = q.lxs[1] * ry; bm[e] = q.lys[1] * ry;
     cn[e] = q.n[2] * rz; cl[e] = q.lxs[2] * rz; cm[e] = q.lys[2] * rz;
@@ -385,39 +409,96 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
      then all n.ray share the sign of c and the cube projects inside the hull of its corners), else the
      bounds mean nothing and the cube is kept */
   if (!(tlo > 1.e-4f && thi < 0.9999f)) return false;
+  if (!(xlo > -1.e6f && xhi < 1.e6f && ylo > -1.e6f && yhi < 1.e6f)) return false;
+  const double zcap = (double)znear + (1.e-4 * fabs((double)znear) + 1.e-6);
+  const unsigned long long limit = ord_of(zcap);
   /* a fragment exists only where a PIXEL CENTRE lies inside a triangle (render.c:94-115; the +-1 pixel box of
      render.c:81-89 is just the search range), and every triangle lies inside the hull of the corners:
      the pixels to look at are those whose centre (i + 0.5) / W - 0.5 falls within the bounds, +- 0.05 pixel */
-  const float fx0 = (0.5f + xlo) * q.W - 0.55f, fx1 = (0.5f + xhi) * q.W - 0.45f;
-  const float fy0 = (0.5f + ylo) * q.H - 0.55f, fy1 = (0.5f + yhi) * q.H - 0.45f;
-  if (!(fx0 > -1.e6f && fx1 < 1.e6f && fy0 > -1.e6f && fy1 < 1.e6f)) return false;
-  const int imin = max(0, (int)ceilf(fx0)), imax = min(q.w - 1, (int)floorf(fx1));
-  const int jmin = max(0, (int)ceilf(fy0)), jmax = min(q.h - 1, (int)floorf(fy1));
-  if (imax < imin || jmax < jmin) return true;                 /* no pixel centre inside: nothing to draw */
-  if ((imax - imin + 1) * (jmax - jmin + 1) > 64) return false;
-  const double zcap = (double)znear + (1.e-4 * fabs((double)znear) + 1.e-6);
-  const unsigned long long limit = ord_of(zcap);
-  for (int pj = jmin; pj <= jmax; pj++) {
-    const unsigned long long *row = reinterpret_cast<const unsigned long long *>(canvas + (long long)pj * q.w);
-    for (int pi = imin; pi <= imax; pi++) {
-      if (__ldcg(row + 2 * pi) <= limit) return false;
-    }
-  }
+  if (!region_hidden(canvas, q, (0.5f + xlo) * q.W - 0.55f, (0.5f + xhi) * q.W - 0.45f, (0.5f + ylo) * q.H - 0.55f,
+                     (0.5f + yhi) * q.H - 0.45f, true, limit)) return false;
   return true;
 }
 
+/*
+ * The same question for ONE triangle, asked before its exact (and expensive) fp64 set-up: an fp32
+ * estimate of the three vertices with explicit error bounds gives a box that certainly contains the
+ * exact projected triangle.  No pixel centre inside the box (true for about half of the sub-pixel
+ * triangles of a 1024^3 field on a 4K screen), or every such pixel already nearer in the z-buffer
+ * than the triangle can be -> it cannot produce a surviving fragment and is dropped.
+ *
+ * Error budget per vertex: the cut position p0 + f (p1 - p0) has f = (thr - v0) / (v1 - v0) with an
+ * absolute error below ferr = 2e-7 (|thr| + |v0| + |v1|) / |v1 - v0| (inputs rounded to fp32, three
+ * rounded operations); the vertex moves by at most ferr |p1 - p0| in space, i.e. by at most
+ * G ferr |p1 - p0|_1 on the screen with G = |t| N (|l| + |ray.l| |t| / |c|) the local magnification of
+ * the projection (x1.5 for its curvature over that distance); fp32 evaluation of the projection itself
+ * stays below 0.01 pixel on screens up to 2^20 pixels wide; 0.05 pixel is added on top.  Anything that
+ * does not fit these assumptions (ferr > 0.02, vertices near the screen plane, NaN) keeps the triangle.
+ */
+__device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsigned long long entry, const unsigned int s,
+                                                const Pixel *__restrict__ canvas) {
+  const CullCam &q = p.cull;
+  const unsigned int code = C3D_ENTRY_CODE(entry);
+  const FieldView &f = p.view[C3D_ENTRY_OBJ(entry)];
+  const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
+  const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
+  const long long base = k * f.sz + j * f.sy + i;
+  const float thr = (float)f.thr;
+  float xlo = 3.e38f, xhi = -3.e38f, ylo = 3.e38f, yhi = -3.e38f, znear = -3.e38f, zslack = 0.f;
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
+    const float v0 = (float)ld_value(f, base + (tail & 1u) + ((tail >> 1) & 1u) * f.sy + (tail >> 2) * f.sz);
+    const float v1 = (float)ld_value(f, base + (head & 1u) + ((head >> 1) & 1u) * f.sy + (head >> 2) * f.sz);
+    const float dv = v1 - v0;
+    const float ferr = 2.e-7f * (fabsf(thr) + fabsf(v0) + fabsf(v1)) / fabsf(dv);
+    if (!(ferr < 0.02f) || !(fabsf(dv) > 1.e-7f)) return false;    /* incl. the |dv| < 1e-8 branch of triangulate.c:62-71 */
+    const float fr = fminf(fmaxf((thr - v0) / dv, 0.f), 1.f);
+    /* a vertex that may sit within 1e-5 of a cube corner: the triangle may have collapsed to a point, which the
+       reference draws as its whole +-1 pixel box (see cube_hidden); leave those to the exact path */
+    if (!(fr - ferr > 1.e-5f && fr + ferr < 0.99999f)) return false;
+    const float x0 = __ldg(f.gf[0] + i + (tail & 1u)), y0 = __ldg(f.gf[1] + j + ((tail >> 1) & 1u)), z0 = __ldg(f.gf[2] + k + (tail >> 2));
+    const float ex = __ldg(f.gf[0] + i + (head & 1u)) - x0, ey = __ldg(f.gf[1] + j + ((head >> 1) & 1u)) - y0, ez = __ldg(f.gf[2] + k + (head >> 2)) - z0;
+    const float rx = x0 + fr * ex - q.cam[0], ry = y0 + fr * ey - q.cam[1], rz = z0 + fr * ez - q.cam[2];
+    const float nr = q.n[0] * rx + q.n[1] * ry + q.n[2] * rz;
+    const float t = __fdividef(q.c, nr);
+    if (!(t > 1.e-4f && t < 0.9999f)) return false;
+    const float rl = rx * q.lxs[0] + ry * q.lxs[1] + rz * q.lxs[2];
+    const float rm = rx * q.lys[0] + ry * q.lys[1] + rz * q.lys[2];
+    /* pixel coordinates: pixel i has its centre at X = i */
+    const float X = (0.5f + q.ax + t * rl) * q.W - 0.5f, Y = (0.5f + q.ay + t * rm) * q.H - 0.5f;
+    const float span = ferr * (fabsf(ex) + fabsf(ey) + fabsf(ez));
+    const float tc = t * q.inv_abs_c;
+    const float mx = 0.05f + 1.5f * span * t * q.W * (q.lx_norm + fabsf(rl) * tc);
+    const float my = 0.05f + 1.5f * span * t * q.H * (q.ly_norm + fabsf(rm) * tc);
+    xlo = fminf(xlo, X - mx); xhi = fmaxf(xhi, X + mx);
+    ylo = fminf(ylo, Y - my); yhi = fmaxf(yhi, Y + my);
+    znear = fmaxf(znear, nr);
+    zslack = fmaxf(zslack, span);
+  }
+  if (!(xlo > -1.e6f && xhi < 1.e6f && ylo > -1.e6f && yhi < 1.e6f)) return false;
+  const double zcap = (double)znear + (1.e-4 * fabs((double)znear) + 1.e-6 + 2. * (double)zslack);
+  return region_hidden(canvas, q, xlo, xhi, ylo, yhi, true, ord_of(zcap));
+}
+
+/* list entry + triangle index in its four spare bits */
+#define C3D_TRI_PACK(entry, s) (((entry) & 0x0fffffffffffffffull) | ((unsigned long long)(s) << 60))
+#define C3D_TRI_ENTRY(q) ((q) & 0x0fffffffffffffffull)
+#define C3D_TRI_INDEX(q) ((unsigned int)((q) >> 60))
+
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ list,
-                                                const unsigned long long *__restrict__ count, const unsigned long long capacity,
-                                                Pixel *__restrict__ canvas, unsigned long long *__restrict__ culled) {
+                                                     const unsigned long long *__restrict__ count, const unsigned long long capacity,
+                                                     Pixel *__restrict__ canvas, unsigned long long *__restrict__ culled) {
   __shared__ unsigned long long s_entry[4][32];
   __shared__ unsigned int s_first[4][32];
+  __shared__ unsigned long long s_queue[4][64];       /* triangles that passed the pre-test, waiting for a full warp */
   unsigned long long n = *count;
   if (n > capacity) n = capacity;
   const unsigned int lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   const unsigned long long warp = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + wid;
   const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
-  unsigned int hidden_total = 0u;
+  unsigned int hidden_total = 0u, hidden_tris = 0u, queued = 0u;
   for (unsigned long long base = warp * 32ull; base < n; base += nwarps * 32ull) {
     unsigned long long entry = 0ull;
     unsigned int ntri = 0u;
@@ -450,10 +531,40 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
       const unsigned int starts = __reduce_or_sync(C3D_FULL_MASK, starts_here ? 1u << (excl - t0) : 0u);
       const unsigned int before = __popc(__ballot_sync(C3D_FULL_MASK, ntri > 0u && excl < t0));
       const unsigned int src = (before + __popc(starts & (0xffffffffu >> (31u - lane))) - 1u) & 31u;
-      if (t0 + lane < total) raster_triangle(p, s_entry[wid][src], t0 + lane - s_first[wid][src], canvas);
+      bool keep = false;
+      unsigned long long mine = 0ull;
+      if (t0 + lane < total) {
+        const unsigned long long e = s_entry[wid][src];
+        const unsigned int s = t0 + lane - s_first[wid][src];
+        mine = C3D_TRI_PACK(e, s);
+        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden(p, e, s, canvas));
+      }
+      const unsigned int kept = __ballot_sync(C3D_FULL_MASK, keep);
+      hidden_tris += __popc(__ballot_sync(C3D_FULL_MASK, t0 + lane < total)) - __popc(kept);
+      if (keep) s_queue[wid][queued + __popc(kept & ((1u << lane) - 1u))] = mine;
+      queued += __popc(kept);
+      __syncwarp();
+      if (queued >= 32u) {
+        /* a full warp of triangles that need the exact treatment */
+        const unsigned long long q = s_queue[wid][lane];
+        const unsigned long long rest = (lane + 32u < queued) ? s_queue[wid][lane + 32u] : 0ull;
+        __syncwarp();
+        if (lane + 32u < queued) s_queue[wid][lane] = rest;
+        queued -= 32u;
+        __syncwarp();
+        raster_triangle(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), canvas);
+      }
     }
   }
-  if (0u == lane && hidden_total > 0u && nullptr != culled) atomicAdd(culled, (unsigned long long)hidden_total);
+  __syncwarp();
+  if (lane < queued) {
+    const unsigned long long q = s_queue[wid][lane];
+    raster_triangle(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), canvas);
+  }
+  if (0u == lane && nullptr != culled) {
+    if (hidden_total > 0u) atomicAdd(culled, (unsigned long long)hidden_total);
+    if (hidden_tris > 0u) atomicAdd(culled + 1, (unsigned long long)hidden_tris);
+  }
 }
 
 extern "C" int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const unsigned long long *count, unsigned long long capacity,
@@ -535,6 +646,17 @@ __global__ void k_depth_extract(const Pixel *__restrict__ canvas, unsigned long 
 
 extern "C" int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t npix, cudaStream_t s) {
   k_depth_extract<<<148 * 8, 256, 0, s>>>(canvas, depth, npix);
+  return (int)cudaGetLastError();
+}
+
+/* fp32 copies of the grid coordinates (visibility pre-tests) */
+__global__ void k_to_float(const double *__restrict__ in, float *__restrict__ out, const size_t n) {
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = (float)in[q];
+}
+
+extern "C" int c3d_k_to_float(const double *in, float *out, size_t n, cudaStream_t s) {
+  if (0 == n) return 0;
+  k_to_float<<<(unsigned int)((n + 255) / 256 < 256 ? (n + 255) / 256 : 256), 256, 0, s>>>(in, out, n);
   return (int)cudaGetLastError();
 }
 

@@ -101,7 +101,7 @@ struct c3d_field {
   bool halo_valid;
 };
 
-enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_SHADE_SPILL = 3, CNT_OBJ = 4, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
+enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_CULLED_TRIS = 3, CNT_SHADE_SPILL = 4, CNT_OBJ = 5, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
 enum { EV_START, EV_HALO, EV_CLEAR, EV_SWEEP, EV_EXPAND, EV_RASTER, EV_LINES, EV_RESOLVE, EV_REDUCE0, EV_SHADE, EV_REDUCE1, EV_PACK, EV_DOWNLOAD, EV_COUNT };
 
 struct c3d_context {
@@ -485,6 +485,12 @@ static float smallest_float_above(const double thr) {
   return nextafterf(f, INFINITY);
 }
 
+static size_t grid_slot_doubles(const c3d_field *f) {
+  const size_t total = f->ext[0] + f->ext[1] + f->ext[2];
+  return total + (total + 1) / 2 + 1;
+}
+
+/* grid_slot: room for sum(ext) doubles followed by sum(ext) floats */
 static int make_view(c3d_context *ctx, const c3d_field *f, const double *const grids[3], const double threshold,
                      const uint8_t color[3], double *grid_slot, FieldView *v) {
   v->data = f->data;
@@ -492,13 +498,18 @@ static int make_view(c3d_context *ctx, const c3d_field *f, const double *const g
   for (int d = 0; d < 3; d++) v->n[d] = (long long)f->ext[d];
   v->sy = (long long)f->ext[0];
   v->sz = (long long)(f->ext[0] * f->ext[1]);
+  const size_t total = f->ext[0] + f->ext[1] + f->ext[2];
   double *at = grid_slot;
+  float *atf = (float *)(grid_slot + total);
   for (int d = 0; d < 3; d++) {
     if (NULL == grids || NULL == grids[d]) return c3d_error("grid coordinates of direction %d are missing", d);
     CUDA_OK(cudaMemcpyAsync(at, grids[d] + f->ext_off[d], f->ext[d] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     v->g[d] = at;
+    v->gf[d] = atf;
     at += f->ext[d];
+    atf += f->ext[d];
   }
+  LAUNCH_OK(c3d_k_to_float(grid_slot, (float *)(grid_slot + total), total, ctx->stream));
   v->thr = threshold;
   v->thr_ge = smallest_float_above(threshold);
   v->color[0] = color[0]; v->color[1] = color[1]; v->color[2] = color[2];
@@ -589,6 +600,9 @@ static void make_cull(const Cam *c, CullCam *q) {
   q->ax = (float)(cx / c->lxlx);
   q->ay = (float)(cy / c->lyly);
   q->c = (float)(c->d - c->nc);
+  q->inv_abs_c = (float)(1. / fabs(c->d - c->nc));
+  q->lx_norm = (float)(sqrt(c->lxlx) / c->lxlx * 1.000001);
+  q->ly_norm = (float)(sqrt(c->lyly) / c->lyly * 1.000001);
   q->W = (float)c->W;
   q->H = (float)c->H;
   q->w = (int)c->w;
@@ -621,7 +635,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   size_t grid_elems = 0;
   for (size_t n = 0; n < nc; n++) {
     const c3d_field *f = contours[n].field;
-    grid_elems += f->ext[0] + f->ext[1] + f->ext[2];
+    grid_elems += grid_slot_doubles(f);
   }
   {
     size_t cap = ctx->grids_cap * sizeof(double);
@@ -647,7 +661,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
         if ((long long)f->ext[d] - 1 > C3D_MAX_AXIS) return c3d_error("extended array too large in direction %d (%zu points)", d, f->ext[d]);
       }
       if (0 != make_view(ctx, f, contours[n].grids, contours[n].threshold, contours[n].color, slot, &views[n])) return 1;
-      slot += f->ext[0] + f->ext[1] + f->ext[2];
+      slot += grid_slot_doubles(f);
     }
   }
   std::vector<LineDev> hl(nl);
@@ -863,6 +877,8 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   t->launches = launches;
   t->nsweeps = nsweeps;
   t->culled_cubes = ctx->counts_host[CNT_CULLED];
+  t->culled_triangles = ctx->counts_host[CNT_CULLED_TRIS];
+  t->shade_spills = ctx->counts_host[CNT_SHADE_SPILL];
   for (uint32_t m = 0; m < nsweeps; m++) {
     cudaEventElapsedTime(&t->sweep_each[m], ctx->ev_sweep[m], ctx->ev_sweep[m + 1]);
     t->sweep_bytes[m] = sweep_bytes[m];
@@ -938,13 +954,13 @@ extern "C" int c3d_frame_canvas(c3d_context_t *ctx, double *host_depth, uint64_t
 static int stage_view(c3d_context *ctx, const c3d_field *f, const double *const grids[3], const double thr, FieldView *v) {
   const uint8_t white[3] = {255, 255, 255};
   size_t cap = ctx->grids_cap * sizeof(double);
-  const size_t elems = f->ext[0] + f->ext[1] + f->ext[2];
+  const size_t elems = grid_slot_doubles(f);
   if (0 != ensure_bytes((void **)&ctx->grids_dev, &cap, (elems + 8) * sizeof(double))) return 1;
   ctx->grids_cap = cap / sizeof(double);
   if (NULL == grids) {
     /* classification does not need coordinates */
     v->data = f->data; v->elem_bytes = f->elem_bytes;
-    for (int d = 0; d < 3; d++) { v->n[d] = (long long)f->ext[d]; v->g[d] = ctx->grids_dev; }
+    for (int d = 0; d < 3; d++) { v->n[d] = (long long)f->ext[d]; v->g[d] = ctx->grids_dev; v->gf[d] = (const float *)ctx->grids_dev; }
     v->sy = (long long)f->ext[0]; v->sz = (long long)(f->ext[0] * f->ext[1]);
     v->thr = thr; v->thr_ge = smallest_float_above(thr);
     return 0;

@@ -453,6 +453,74 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(const unsigned int *__rest
   if (1023u == threadIdx.x) *count = first + part[1023];
 }
 
+/*
+ * Can a triangle of this 4 x 8 patch of cubes have collapsed to a point?  Vertices reach a cube corner only
+ * when an interpolation factor (thr - v0) / (v1 - v0) = a0 / (a0 + a1), a = |v - thr|, is within rounding of
+ * 0 or 1 (or |v1 - v0| < 1e-8, triangulate.c:62-71).  If min a > 1e-6 max a over the points of the patch that
+ * its cut cubes use, every factor of every such cube lies in (5e-7, 1 - 5e-7): no collapse.  Anything else (including
+ * NaN / infinite data) marks the patch, and the raster then skips its visibility shortcuts there.
+ */
+__device__ __forceinline__ bool patch_irregular(const FieldView &f, const unsigned int x, const unsigned int j, const unsigned int k,
+                                                const unsigned int active) {
+  /* only the point rows that cut cubes of the patch touch (cube row r uses point rows r and r + 1) */
+  unsigned int need = 0u;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if ((active >> (4 * r)) & 15u) need |= 3u << r;
+  }
+  const long long nx = f.n[0] - (long long)x < 5 ? f.n[0] - (long long)x : 5;
+  if (4 == f.elem_bytes) {
+    /* fp32 data: v - thr32 is exact where it matters (Sterbenz: operands within a factor of two), so the only
+       error in a = |v - thr| is the rounding of the iso-value itself, thr_err = |thr - (double)thr32|; with
+       amin32 > 1.1e-6 amax32 + 1.01 thr_err the exact quantities satisfy amin > 1e-6 amax */
+    const float thr32 = (float)f.thr;
+    const float thr_err = (float)(fabs(f.thr - (double)thr32) * 1.01) + 0.f;
+    const float *data = (const float *)f.data;
+    const bool vec = (0 == (f.sy & 3)) && (0 == (f.sz & 3)) && (0 == ((uintptr_t)data & 15)) && nx >= 4;   /* x is a multiple of 4 */
+    float amin = FLT_MAX, amax = 0.f, sum = 0.f;
+    for (int dz = 0; dz < 2; dz++) {
+      for (int r = 0; r < 9; r++) {
+        if ((long long)j + r >= f.n[1]) break;
+        if (0u == ((need >> r) & 1u)) continue;
+        const float *row = data + ((long long)k + dz) * f.sz + ((long long)j + r) * f.sy + (long long)x;
+        float v[5];
+        if (vec) {
+          const float4 q = __ldg(reinterpret_cast<const float4 *>(row));
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+          v[4] = nx > 4 ? __ldg(row + 4) : q.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 5; c++) v[c] = __ldg(row + (c < nx ? c : 0));
+        }
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+          const float a = fabsf(v[c] - thr32);
+          amin = fminf(amin, a);
+          amax = fmaxf(amax, a);
+          sum += a;                        /* NaN / inf detector (fminf / fmaxf would drop a NaN) */
+        }
+      }
+    }
+    return !(sum <= FLT_MAX) || !(amin > 1.1e-6f * amax + thr_err);
+  }
+  double amin = DBL_MAX, amax = 0.;
+  bool bad = false;
+  for (int dz = 0; dz < 2; dz++) {
+    for (int r = 0; r < 9; r++) {
+      if ((long long)j + r >= f.n[1]) break;
+      if (0u == ((need >> r) & 1u)) continue;
+      const double *row = (const double *)f.data + ((long long)k + dz) * f.sz + ((long long)j + r) * f.sy + (long long)x;
+      for (long long c = 0; c < nx; c++) {
+        const double a = fabs(__ldg(row + c) - f.thr);
+        bad |= !(a <= DBL_MAX);
+        amin = fmin(amin, a);
+        amax = fmax(amax, a);
+      }
+    }
+  }
+  return bad || !(amin > 1.e-6 * amax);
+}
+
 template <bool SORTED>
 __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ FrameParams p, const DepthOrder o,
                                                 const SweepRecord *__restrict__ records, const unsigned long long *__restrict__ nrecords,
@@ -490,6 +558,7 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ FramePar
       if (0u == lane) at = atomicAdd(count, (unsigned long long)total);
       at = __shfl_sync(SW_FULL, at, 0) + (incl - mine);
     }
+    const unsigned long long flag = (SORTED && 0u != mine && patch_irregular(p.view[obj], x, j, k, active)) ? C3D_ENTRY_IRREGULAR_BIT : 0ull;
     /* rows 0..8 of the four bit planes */
     const unsigned long long pl = a.x | ((unsigned long long)(b.y & 15u) << 32), ql = a.y | ((unsigned long long)((b.y >> 4) & 15u) << 32);
     const unsigned long long pu = a.z | ((unsigned long long)((b.y >> 8) & 15u) << 32), qu = a.w | ((unsigned long long)((b.y >> 12) & 15u) << 32);
@@ -505,7 +574,7 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ FramePar
                               | ((unsigned int)((pl >> (bit + 4)) & 1ull) << 2) | ((unsigned int)((ql >> (bit + 4)) & 1ull) << 3)
                               | ((unsigned int)((pu >> bit) & 1ull) << 4) | ((unsigned int)((qu >> bit) & 1ull) << 5)
                               | ((unsigned int)((pu >> (bit + 4)) & 1ull) << 6) | ((unsigned int)((qu >> (bit + 4)) & 1ull) << 7);
-      if (at < capacity) list[at] = C3D_ENTRY(obj, x + (unsigned int)(bit & 3), j + (unsigned int)(bit >> 2), k, code);
+      if (at < capacity) list[at] = C3D_ENTRY(obj, x + (unsigned int)(bit & 3), j + (unsigned int)(bit >> 2), k, code) | flag;
       at++;
     }
   }

@@ -85,6 +85,8 @@ typedef struct {
   uint32_t sweep_thresholds[16]; /* iso-values classified by each sweep launch */
   uint64_t active_cubes[16];     /* per contour object, rendered range */
   uint64_t culled_cubes;         /* cut cubes the raster skipped because the z-buffer already hid them */
+  uint64_t culled_triangles;     /* triangles of the remaining cubes dropped by the per-triangle pre-test */
+  uint64_t shade_spills;         /* shading sub-batches that took the one-thread-per-vertex path */
   uint32_t nsweeps;
   uint32_t ncontours;
   uint32_t launches;             /* kernels launched by this library in the frame */

@@ -183,6 +183,28 @@ def test_frame_exact_threshold_hits_nan_normals(ctx):
     assert np.array_equal(depth, odepth)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_frame_collapsed_triangles_behind_occluders(ctx, dtype):
+    """Grid values exactly on the iso-value collapse triangles to points, which the reference draws as +-1 pixel
+    blobs of infinite depth (clamped area, render.c:103-106 -> weights +-0 -> 1 / +-0): they show through nearer
+    surfaces.  The raster's visibility shortcuts (cube / triangle occlusion tests, front-to-back order) must not
+    lose them: such cubes are flagged by k_expand and always take the exact path."""
+    n = 40
+    f = scenes.noise(n, seed=21).astype(dtype)
+    thr_in, thr_out = dtype(0.05), dtype(-0.25)
+    rng = np.random.default_rng(5)
+    for _ in range(120):                                  # exact hits deep inside, below the outer surface
+        k, j, i = rng.integers(6, n - 6, size=3)
+        f[k, j, i] = thr_in
+    g = scenes.uniform_grids(n, n, n)
+    scene = scenes.scene(480, 270)
+    contours = [dict(threshold=float(thr_out), color=(250, 160, 60)), dict(threshold=float(thr_in), color=(60, 160, 250))]
+    img, want, depth, odepth, _ = _render_both(ctx, scene, [f], g, contours, scenes.box_lines(nitems=10, width=2.0))
+    _assert_image(img, want)
+    assert np.array_equal(depth, odepth)
+    assert np.isinf(odepth).any(), "the scene was meant to contain collapsed triangles (infinite depth)"
+
+
 def test_dropin_contour3d_execute_host_buffers(ctx, tmp_path):
     """the public entry point, host double arrays in, PPM file out; config 1 in miniature"""
     g = load_golden("frame_sines24.npz")
