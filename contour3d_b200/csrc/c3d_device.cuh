@@ -213,11 +213,8 @@ __device__ __forceinline__ long long clamp_ll(const long long lo, const long lon
   return hi < m ? hi : m;
 }
 
-__device__ __forceinline__ bool setup_triangle(const Cam &c, const V3 v[3], Tri2D &t) {
-#pragma unroll
-  for (int m = 0; m < 3; m++) {
-    if (!project(c, v[m], t.q[m])) return false;    /* render.c:62-72 */
-  }
+/* bounding box, edge differences and inverse area of a triangle whose projected vertices t.q[] are set */
+__device__ __forceinline__ void setup_projected(const Cam &c, Tri2D &t) {
   const double xlo = fmin(t.q[0].x, fmin(t.q[1].x, t.q[2].x));
   const double xhi = fmax(t.q[0].x, fmax(t.q[1].x, t.q[2].x));
   const double ylo = fmin(t.q[0].y, fmin(t.q[1].y, t.q[2].y));
@@ -240,6 +237,14 @@ __device__ __forceinline__ bool setup_triangle(const Cam &c, const V3 v[3], Tri2
   /* area = edge_function(v0, v1, v2), render.c:102: a = q0, b = q1 (edge 2), evaluated at q2 */
   const double area = r_sub(r_mul(r_sub(t.q[2].x, t.q[0].x), t.ey[2]), r_mul(r_sub(t.q[2].y, t.q[0].y), t.ex[2]));
   t.area_inv = r_div(1., area < 0. ? fmin(area, -1.e-16) : fmax(area, +1.e-16));
+}
+
+__device__ __forceinline__ bool setup_triangle(const Cam &c, const V3 v[3], Tri2D &t) {
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    if (!project(c, v[m], t.q[m])) return false;    /* render.c:62-72 */
+  }
+  setup_projected(c, t);
   return true;
 }
 
@@ -292,3 +297,17 @@ __device__ __forceinline__ void submit_fragment(Pixel *slot, const unsigned long
     cur = prev;
   }
 }
+
+/* Out-of-line on purpose: the raster and shading kernels are large, and their warps sit in different phases;
+   one shared copy of "cut the edge and project" keeps the hot code within reach of the instruction cache. */
+/* triangle vertex on the cube edge tail -> head (triangulate.c:40-73), projected (project.c:9-67);
+   returned by value (registers), .w = 1 when the projection accepted the point */
+struct ProjectedVertex { double x, y, z, w; };
+static __device__ __noinline__ ProjectedVertex exact_vertex(const FrameParams &p, const unsigned int obj, const long long i, const long long j,
+                                                            const long long k, const unsigned int tail, const unsigned int head) {
+  const FieldView &f = p.view[obj];
+  V3 q = V3{0., 0., 0.};
+  const bool ok = project(p.cam, cut_edge_global(f, i, j, k, f.thr, tail, head), q);
+  return ProjectedVertex{q.x, q.y, q.z, ok ? 1. : 0.};
+}
+

@@ -285,13 +285,17 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
                                                 Pixel *__restrict__ canvas) {
   const unsigned int obj = C3D_ENTRY_OBJ(entry), code = C3D_ENTRY_CODE(entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
-  const FieldView &f = p.view[obj];
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
-  V3 v[3];
-#pragma unroll
-  for (int m = 0; m < 3; m++) v[m] = cut_edge_global(f, i, j, k, f.thr, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
   Tri2D t;
-  if (!setup_triangle(p.cam, v, t)) return;
+  /* one out-of-line copy of "cut the edge and project" serves the three vertices: the kernel's code must stay
+     within reach of the instruction cache while its warps sit in different phases */
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const ProjectedVertex v = exact_vertex(p, obj, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+    if (0. == v.w) return;                          /* render.c:62-72 */
+    t.q[m] = V3{v.x, v.y, v.z};
+  }
+  setup_projected(p.cam, t);
   const unsigned long long mykey = ((unsigned long long)(obj + 1u) << C3D_KEY_OBJ_SHIFT)
                                  | ((unsigned long long)k << 36) | ((unsigned long long)j << 20) | ((unsigned long long)i << 4) | s;
   /*
@@ -445,7 +449,7 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsi
   const long long base = k * f.sz + j * f.sy + i;
   const float thr = (float)f.thr;
   float xlo = 3.e38f, xhi = -3.e38f, ylo = 3.e38f, yhi = -3.e38f, znear = -3.e38f, zslack = 0.f;
-#pragma unroll
+#pragma unroll 1
   for (int m = 0; m < 3; m++) {
     const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
     const float v0 = (float)ld_value(f, base + (tail & 1u) + ((tail >> 1) & 1u) * f.sy + (tail >> 2) * f.sz);
@@ -573,7 +577,7 @@ extern "C" int c3d_k_raster(const FrameParams *p, const unsigned long long *list
   static int occ = -1;
   if (occ < 0) {
     const char *env = getenv("CONTOUR3D_RASTER_OCC");
-    occ = (NULL != env && '\0' != *env) ? atoi(env) : 5;
+    occ = (NULL != env && '\0' != *env) ? atoi(env) : 6;
   }
   if (occ >= 8) k_raster<8><<<sm_count * 16, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
   else if (occ >= 6) k_raster<6><<<sm_count * 12, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);

@@ -161,11 +161,16 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_smooth(const __grid_consta
         const unsigned int code = cube_code(f, i, j, k);
         const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
         const unsigned int edges = __ldg(p.tab.edges + code * C3D_MAX_TRIS + s);
-        V3 v[3];
-#pragma unroll
-        for (int m = 0; m < 3; m++) v[m] = cut_edge_global(f, i, j, k, f.thr, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
         Tri2D t;
-        if (setup_triangle(p.cam, v, t)) {
+        bool ok = true;
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const ProjectedVertex v = exact_vertex(p, obj, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+          ok = ok && (0. != v.w);
+          t.q[m] = V3{v.x, v.y, v.z};
+        }
+        if (ok) {
+          setup_projected(p.cam, t);
           pixel_weights(t, __ldg(p.px + (pix % (unsigned int)p.cam.w)), __ldg(p.py + (pix / (unsigned int)p.cam.w)), me.w);
         }
         me.valid = 1;
