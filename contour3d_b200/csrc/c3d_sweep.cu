@@ -9,15 +9,20 @@
  * tessellation runs on the >90 % of cubes that the surface does not cut.
  *
  * Design (sm_100a):
- *  - every warp owns tiles of 124 x 31 cubes (128 x 32 points) and marches
- *    through `zc` planes; tiles are handed out by an atomic cursor;
- *  - rows travel HBM -> shared memory as 1-D bulk async copies
- *    (cp.async.bulk ... mbarrier::complete_tx::bytes, SASS UBLKCP) into a
- *    warp-private ring of 3-4 slots of 8 rows, so 12-16 KiB per warp are
- *    always in flight and no register is tied up by a load;
+ *  - every warp owns tiles of 128 x 31 cubes and marches through `zc` planes;
+ *    tiles are handed out by an atomic cursor;
+ *  - the field travels HBM -> shared memory through the TMA engine: ONE
+ *    cp.async.bulk.tensor.3d (SASS UTMALDG) per 8 rows x (128 + pad) points,
+ *    described by a tensor map of the extended array (points outside it are
+ *    zero-filled and never reported), completion counted in bytes on an
+ *    mbarrier, into a warp-private ring of 3-4 slots, so 12-16 KiB per warp
+ *    are always in flight, no register is tied up by a load and no lane
+ *    computes an address;
  *  - a lane reads its 4 points of a row with one LDS.128 and folds
  *    `thr < v` of the 4 points into bit 4r+c of a 32-bit word per iso-value
- *    (8 rows x 4 points; FSET + LOP3 each), so one word describes 32 points;
+ *    (8 rows x 4 points; FSET + FFMA each), so one word describes 32 points;
+ *    the point right of the tile (x + 128, the pad of each row) is classified
+ *    by lanes 0, 4, .. 28 and reaches lane 31 through one ballot;
  *  - "is the cube cut?" is evaluated for 32 cubes per lane at once with ~12
  *    word-wide logic instructions (OR/AND over the 8 corners, built from a
  *    1-lane shuffle for x+1, a 4-bit funnel shift for y+1 and the previous
@@ -33,11 +38,13 @@
  */
 #include <float.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <cuda.h>           /* CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint) */
 #include "c3d_internal.h"
 
 #define SW_ROWS 8           /* rows per slot = rows per 32-bit word */
 #define SW_GROUPS 4         /* row groups per tile: 32 point rows, 31 cube rows */
-#define SW_XCUBES 124       /* cubes per tile row (lane 31 only supplies the x+1 neighbour) */
+#define SW_XCUBES 128       /* cubes per tile row: 4 per lane; the x+1 neighbour of lane 31 is the row's pad point */
 #define SW_YCUBES 31
 #define SW_STAGE 32         /* records staged per warp before a flush */
 #define SW_FULL 0xffffffffu
@@ -51,9 +58,16 @@ struct SweepRecord {        /* 32 bytes: the corner bits of a 4 (x) x 8 (y) patc
   unsigned int kobj;        /* k | object << 16 */
 };
 
+/* shared-memory geometry of one row: 128 points + one 16-byte unit that carries the point right of the tile */
+template <typename T> struct RowGeom {
+  static constexpr unsigned int PAD = 16u / sizeof(T);
+  static constexpr unsigned int ROWP = SW_XCUBES + PAD;
+  static constexpr unsigned int ROWB = ROWP * sizeof(T);
+  static constexpr unsigned int SLOTB = SW_ROWS * ROWB;       /* 4224 / 8320 bytes: multiples of 128 */
+};
+
 struct TileSweepParams {
-  const void *data;
-  long long mx, my, mz, sy, sz;
+  long long mx, my, mz;
   int nthr;
   float thr_ge[C3D_SWEEP_MAX_THR];   /* fp32 fields: thr < (double)v  <=>  v >= thr_ge */
   double thr[C3D_SWEEP_MAX_THR];     /* fp64 fields: thr < v */
@@ -87,10 +101,11 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
       "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
       : "memory");
 }
-/* 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, no tensor map needed) */
-__device__ __forceinline__ void bulk_g2s(const uint32_t dst, const void *src, const uint32_t bytes, const uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-               "r"(bar)
+/* one box of the tensor map (x, y, z: point coordinates of its first element) global -> shared; the whole box,
+   zero-filled where it leaves the array, counts towards the mbarrier's transaction bytes */
+__device__ __forceinline__ void tma_box_g2s(const uint32_t dst, const CUtensorMap *map, const int x, const int y, const int z, const uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -118,6 +133,7 @@ template <> struct GroupBits<float> {
     else hi = fmaf(one, weight, hi);
   }
   __device__ __forceinline__ unsigned int word() const { return __float2uint_rz(lo) | (__float2uint_rz(hi) << 16); }
+  __device__ static __forceinline__ bool above(const float v, const float thr_ge) { return v >= thr_ge; }
 };
 template <> struct GroupBits<double> {
   unsigned int w;
@@ -126,6 +142,7 @@ template <> struct GroupBits<double> {
     if (thr < v) w |= 1u << (4 * R + C);
   }
   __device__ __forceinline__ unsigned int word() const { return w; }
+  __device__ static __forceinline__ bool above(const double v, const double thr) { return thr < v; }
 };
 
 template <typename T> struct Thr;
@@ -155,7 +172,7 @@ __device__ __forceinline__ Quad4<double> lds_quad(const double *row, const unsig
 template <typename T, int NT, int R>
 __device__ __forceinline__ void RowFold<T, NT, R>::run(const T *rows, const unsigned int lane, const TileSweepParams &p, GroupBits<T> (&acc)[NT]) {
   if constexpr (R < SW_ROWS) {
-    const Quad4<T> v = lds_quad(rows + R * 128, lane);
+    const Quad4<T> v = lds_quad(rows + R * RowGeom<T>::ROWP, lane);
 #pragma unroll
     for (int t = 0; t < NT; t++) {
       const auto thr = Thr<T>::get(p, t);
@@ -170,14 +187,14 @@ __device__ __forceinline__ void RowFold<T, NT, R>::run(const T *rows, const unsi
 
 /*
  * One warp = one tile at a time.  Shared memory per warp:
- *   ring   SW_SLOTS x SW_ROWS rows x 128 points
+ *   ring   SW_SLOTS x SW_ROWS rows x (128 + pad) points
  *   stage  SW_STAGE records
  *   bars   SW_SLOTS mbarriers
  */
 template <typename T, int NT, int WARPS, int SW_SLOTS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_constant__ TileSweepParams p) {
-  constexpr unsigned int ROWB = 128u * sizeof(T);
-  constexpr unsigned int SLOTB = SW_ROWS * ROWB;
+__global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_constant__ TileSweepParams p, const __grid_constant__ CUtensorMap tmap) {
+  constexpr unsigned int ROWB = RowGeom<T>::ROWB;
+  constexpr unsigned int SLOTB = RowGeom<T>::SLOTB;
   extern __shared__ __align__(128) unsigned char smem[];
   const unsigned int lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   unsigned char *ring = smem + (size_t)wid * (SW_SLOTS * SLOTB);
@@ -194,7 +211,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
 
   unsigned int cslot = 0u, cphase = 0u;     /* consume cursor of the ring (continues across tiles) */
   unsigned int fill = 0u;                   /* records waiting in the staging buffer */
-  const T *const base = static_cast<const T *>(p.data);
 
   auto flush = [&]() {
     __syncwarp();
@@ -228,15 +244,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
     const long long k0 = p.klo + (long long)zt * p.zc;
     const long long k1 = (k0 + p.zc - 1 < p.khi) ? k0 + p.zc - 1 : p.khi;
     const int nplanes = (int)(k1 - k0) + 2;                 /* point planes k0 .. k1 + 1 */
-    const long long xleft = p.mx - x0;
-    const uint32_t xbytes = (uint32_t)((xleft < 128 ? xleft : 128) * (long long)sizeof(T));
-    /* rows available per group; valid groups form a prefix */
-    int nrows[SW_GROUPS], ng = 0;
+    /* row groups that hold at least one row of the array (a prefix); the rest of a box is zero-filled */
+    int ng = 0;
 #pragma unroll
     for (int g = 0; g < SW_GROUPS; g++) {
-      const long long left = p.my - (j0 + SW_ROWS * g);
-      nrows[g] = (int)(left < 0 ? 0 : (left > SW_ROWS ? SW_ROWS : left));
-      if (nrows[g] > 0) ng = g + 1;
+      if (j0 + SW_ROWS * g < p.my) ng = g + 1;
     }
     /* which of my 32 cubes per group may be reported */
     unsigned int valid[SW_GROUPS];
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         const long long i = x0 + 4 * (long long)lane + c;
-        if (lane < 31u && i >= p.ilo && i <= p.ihi) xm |= 1u << c;
+        if (i >= p.ilo && i <= p.ihi) xm |= 1u << c;
       }
 #pragma unroll
       for (int g = 0; g < SW_GROUPS; g++) {
@@ -263,15 +275,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
     const int nsteps = nplanes * ng;
     int ipl = 0, ig = 0, issued = 0;
     unsigned int islot = cslot;
+    const int tx = (int)x0, ty = (int)j0;
+    const int tz = (int)(p.flip[2] ? k1 + 1 : k0), tdz = p.flip[2] ? -1 : 1;
     auto issue = [&]() {
-      const int rows = (0 == ig) ? nrows[0] : (1 == ig) ? nrows[1] : (2 == ig) ? nrows[2] : nrows[3];
-      const uint32_t bar = bars_s + 8u * islot;
-      if (0u == lane) mbar_expect_tx(bar, (uint32_t)rows * xbytes);
-      __syncwarp();
-      if ((int)lane < rows) {
-        const long long plane = p.flip[2] ? k1 + 1 - ipl : k0 + ipl;
-        const T *src = base + plane * p.sz + (j0 + SW_ROWS * ig + (long long)lane) * p.sy + x0;
-        bulk_g2s(ring_s + islot * SLOTB + lane * ROWB, src, xbytes, bar);
+      if (0u == lane) {
+        const uint32_t bar = bars_s + 8u * islot;
+        mbar_expect_tx(bar, SLOTB);
+        tma_box_g2s(ring_s + islot * SLOTB, &tmap, tx, ty + SW_ROWS * ig, tz + tdz * ipl, bar);
       }
       issued++;
       if (++ig == ng) { ig = 0; ipl++; }
@@ -298,11 +308,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
 #pragma unroll 1
       for (int g = 0; g < SW_GROUPS; g++) {
         GroupBits<T> acc[NT];
+        unsigned int edge[NT];                /* bit 4r: the point right of the tile (x0 + 128) in row r is above */
 #pragma unroll
-        for (int t = 0; t < NT; t++) acc[t].clear();
+        for (int t = 0; t < NT; t++) { acc[t].clear(); edge[t] = 0u; }
         if (g < ng) {
           mbar_wait(bars_s + 8u * cslot, cphase);
-          RowFold<T, NT, 0>::run(reinterpret_cast<const T *>(ring + cslot * SLOTB), lane, p, acc);
+          const T *rows = reinterpret_cast<const T *>(ring + cslot * SLOTB);
+          RowFold<T, NT, 0>::run(rows, lane, p, acc);
+          const T pad = rows[(lane >> 2) * RowGeom<T>::ROWP + SW_XCUBES];
+#pragma unroll
+          for (int t = 0; t < NT; t++) edge[t] = __ballot_sync(SW_FULL, 0u == (lane & 3u) && GroupBits<T>::above(pad, Thr<T>::get(p, t)));
           /* the slot is free again: refill it SW_SLOTS steps ahead */
           fence_proxy_async();
           __syncwarp();
@@ -312,7 +327,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
 #pragma unroll
         for (int t = 0; t < NT; t++) {
           const unsigned int w = acc[t].word();
-          const unsigned int right = __shfl_down_sync(SW_FULL, w, 1);
+          const unsigned int nb = __shfl_down_sync(SW_FULL, w, 1);
+          const unsigned int right = 31u == lane ? edge[t] : nb;
 #pragma unroll
           for (int h = 0; h + 1 < SW_GROUPS; h++) { UP[t][h] = UP[t][h + 1]; UQ[t][h] = UQ[t][h + 1]; }
           UP[t][SW_GROUPS - 1] = w;
@@ -583,20 +599,59 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ FramePar
 /* ---------------------------------------------------------------- launchers */
 
 template <typename T, int NT, int WARPS, int SW_SLOTS>
-static int launch_tiles(const TileSweepParams &p, const int sm_count, cudaStream_t s) {
-  const size_t smem = (size_t)WARPS * (SW_SLOTS * SW_ROWS * 128 * sizeof(T) + SW_STAGE * sizeof(SweepRecord) + SW_SLOTS * 8);
+static int launch_tiles(const TileSweepParams &p, const CUtensorMap &tmap, const int sm_count, cudaStream_t s) {
+  const size_t smem = (size_t)WARPS * (SW_SLOTS * RowGeom<T>::SLOTB + SW_STAGE * sizeof(SweepRecord) + SW_SLOTS * 8);
   /* per device, so not cached in a static */
   const cudaError_t err = cudaFuncSetAttribute(k_sweep_tiles<T, NT, WARPS, SW_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (cudaSuccess != err) return (int)err;
   const unsigned int need = (p.ntiles + WARPS - 1) / WARPS;
   const unsigned int blocks = need < (unsigned int)sm_count ? need : (unsigned int)sm_count;
-  k_sweep_tiles<T, NT, WARPS, SW_SLOTS><<<blocks, WARPS * 32, smem, s>>>(p);
+  k_sweep_tiles<T, NT, WARPS, SW_SLOTS><<<blocks, WARPS * 32, smem, s>>>(p, tmap);
   return (int)cudaGetLastError();
 }
 
-extern "C" int c3d_k_sweep_tiles_ok(const FieldView *f) {
+/* cuTensorMapEncodeTiled through the runtime (libcuda is not a link-time dependency) */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled(void) {
+  static EncodeTiledFn fn = NULL;
+  if (NULL == fn) {
+    void *sym = NULL;
+    cudaDriverEntryPointQueryResult found = cudaDriverEntryPointSymbolNotFound;
+    if (cudaSuccess == cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &found) && cudaDriverEntryPointSuccess == found) {
+      fn = (EncodeTiledFn)sym;
+    }
+  }
+  return fn;
+}
+
+/* tensor map of the extended array: boxes of 8 rows x (128 + pad) points of one plane, zero fill outside */
+static int make_tensor_map(const FieldView *f, CUtensorMap *map) {
+  const EncodeTiledFn encode = encode_tiled();
+  if (NULL == encode) return (int)cudaErrorNotSupported;
   const size_t eb = (size_t)f->elem_bytes;
-  return (0 == ((uintptr_t)f->data % 16)) && (0 == (f->sy * eb) % 16) && (0 == (f->sz * eb) % 16) && (0 == (f->n[0] * eb) % 16);
+  const cuuint64_t dims[3] = {(cuuint64_t)f->n[0], (cuuint64_t)f->n[1], (cuuint64_t)f->n[2]};
+  const cuuint64_t strides[2] = {(cuuint64_t)f->sy * eb, (cuuint64_t)f->sz * eb};
+  const cuuint32_t box[3] = {4 == eb ? RowGeom<float>::ROWP : RowGeom<double>::ROWP, SW_ROWS, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  static int promo = -1;
+  if (promo < 0) {
+    const char *env = getenv("CONTOUR3D_SWEEP_L2PROMO");
+    promo = (NULL != env && '\0' != *env) ? atoi(env) : 2;
+  }
+  const CUtensorMapL2promotion l2 = 0 == promo ? CU_TENSOR_MAP_L2_PROMOTION_NONE : 1 == promo ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                  : 2 == promo ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  const CUresult rc = encode(map, 4 == eb ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3u, const_cast<void *>(f->data), dims,
+                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return CUDA_SUCCESS == rc ? 0 : (int)cudaErrorInvalidValue;
+}
+
+extern "C" int c3d_k_sweep_tiles_ok(const FieldView *f) {
+  /* what a tensor map asks of the array: 16-byte aligned base and strides, strides below 2^40 bytes */
+  const size_t eb = (size_t)f->elem_bytes;
+  return (0 == ((uintptr_t)f->data % 16)) && (0 == (f->sy * eb) % 16) && (0 == (f->sz * eb) % 16) && (f->sz * eb < (1ull << 40))
+      && (f->sy >= f->n[0]) && (NULL != encode_tiled());
 }
 
 extern "C" int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nthr, const double *thr, const float *thr_ge, const unsigned int *obj,
@@ -604,9 +659,7 @@ extern "C" int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nt
                                  int sm_count, cudaStream_t s) {
   if (nthr < 1 || nthr > C3D_SWEEP_MAX_THR) return (int)cudaErrorInvalidValue;
   TileSweepParams p;
-  p.data = f->data;
   p.mx = f->n[0]; p.my = f->n[1]; p.mz = f->n[2];
-  p.sy = f->sy; p.sz = f->sz;
   p.nthr = nthr;
   for (int t = 0; t < C3D_SWEEP_MAX_THR; t++) {
     const int u = t < nthr ? t : 0;
@@ -621,7 +674,12 @@ extern "C" int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nt
   p.nyt = (int)((p.jhi - p.jlo + SW_YCUBES) / SW_YCUBES);
   const long long nk = p.khi - p.klo + 1;
   /* planes per tile: enough tiles for ~6 per resident warp (dynamic hand-out evens the tail), at most 1/32 z re-reads */
-  const int warps = 4 == f->elem_bytes ? (nthr >= 3 ? 12 : 16) : 8;
+  static int wide = -1;         /* experiment switch: 16 warps x 3 slots instead of 12 x 4 for 3-4 fused iso-values */
+  if (wide < 0) {
+    const char *env = getenv("CONTOUR3D_SWEEP_WARPS");
+    wide = (NULL != env && 16 == atoi(env)) ? 1 : 0;
+  }
+  const int warps = 4 == f->elem_bytes ? ((nthr >= 3 && !wide) ? 12 : 16) : 8;
   const long long per_chunk = (long long)p.nxt * p.nyt;
   const long long want_tiles = 6ll * warps * sm_count;
   long long chunks = (want_tiles + per_chunk - 1) / per_chunk;
@@ -635,21 +693,24 @@ extern "C" int c3d_k_sweep_tiles(const FieldView *f, const SweepRange *r, int nt
   p.records = static_cast<SweepRecord *>(records);
   p.count = count;
   p.capacity = capacity;
+  CUtensorMap tmap;
+  const int rc = make_tensor_map(f, &tmap);
+  if (0 != rc) return rc;
   const cudaError_t err = cudaMemsetAsync(tile_cursor, 0, sizeof(unsigned int), s);
   if (cudaSuccess != err) return (int)err;
   if (4 == f->elem_bytes) {
     switch (nthr) {
-      case 1: return launch_tiles<float, 1, 16, 3>(p, sm_count, s);
-      case 2: return launch_tiles<float, 2, 16, 3>(p, sm_count, s);
-      case 3: return launch_tiles<float, 3, 12, 4>(p, sm_count, s);
-      default: return launch_tiles<float, 4, 12, 4>(p, sm_count, s);
+      case 1: return launch_tiles<float, 1, 16, 3>(p, tmap, sm_count, s);
+      case 2: return launch_tiles<float, 2, 16, 3>(p, tmap, sm_count, s);
+      case 3: return wide ? launch_tiles<float, 3, 16, 3>(p, tmap, sm_count, s) : launch_tiles<float, 3, 12, 4>(p, tmap, sm_count, s);
+      default: return launch_tiles<float, 4, 12, 4>(p, tmap, sm_count, s);
     }
   }
   switch (nthr) {
-    case 1: return launch_tiles<double, 1, 8, 3>(p, sm_count, s);
-    case 2: return launch_tiles<double, 2, 8, 3>(p, sm_count, s);
-    case 3: return launch_tiles<double, 3, 8, 3>(p, sm_count, s);
-    default: return launch_tiles<double, 4, 8, 3>(p, sm_count, s);
+    case 1: return launch_tiles<double, 1, 8, 3>(p, tmap, sm_count, s);
+    case 2: return launch_tiles<double, 2, 8, 3>(p, tmap, sm_count, s);
+    case 3: return launch_tiles<double, 3, 8, 3>(p, tmap, sm_count, s);
+    default: return launch_tiles<double, 4, 8, 3>(p, tmap, sm_count, s);
   }
 }
 
