@@ -77,6 +77,8 @@ struct __align__(16) Pixel { unsigned long long depth, key; };
 
 #define C3D_MAX_OBJECTS 16
 #define C3D_DEPTH_BUCKETS 2048        /* view-depth slabs of the front-to-back ordering (multiple of 1024) */
+#define C3D_HIZ_TILE 8                /* pixels per side of a coarse z-buffer tile */
+#define C3D_RASTER_PARTS 64u          /* the raster's list is cut at multiples of 1/64 of its length */
 #define C3D_SWEEP_MAX_THR 4        /* iso-values of one array classified by a single sweep launch */
 
 struct SweepRange { long long lo[3], hi[3]; }; /* inclusive cube ranges to emit */
@@ -122,8 +124,13 @@ int c3d_k_expand(const FrameParams *fp, int sorted, float near_depth, float far_
                  const void *records, const unsigned long long *nrecords, unsigned long long rec_capacity, unsigned long long *list,
                  unsigned long long *count, unsigned long long capacity, unsigned int *histogram, unsigned long long *cursors,
                  unsigned long long *per_object, unsigned int nobjects, int sm_count, cudaStream_t s);
+/* draws the entries [n * part_begin / C3D_RASTER_PARTS, n * part_end / C3D_RASTER_PARTS) of the list; hiz_tiles may be NULL */
 int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const unsigned long long *count, unsigned long long capacity,
-                 Pixel *canvas, unsigned long long *culled, int sm_count, cudaStream_t s);
+                 Pixel *canvas, unsigned long long *culled, const unsigned long long *hiz_tiles, unsigned int part_begin,
+                 unsigned int part_end, int sm_count, cudaStream_t s);
+int c3d_k_hiz_build(const Pixel *canvas, long long w, long long h, unsigned long long *tiles, int sm_count, cudaStream_t s);
+int c3d_k_overflow_flag(const unsigned long long *nrec, unsigned long long rec_cap, const unsigned long long *nlist,
+                        unsigned long long list_cap, unsigned long long *flag, cudaStream_t s);
 int c3d_k_lines(const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines, unsigned long long first_obj,
                 Pixel *canvas, cudaStream_t s);
 int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t npix, cudaStream_t s);

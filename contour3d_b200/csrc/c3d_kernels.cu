@@ -367,6 +367,31 @@ __device__ __forceinline__ bool region_hidden(const Pixel *__restrict__ canvas, 
   return true;
 }
 
+/* Coarse z-buffer ("Hi-Z"): one word per C3D_HIZ_TILE x C3D_HIZ_TILE pixel tile = the FARTHEST depth stored in the tile when
+   the table was built (k_hiz_build), across ranks the maximum of that (ncclMax).  Stored depths only grow
+   (render.c:125-132), so every pixel of the tile holds -- on the rank that will win it -- at least this depth for the
+   rest of the frame: a region whose tiles all exceed `limit` is hidden, by the same argument as region_hidden(),
+   without touching the pixels and including what OTHER ranks have drawn in front.  Undecided (false) otherwise. */
+struct HiZ {
+  const unsigned long long *tile;    /* nullptr: no table */
+  int tw;                            /* tiles per row */
+};
+
+__device__ __forceinline__ bool hiz_hidden(const HiZ &z, const CullCam &q, const float x0, const float x1, const float y0, const float y1,
+                                           const unsigned long long limit) {
+  const int imin = max(0, (int)ceilf(x0)), imax = min(q.w - 1, (int)floorf(x1));
+  const int jmin = max(0, (int)ceilf(y0)), jmax = min(q.h - 1, (int)floorf(y1));
+  if (imax < imin || jmax < jmin) return true;              /* no pixel centre inside: nothing can be drawn */
+  const int ti0 = imin / C3D_HIZ_TILE, ti1 = imax / C3D_HIZ_TILE, tj0 = jmin / C3D_HIZ_TILE, tj1 = jmax / C3D_HIZ_TILE;
+  if ((ti1 - ti0 + 1) * (tj1 - tj0 + 1) > 16) return false;
+  for (int tj = tj0; tj <= tj1; tj++) {
+    for (int ti = ti0; ti <= ti1; ti++) {
+      if (__ldg(z.tile + (long long)tj * z.tw + ti) <= limit) return false;
+    }
+  }
+  return true;
+}
+
 /*
  * Conservative occlusion test of a whole cube against the z-buffer as it
  * stands: true only when every pixel any of the cube's triangles could touch
@@ -376,7 +401,7 @@ __device__ __forceinline__ bool region_hidden(const Pixel *__restrict__ canvas, 
  * fp32 error (0.25 pixel, 1e-4 relative depth); anything doubtful is kept.
  * With a depth complexity of ~20 most cubes of a turbulent field are hidden.
  */
-__device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned long long entry, const Pixel *__restrict__ canvas) {
+__device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned long long entry, const Pixel *__restrict__ canvas, const HiZ &hiz) {
   /* A triangle whose vertices have collapsed onto one cube corner is drawn by the reference as a blob: the
      clamped area (render.c:103-106) makes all three weights +-0, every pixel of the +-1 pixel box passes the
      inside test and the depth is 1 / +-0 = +-inf -- it beats any finite depth.  Collapse needs an interpolation
@@ -419,9 +444,9 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
   /* a fragment exists only where a PIXEL CENTRE lies inside a triangle (render.c:94-115; the +-1 pixel box of
      render.c:81-89 is just the search range), and every triangle lies inside the hull of the corners:
      the pixels to look at are those whose centre (i + 0.5) / W - 0.5 falls within the bounds, +- 0.05 pixel */
-  if (!region_hidden(canvas, q, (0.5f + xlo) * q.W - 0.55f, (0.5f + xhi) * q.W - 0.45f, (0.5f + ylo) * q.H - 0.55f,
-                     (0.5f + yhi) * q.H - 0.45f, true, limit)) return false;
-  return true;
+  const float X0 = (0.5f + xlo) * q.W - 0.55f, X1 = (0.5f + xhi) * q.W - 0.45f, Y0 = (0.5f + ylo) * q.H - 0.55f, Y1 = (0.5f + yhi) * q.H - 0.45f;
+  if (nullptr != hiz.tile && hiz_hidden(hiz, q, X0, X1, Y0, Y1, limit)) return true;
+  return region_hidden(canvas, q, X0, X1, Y0, Y1, true, limit);
 }
 
 /*
@@ -493,7 +518,8 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsi
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ list,
                                                      const unsigned long long *__restrict__ count, const unsigned long long capacity,
-                                                     Pixel *__restrict__ canvas, unsigned long long *__restrict__ culled) {
+                                                     Pixel *__restrict__ canvas, unsigned long long *__restrict__ culled,
+                                                     const HiZ hiz, const unsigned int part_begin, const unsigned int part_end) {
   __shared__ unsigned long long s_entry[4][32];
   __shared__ unsigned int s_first[4][32];
   __shared__ unsigned long long s_queue[4][64];       /* triangles that passed the pre-test, waiting for a full warp */
@@ -503,13 +529,16 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
   const unsigned long long warp = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + wid;
   const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
   unsigned int hidden_total = 0u, hidden_tris = 0u, queued = 0u;
-  for (unsigned long long base = warp * 32ull; base < n; base += nwarps * 32ull) {
+  /* this launch draws the entries [n * part_begin / 64, n * part_end / 64) of the nearest-first list (whole warps of 32) */
+  const unsigned long long first = (n * part_begin / C3D_RASTER_PARTS) & ~31ull;
+  if (part_end < C3D_RASTER_PARTS) n = (n * part_end / C3D_RASTER_PARTS) & ~31ull;
+  for (unsigned long long base = first + warp * 32ull; base < n; base += nwarps * 32ull) {
     unsigned long long entry = 0ull;
     unsigned int ntri = 0u;
     if (base + lane < n) {
       entry = __ldg(list + base + lane);
       ntri = __ldg(p.tab.count + C3D_ENTRY_CODE(entry));
-      if (p.cull.enabled && cube_hidden(p, entry, canvas)) ntri = 0u;
+      if (p.cull.enabled && cube_hidden(p, entry, canvas, hiz)) ntri = 0u;
     }
     const unsigned int alive = __ballot_sync(C3D_FULL_MASK, ntri > 0u);
     hidden_total += __popc(__ballot_sync(C3D_FULL_MASK, base + lane < n)) - __popc(alive);
@@ -572,17 +601,65 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
 }
 
 extern "C" int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const unsigned long long *count, unsigned long long capacity,
-                            Pixel *canvas, unsigned long long *culled, int sm_count, cudaStream_t s) {
+                            Pixel *canvas, unsigned long long *culled, const unsigned long long *hiz_tiles, unsigned int part_begin,
+                            unsigned int part_end, int sm_count, cudaStream_t s) {
   /* resident blocks per SM: the kernel is bound by dependent fp64 chains, so more warps help until spills hurt (tuned by measurement) */
   static int occ = -1;
   if (occ < 0) {
     const char *env = getenv("CONTOUR3D_RASTER_OCC");
     occ = (NULL != env && '\0' != *env) ? atoi(env) : 6;
   }
-  if (occ >= 8) k_raster<8><<<sm_count * 16, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
-  else if (occ >= 6) k_raster<6><<<sm_count * 12, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
-  else if (occ >= 5) k_raster<5><<<sm_count * 10, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
-  else k_raster<4><<<sm_count * 8, 128, 0, s>>>(*p, list, count, capacity, canvas, culled);
+  if (part_end > C3D_RASTER_PARTS || part_begin >= part_end) return (int)cudaErrorInvalidValue;
+  HiZ hiz;
+  hiz.tile = hiz_tiles;
+  hiz.tw = (int)((p->cam.w + C3D_HIZ_TILE - 1) / C3D_HIZ_TILE);
+  if (occ >= 8) k_raster<8><<<sm_count * 16, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end);
+  else if (occ >= 6) k_raster<6><<<sm_count * 12, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end);
+  else if (occ >= 5) k_raster<5><<<sm_count * 10, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end);
+  else k_raster<4><<<sm_count * 8, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end);
+  return (int)cudaGetLastError();
+}
+
+/* farthest stored depth of every C3D_HIZ_TILE^2 pixel tile (pixels outside the screen do not count); one warp per tile */
+__global__ void __launch_bounds__(256) k_hiz_build(const Pixel *__restrict__ canvas, const int w, const int h, const int tw, const int th,
+                                                   unsigned long long *__restrict__ tiles) {
+  const unsigned int lane = threadIdx.x & 31u;
+  const int ntiles = tw * th;
+  for (int t = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); t < ntiles; t += (int)(gridDim.x * (blockDim.x >> 5))) {
+    const int ti = t % tw, tj = t / tw;
+    unsigned long long lo = ~0ull;
+    for (int q = (int)lane; q < C3D_HIZ_TILE * C3D_HIZ_TILE; q += 32) {
+      const int pi = ti * C3D_HIZ_TILE + q % C3D_HIZ_TILE, pj = tj * C3D_HIZ_TILE + q / C3D_HIZ_TILE;
+      if (pi < w && pj < h) {
+        const unsigned long long d = __ldcg(reinterpret_cast<const unsigned long long *>(canvas + (long long)pj * w + pi));
+        lo = d < lo ? d : lo;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(C3D_FULL_MASK, lo, d);
+      lo = other < lo ? other : lo;
+    }
+    if (0u == lane) tiles[t] = lo;
+  }
+}
+
+extern "C" int c3d_k_hiz_build(const Pixel *canvas, long long w, long long h, unsigned long long *tiles, int sm_count, cudaStream_t s) {
+  const int tw = (int)((w + C3D_HIZ_TILE - 1) / C3D_HIZ_TILE), th = (int)((h + C3D_HIZ_TILE - 1) / C3D_HIZ_TILE);
+  k_hiz_build<<<sm_count * 8, 256, 0, s>>>(canvas, (int)w, (int)h, tw, th, tiles);
+  return (int)cudaGetLastError();
+}
+
+/* flag[0] = 1 when a work buffer of this frame overflowed (agreed across ranks by ncclMax before anybody redoes the frame) */
+__global__ void k_overflow_flag(const unsigned long long *__restrict__ nrec, const unsigned long long rec_cap,
+                                const unsigned long long *__restrict__ nlist, const unsigned long long list_cap,
+                                unsigned long long *__restrict__ flag) {
+  *flag = (*nrec > rec_cap || *nlist > list_cap) ? 1ull : 0ull;
+}
+
+extern "C" int c3d_k_overflow_flag(const unsigned long long *nrec, unsigned long long rec_cap, const unsigned long long *nlist,
+                                   unsigned long long list_cap, unsigned long long *flag, cudaStream_t s) {
+  k_overflow_flag<<<1, 1, 0, s>>>(nrec, rec_cap, nlist, list_cap, flag);
   return (int)cudaGetLastError();
 }
 

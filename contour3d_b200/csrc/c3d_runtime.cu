@@ -101,7 +101,9 @@ struct c3d_field {
   bool halo_valid;
 };
 
-enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_CULLED_TRIS = 3, CNT_SHADE_SPILL = 4, CNT_OBJ = 5, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
+enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_CULLED_TRIS = 3, CNT_SHADE_SPILL = 4, CNT_OVERFLOW = 5, CNT_OBJ = 6, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
+#define C3D_HIZ_CUTS_MULTI "6,20,40"
+#define C3D_HIZ_CUTS_SINGLE ""
 enum { EV_START, EV_HALO, EV_CLEAR, EV_SWEEP, EV_EXPAND, EV_RASTER, EV_LINES, EV_RESOLVE, EV_REDUCE0, EV_SHADE, EV_REDUCE1, EV_PACK, EV_DOWNLOAD, EV_COUNT };
 
 struct c3d_context {
@@ -115,6 +117,9 @@ struct c3d_context {
   size_t npix_cap;
   Pixel *canvas;                                   /* (depth, winner key) per pixel */
   unsigned long long *depth_local, *depth_global;  /* multi-rank only: contiguous depth planes for ncclMax */
+  unsigned long long *hiz;                         /* coarse z-buffer: farthest depth per C3D_HIZ_TILE^2 pixels (c3d_k_hiz_build) */
+  int raster_cuts[C3D_RASTER_PARTS];               /* where the raster's list is cut for a Hi-Z refresh, in 1/64ths, ascending */
+  int nraster_cuts;
   double *pixel_xy;                                /* pixel-centre tables: width + height doubles */
   size_t table_w, table_h;
   unsigned int *rgba;
@@ -205,6 +210,21 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   CUDA_OK(cudaMalloc(&ctx->bucket_hist, C3D_DEPTH_BUCKETS * sizeof(unsigned int)));
   CUDA_OK(cudaMalloc(&ctx->bucket_cursors, C3D_DEPTH_BUCKETS * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->views_dev, C3D_MAX_OBJECTS * sizeof(FieldView)));
+  /* Hi-Z refresh points of the raster (see frame_once): "a,b,..." in 1/64ths of the nearest-first list, "" or "0" = none.
+     Several ranks: what the others have drawn in front is only known through this table, so it is on by default;
+     every rank must use the same cuts (each refresh is a collective). */
+  {
+    const char *env = getenv("CONTOUR3D_HIZ_CUTS");
+    const char *spec = NULL != env ? env : (comm_size > 1 ? C3D_HIZ_CUTS_MULTI : C3D_HIZ_CUTS_SINGLE);
+    int last = 0;
+    while ('\0' != *spec && ctx->nraster_cuts < (int)C3D_RASTER_PARTS - 1) {
+      char *end = NULL;
+      const long v = strtol(spec, &end, 10);
+      if (end == spec) break;
+      if (v > last && v < (long)C3D_RASTER_PARTS) ctx->raster_cuts[ctx->nraster_cuts++] = last = (int)v;
+      spec = (',' == *end) ? end + 1 : end;
+    }
+  }
   if (comm_size > 1) {
     if (NULL == nccl_id128) return c3d_error("c3d_context_create: %d ranks need an NCCL unique id", comm_size);
     if (0 != nccl_load()) return 1;
@@ -224,7 +244,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
   cudaFree(ctx->table_mem);
   cudaFree(ctx->shade_work); cudaFree(ctx->shade_nwork);
-  cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->pixel_xy); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
+  cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->hiz); cudaFree(ctx->pixel_xy); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
   if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
   cudaFree(ctx->list); cudaFree(ctx->records); cudaFree(ctx->tile_cursor); cudaFree(ctx->bucket_hist); cudaFree(ctx->bucket_cursors); cudaFree(ctx->counts_dev);
   if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
@@ -528,7 +548,8 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
   const size_t npix = w * h;
   if (npix > ctx->npix_cap) {
     cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
-    cudaFree(ctx->shade_work);
+    cudaFree(ctx->shade_work); cudaFree(ctx->hiz);
+    ctx->hiz = NULL;
     ctx->shade_work = NULL;
     if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
     ctx->canvas = NULL; ctx->depth_local = ctx->depth_global = NULL; ctx->rgba = NULL; ctx->ppm_dev = NULL; ctx->ppm_host = NULL;
@@ -539,6 +560,8 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
       CUDA_OK(cudaMalloc(&ctx->depth_global, npix * 8));
     }
     CUDA_OK(cudaMalloc(&ctx->rgba, npix * 4));
+    /* one word per pixel is an upper bound for any screen shape (a tile row / column may be partial) */
+    CUDA_OK(cudaMalloc(&ctx->hiz, (npix / 8 + w + h + 64) * sizeof(unsigned long long)));
     CUDA_OK(cudaMalloc(&ctx->shade_work, npix * 4));
     CUDA_OK(cudaMalloc(&ctx->ppm_dev, npix * 3));
     CUDA_OK(cudaMallocHost(&ctx->ppm_host, npix * 3));
@@ -788,9 +811,25 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_EXPAND], s));
   /* 2. tessellate + rasterise every active cube, contours in one launch (src/contour3d/main.c:105-117) */
+  /*    The nearest-first list is drawn in parts; between parts the coarse z-buffer is rebuilt from the canvas and,
+        with several ranks, maximised across them (1 MB at 4K): from then on a rank also drops the cubes that ANOTHER
+        rank has already hidden -- without this a slab behind its neighbours rasterises everything it owns.  The table is
+        only ever a lower bound of the final depths, so the image cannot change (cube_hidden, c3d_kernels.cu). */
   if (nc > 0) {
-    LAUNCH_OK(c3d_k_raster(&fp, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->canvas, ctx->counts_dev + CNT_CULLED, ctx->sm_count, s));
-    launches += 1;
+    const int ncuts = fp.cull.enabled ? ctx->nraster_cuts : 0;
+    const size_t ntiles = ((scene->width + C3D_HIZ_TILE - 1) / C3D_HIZ_TILE) * ((scene->height + C3D_HIZ_TILE - 1) / C3D_HIZ_TILE);
+    for (int part = 0; part <= ncuts; part++) {
+      const unsigned int begin = 0 == part ? 0u : (unsigned int)ctx->raster_cuts[part - 1];
+      const unsigned int end = part == ncuts ? C3D_RASTER_PARTS : (unsigned int)ctx->raster_cuts[part];
+      LAUNCH_OK(c3d_k_raster(&fp, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->canvas, ctx->counts_dev + CNT_CULLED,
+                             part > 0 ? ctx->hiz : NULL, begin, end, ctx->sm_count, s));
+      launches += 1;
+      if (part < ncuts) {
+        LAUNCH_OK(c3d_k_hiz_build(ctx->canvas, cam.w, cam.h, ctx->hiz, ctx->sm_count, s));
+        launches += 1;
+        if (ctx->size > 1) NCCL_OK(g_nccl.AllReduce(ctx->hiz, ctx->hiz, ntiles, ncclUint64, ncclMax, ctx->comm, s));
+      }
+    }
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_RASTER], s));
   /* 3. lines: drawn after the contours in the reference (main.c:119-129); their keys are larger, so they win ties */
@@ -824,6 +863,12 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   CUDA_OK(cudaEventRecord(ctx->ev[EV_PACK], s));
   const bool want_host = (0 == ctx->rank) && (NULL != host_rgb || NULL != fname);
   if (want_host) CUDA_OK(cudaMemcpyAsync(ctx->ppm_host, ctx->ppm_dev, 3 * npix, cudaMemcpyDeviceToHost, s));
+  if (ctx->size > 1) {
+    /* the frame is redone when a work buffer overflowed: all ranks must agree, the frame is full of collectives */
+    LAUNCH_OK(c3d_k_overflow_flag(ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->counts_dev + CNT_OVERFLOW, s));
+    NCCL_OK(g_nccl.AllReduce(ctx->counts_dev + CNT_OVERFLOW, ctx->counts_dev + CNT_OVERFLOW, 1, ncclUint64, ncclMax, ctx->comm, s));
+    launches += 1;
+  }
   CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaEventRecord(ctx->ev[EV_DOWNLOAD], s));
   CUDA_OK(cudaStreamSynchronize(s));
@@ -850,6 +895,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
       if (cudaSuccess != err) return c3d_error("failed to grow the active-cube list to %zu entries: %s", want, cudaGetErrorString(err));
       ctx->list_cap = want;
     }
+    if (0ull != ctx->counts_host[CNT_OVERFLOW]) *overflow = true;      /* another rank's buffer: redo with it */
     if (*overflow) return 0;
   }
   /* timings */

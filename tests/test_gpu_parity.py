@@ -205,6 +205,30 @@ def test_frame_collapsed_triangles_behind_occluders(ctx, dtype):
     assert np.isinf(odepth).any(), "the scene was meant to contain collapsed triangles (infinite depth)"
 
 
+@pytest.mark.parametrize("cuts", ["4,12,32", "1,2,3,5,8,13,21,34,55", ""])
+def test_frame_hiz_refresh_does_not_change_the_image(cuts, monkeypatch):
+    """The raster's list drawn in parts with a coarse z-buffer rebuilt in between (the cross-rank occlusion path of
+    N > 1, forced on here on one GPU): many nested surfaces so that most cubes are hidden; image and z-buffer stay exact."""
+    monkeypatch.setenv("CONTOUR3D_HIZ_CUTS", cuts)
+    own = api.Context(device=0)
+    try:
+        n = 56
+        f = scenes.noise(n, seed=77)
+        g = scenes.uniform_grids(n, n, n)
+        scene = scenes.scene(640, 360)
+        contours = [dict(threshold=float(np.float32(t)), color=c) for t, c in
+                    ((-0.35, (255, 80, 80)), (-0.1, (200, 200, 80)), (0.1, (80, 255, 80)), (0.3, (80, 80, 255)))]
+        img, want, depth, odepth, _ = _render_both(own, scene, [f], g, contours, scenes.box_lines(nitems=24, width=2.0))
+        _assert_image(img, want)
+        assert np.array_equal(depth, odepth)
+        t = own.timings()
+        if cuts:
+            assert t["launches"] >= 2 * len(cuts.split(",")), t["launches"]
+            assert t["culled_cubes"] > 0
+    finally:
+        own.destroy()
+
+
 def test_dropin_contour3d_execute_host_buffers(ctx, tmp_path):
     """the public entry point, host double arrays in, PPM file out; config 1 in miniature"""
     g = load_golden("frame_sines24.npz")
