@@ -254,6 +254,14 @@ def ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     elapsed_ms = float(tt.item())
     active = t["active_cubes"]
+    # where each rank spent the frame (the front slab of this camera owns most of the visible surface)
+    per_rank = None
+    if world > 1:
+        mine = {k: round(v / args.steps, 4) for k, v in stage_sum.items()}
+        mine["active_cubes"] = int(sum(active[:len(ISOVALUES)]))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
     voxels = size ** 3 * len(ISOVALUES)
     value = voxels * args.steps / (elapsed_ms * 1e-3) / 1e9
 
@@ -292,6 +300,7 @@ def ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "stages_ms": {k: v / args.steps for k, v in stage_sum.items()},
+            "stages_ms_per_rank": per_rank,
             "active_cubes": active, "culled_cubes": t["culled_cubes"], "culled_triangles": t["culled_triangles"], "shade_spills": t["shade_spills"],
         }
         print(json.dumps(line))

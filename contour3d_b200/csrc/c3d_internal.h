@@ -105,6 +105,18 @@ struct FrameParams {
   FieldView view[C3D_MAX_OBJECTS];
 };
 
+/* device scratch of the deferred shading (c3d_shade.cu), sized by the screen */
+#define C3D_SHADE_PIX_BYTES 56
+struct ShadeScratch {
+  unsigned int *work;            /* pixels won by a contour triangle, compacted: npix words */
+  unsigned int *counters;        /* [0] listed pixels, [1] distinct vertices */
+  void *pix;                     /* per listed pixel: weights, cube, vertex slots: npix x C3D_SHADE_PIX_BYTES */
+  unsigned long long *table;     /* open-addressing set of the vertices (global cube edges) the listed pixels reference */
+  unsigned int table_mask;       /* slots - 1 (a power of two) */
+  unsigned int *vlist;           /* occupied slots in order of first insertion: one word per slot */
+  double *vn;                    /* unit vertex normal of each slot: 3 doubles */
+};
+
 #if defined(__cplusplus)
 extern "C" {
 #endif
@@ -135,7 +147,7 @@ int c3d_k_lines(const Cam *c, const LineDev *lines_dev, const LineDev *lines_hos
                 Pixel *canvas, cudaStream_t s);
 int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t npix, cudaStream_t s);
 int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
-                unsigned int *rgba, size_t npix, unsigned int *work, unsigned int *nwork, unsigned long long *overflowed,
+                unsigned int *rgba, size_t npix, const ShadeScratch *scratch, unsigned long long *overflowed,
                 int sm_count, cudaStream_t s);
 int c3d_k_to_float(const double *in, float *out, size_t n, cudaStream_t s);
 int c3d_k_pack(const unsigned int *rgba, const unsigned char bg[3], long long w, long long h, unsigned char *out, cudaStream_t s);

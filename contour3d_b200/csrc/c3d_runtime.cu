@@ -123,7 +123,7 @@ struct c3d_context {
   double *pixel_xy;                                /* pixel-centre tables: width + height doubles */
   size_t table_w, table_h;
   unsigned int *rgba;
-  unsigned int *shade_work, *shade_nwork;          /* pixels won by a contour triangle (compacted), and their number */
+  ShadeScratch shade;                              /* work list, vertex table and normals of the deferred shading */
   unsigned char *ppm_dev, *ppm_host;
   size_t width, height;
   /* active-cube list of the frame (all contour objects, tagged) */
@@ -206,7 +206,7 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   CUDA_OK(cudaMalloc(&ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long)));
   CUDA_OK(cudaMallocHost(&ctx->counts_host, CNT_TOTAL * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->tile_cursor, sizeof(unsigned int)));
-  CUDA_OK(cudaMalloc(&ctx->shade_nwork, sizeof(unsigned int)));
+  CUDA_OK(cudaMalloc(&ctx->shade.counters, 2 * sizeof(unsigned int)));
   CUDA_OK(cudaMalloc(&ctx->bucket_hist, C3D_DEPTH_BUCKETS * sizeof(unsigned int)));
   CUDA_OK(cudaMalloc(&ctx->bucket_cursors, C3D_DEPTH_BUCKETS * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->views_dev, C3D_MAX_OBJECTS * sizeof(FieldView)));
@@ -243,7 +243,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
   cudaFree(ctx->table_mem);
-  cudaFree(ctx->shade_work); cudaFree(ctx->shade_nwork);
+  cudaFree(ctx->shade.work); cudaFree(ctx->shade.counters); cudaFree(ctx->shade.pix); cudaFree(ctx->shade.table); cudaFree(ctx->shade.vlist); cudaFree(ctx->shade.vn);
   cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->hiz); cudaFree(ctx->pixel_xy); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
   if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
   cudaFree(ctx->list); cudaFree(ctx->records); cudaFree(ctx->tile_cursor); cudaFree(ctx->bucket_hist); cudaFree(ctx->bucket_cursors); cudaFree(ctx->counts_dev);
@@ -548,9 +548,10 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
   const size_t npix = w * h;
   if (npix > ctx->npix_cap) {
     cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
-    cudaFree(ctx->shade_work); cudaFree(ctx->hiz);
+    cudaFree(ctx->shade.work); cudaFree(ctx->shade.pix); cudaFree(ctx->shade.table); cudaFree(ctx->shade.vlist); cudaFree(ctx->shade.vn);
+    cudaFree(ctx->hiz);
     ctx->hiz = NULL;
-    ctx->shade_work = NULL;
+    ctx->shade.work = NULL; ctx->shade.pix = NULL; ctx->shade.table = NULL; ctx->shade.vlist = NULL; ctx->shade.vn = NULL;
     if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
     ctx->canvas = NULL; ctx->depth_local = ctx->depth_global = NULL; ctx->rgba = NULL; ctx->ppm_dev = NULL; ctx->ppm_host = NULL;
     ctx->npix_cap = 0;
@@ -562,7 +563,18 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
     CUDA_OK(cudaMalloc(&ctx->rgba, npix * 4));
     /* one word per pixel is an upper bound for any screen shape (a tile row / column may be partial) */
     CUDA_OK(cudaMalloc(&ctx->hiz, (npix / 8 + w + h + 64) * sizeof(unsigned long long)));
-    CUDA_OK(cudaMalloc(&ctx->shade_work, npix * 4));
+    CUDA_OK(cudaMalloc(&ctx->shade.work, npix * 4));
+    CUDA_OK(cudaMalloc(&ctx->shade.pix, npix * C3D_SHADE_PIX_BYTES));
+    {
+      /* about one slot per pixel: ~20 pixels share a vertex at the benchmark's resolution, 3 per pixel is the worst case
+         (then some vertices do not fit and are computed per pixel, see k_shade_blend) */
+      size_t slots = 1u << 16;
+      while (slots < npix && slots < (1ull << 31)) slots <<= 1;
+      CUDA_OK(cudaMalloc(&ctx->shade.table, slots * sizeof(unsigned long long)));
+      CUDA_OK(cudaMalloc(&ctx->shade.vlist, slots * sizeof(unsigned int)));
+      CUDA_OK(cudaMalloc(&ctx->shade.vn, slots * 3 * sizeof(double)));
+      ctx->shade.table_mask = (unsigned int)(slots - 1);
+    }
     CUDA_OK(cudaMalloc(&ctx->ppm_dev, npix * 3));
     CUDA_OK(cudaMallocHost(&ctx->ppm_host, npix * 3));
     ctx->npix_cap = npix;
@@ -847,9 +859,9 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
   /* 5. shade only what survived */
-  LAUNCH_OK(c3d_k_shade(&fp, ctx->lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, ctx->shade_work, ctx->shade_nwork,
+  LAUNCH_OK(c3d_k_shade(&fp, ctx->lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, &ctx->shade,
                         ctx->counts_dev + CNT_SHADE_SPILL, ctx->sm_count, s));
-  launches += 2;
+  launches += 4;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
   /* 6. colours to the writer (the colour half of the reference's reduce) */
   if (ctx->size > 1) {

@@ -3,33 +3,33 @@
  *
  * Replaces contour3d_contour_compute_vertex_normals + average (contour/normal.c:6-165)
  * and the colour half of contour3d_contour_render_triangle (contour/render.c:137-159).
- * The reference smooths EVERY triangle of every slice; here vertex normals are
- * computed only for the three vertices of the one triangle that owns a pixel,
- * by gathering `area * face_normal` over the triangles that touch the same cube
- * edge in the 1, 2 or 4 cubes that share it, in the reference's fixed visiting
- * order (normal.c:78-158) -- so the sums are bit-identical and do not depend
- * on any atomic ordering.
+ * The reference smooths EVERY triangle of every slice; here a vertex normal is
+ * computed only for vertices of triangles that own a pixel, and only ONCE per
+ * vertex: a vertex lives on a cube edge (triangulate.c:15-32), its normal is the
+ * normalised sum of `area * face_normal` over the triangles that touch that edge
+ * in the 1, 2 or 4 cubes sharing it, visited in a fixed global order
+ * (normal.c:78-158) -- a function of the GLOBAL edge alone.  At 1024^3 on a 4K
+ * screen ~20 pixels reference the same vertex, so the pixels first agree on the
+ * set of distinct vertices through a hash table keyed by the global edge.
+ * Sums are evaluated in the reference's order: bit-identical, and independent of
+ * any atomic ordering (the table only decides WHERE a normal is stored).
  *
  *   k_shade_select   one thread per pixel: background, lines and pixels lost to
  *                    another rank are written at once; pixels won by a contour
  *                    triangle are compacted into a work list
- *   k_shade_smooth   cooperative: a block takes 128 listed pixels; every thread
- *                    rebuilds its pixel's triangle (barycentric weights), then in
- *                    sub-batches of 32 pixels the block enumerates the
- *                    (pixel, vertex, neighbour cube) slots, expands them into one
- *                    item per touching triangle, computes the items' face terms
- *                    with ALL threads (the expensive, previously divergent part),
- *                    adds them up per vertex in order, and shades
+ *   k_shade_setup    one thread per listed pixel: rebuilds the winning triangle,
+ *                    the barycentric weights of the pixel centre (render.c:102-110)
+ *                    and enters its three vertices into the table
+ *   k_shade_normals  eight lanes per distinct vertex: the face terms of the
+ *                    touching triangles in parallel, added up in order, normalised
+ *   k_shade_blend    one thread per listed pixel: blend, light, truncate
+ *                    (render.c:137-159)
  *
  * File:line references are to NaokiHori/Contour3D @ c66854e.
  */
 #include <float.h>
 #include "c3d_device.cuh"
 
-#define SH_THREADS 128
-#define SH_BATCH 32                        /* pixels per sub-batch */
-#define SH_SLOTS (SH_BATCH * 12)           /* 3 vertices x up to 4 cubes */
-#define SH_ITEMS 1024                      /* face terms kept in shared memory per sub-batch */
 
 /* ------------------------------------------------------------------ select */
 
@@ -65,21 +65,7 @@ __global__ void __launch_bounds__(256) k_shade_select(const __grid_constant__ Fr
   }
 }
 
-/* ------------------------------------------------------------------ smooth */
-
-struct ShadePixel {
-  double w[3];                 /* barycentric weights of the pixel centre (render.c:102-110) */
-  unsigned int pix;
-  unsigned short i, j, k;      /* cube of the winning triangle */
-  unsigned char obj, edges[3]; /* cube-edge ids of its three vertices */
-  unsigned char valid;
-};
-
-struct ShadeSlot {             /* one neighbour cube of one vertex */
-  unsigned short i, j, k;
-  unsigned short touch;        /* triangles of that cube with a vertex on the shared edge (bit s) */
-  unsigned char obj, code;
-};
+/* ----------------------------------------------------------------- geometry */
 
 /* the c-th cube (reference visiting order) sharing edge e of cube (i, j, k), and the edge's id in that cube;
    the 19-way branch of normal.c:78-158 */
@@ -131,179 +117,230 @@ __device__ __forceinline__ V3 face_term(const FrameParams &p, const unsigned int
   return v_mul(area, fn);
 }
 
-__global__ void __launch_bounds__(SH_THREADS) k_shade_smooth(const __grid_constant__ FrameParams p, const Pixel *__restrict__ canvas,
-                                                             const unsigned int *__restrict__ work, const unsigned int *__restrict__ nwork,
-                                                             unsigned int *__restrict__ rgba, unsigned long long *__restrict__ overflowed) {
-  __shared__ ShadePixel s_pix[SH_THREADS];
-  __shared__ ShadeSlot s_slot[SH_SLOTS];
-  __shared__ unsigned int s_first[SH_SLOTS + 1];          /* first item of each slot */
-  __shared__ unsigned short s_item[SH_ITEMS];             /* slot << 4 | triangle */
-  __shared__ double s_term[SH_ITEMS][3];
-  __shared__ double s_vn[SH_BATCH * 3][3];
-  __shared__ unsigned int s_warp_total[SH_THREADS / 32];
-  const unsigned int tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-  const unsigned int n = *nwork;
-  for (unsigned int base = blockIdx.x * SH_THREADS; base < n; base += gridDim.x * SH_THREADS) {
-    /* ---- S1: every thread rebuilds the winning triangle of its pixel and the weights of the pixel centre ---- */
-    {
-      ShadePixel me;
-      me.valid = 0;
-      me.pix = 0u; me.i = me.j = me.k = 0; me.obj = 0; me.edges[0] = me.edges[1] = me.edges[2] = 0;
-      me.w[0] = me.w[1] = me.w[2] = 0.;
-      if (base + tid < n) {
-        const unsigned int pix = __ldg(work + base + tid);
-        const unsigned long long key = canvas[pix].key;
-        const unsigned int obj = (unsigned int)(key >> C3D_KEY_OBJ_SHIFT) - 1u;
-        const unsigned long long prim = key & C3D_KEY_PRIM_MASK;
-        const unsigned int s = (unsigned int)(prim & 15ull);
-        const long long i = (long long)((prim >> 4) & 65535ull), j = (long long)((prim >> 20) & 65535ull), k = (long long)((prim >> 36) & 65535ull);
-        const FieldView &f = p.view[obj];
-        const unsigned int code = cube_code(f, i, j, k);
-        const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
-        const unsigned int edges = __ldg(p.tab.edges + code * C3D_MAX_TRIS + s);
-        Tri2D t;
-        bool ok = true;
+
+/* ------------------------------------------------------------------- setup */
+
+struct ShadePix {              /* 56 bytes per listed pixel */
+  double w[3];                 /* barycentric weights of the pixel centre (render.c:102-110) */
+  unsigned int vslot[3];       /* table slots of the three vertices; C3D_NO_SLOT: table full, normal computed on the spot */
+  unsigned int pix;
+  unsigned short i, j, k;      /* cube of the winning triangle */
+  unsigned char obj, edges[3]; /* cube-edge ids of its three vertices */
+};
+static_assert(sizeof(ShadePix) == C3D_SHADE_PIX_BYTES, "ShadePix layout");
+
+#define C3D_NO_SLOT 0xffffffffu
+#define SH_PROBES 32
+
+/* the global edge a cube-local edge id names: the cube whose edge 0 / 4 / 8 / 12 / 14 / 16 / 18 it is (the numbering of
+   triangulate.c:15-32: 0-3 x edges at (dj, dk), 4-7 y edges at (di, dk), 8-11 z edges at (di, dj), 12/13 yz-face
+   diagonals at di, 14/15 xz at dj, 16/17 xy at dk, 18 the body diagonal), packed as
+   1:1 | object:4 | type:3 | k:16 | j:16 | i:16 (never 0 = empty slot) */
+__device__ __forceinline__ unsigned long long vertex_key(const unsigned int obj, const unsigned int i, const unsigned int j, const unsigned int k,
+                                                         const unsigned int e) {
+  unsigned int ci = i, cj = j, ck = k, type;
+  if (e < 12u) {
+    const unsigned int axis = e >> 2, a = e & 1u, b = (e >> 1) & 1u;
+    type = axis;
+    if (0u == axis) { cj += a; ck += b; }
+    else if (1u == axis) { ci += a; ck += b; }
+    else { ci += a; cj += b; }
+  } else if (e < 18u) {
+    const unsigned int kind = (e - 12u) >> 1, a = e & 1u;
+    type = 3u + kind;
+    if (0u == kind) ci += a;
+    else if (1u == kind) cj += a;
+    else ck += a;
+  } else {
+    type = 6u;
+  }
+  return (1ull << 63) | ((unsigned long long)obj << 51) | ((unsigned long long)type << 48) | ((unsigned long long)ck << 32)
+       | ((unsigned long long)cj << 16) | (unsigned long long)ci;
+}
+
+__global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ FrameParams p, const Pixel *__restrict__ canvas,
+                                                     const unsigned int *__restrict__ work, unsigned int *__restrict__ counters,
+                                                     ShadePix *__restrict__ out, unsigned long long *__restrict__ table, const unsigned int mask,
+                                                     unsigned int *__restrict__ vlist, unsigned long long *__restrict__ overflowed) {
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int n = counters[0];
+  /* whole warps iterate together (ballots inside) */
+  for (unsigned int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+    const unsigned int idx = base + lane;
+    const bool valid = idx < n;
+    ShadePix me;
+    me.w[0] = me.w[1] = me.w[2] = 0.;
+    me.vslot[0] = me.vslot[1] = me.vslot[2] = C3D_NO_SLOT;
+    me.pix = 0u; me.i = me.j = me.k = 0; me.obj = 0; me.edges[0] = me.edges[1] = me.edges[2] = 0;
+    unsigned long long vkey[3] = {0ull, 0ull, 0ull};
+    if (valid) {
+      const unsigned int pix = __ldg(work + idx);
+      const unsigned long long key = canvas[pix].key;
+      const unsigned int obj = (unsigned int)(key >> C3D_KEY_OBJ_SHIFT) - 1u;
+      const unsigned long long prim = key & C3D_KEY_PRIM_MASK;
+      const unsigned int s = (unsigned int)(prim & 15ull);
+      const long long i = (long long)((prim >> 4) & 65535ull), j = (long long)((prim >> 20) & 65535ull), k = (long long)((prim >> 36) & 65535ull);
+      const FieldView &f = p.view[obj];
+      const unsigned int code = cube_code(f, i, j, k);
+      const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
+      const unsigned int edges = __ldg(p.tab.edges + code * C3D_MAX_TRIS + s);
+      Tri2D t;
+      bool ok = true;
 #pragma unroll
-        for (int m = 0; m < 3; m++) {
-          const ProjectedVertex v = exact_vertex(p, obj, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
-          ok = ok && (0. != v.w);
-          t.q[m] = V3{v.x, v.y, v.z};
-        }
-        if (ok) {
-          setup_projected(p.cam, t);
-          pixel_weights(t, __ldg(p.px + (pix % (unsigned int)p.cam.w)), __ldg(p.py + (pix / (unsigned int)p.cam.w)), me.w);
-        }
-        me.valid = 1;
-        me.pix = pix;
-        me.i = (unsigned short)i; me.j = (unsigned short)j; me.k = (unsigned short)k;
-        me.obj = (unsigned char)obj;
-        for (int m = 0; m < 3; m++) me.edges[m] = (unsigned char)((edges >> (5 * m)) & 31u);
+      for (int m = 0; m < 3; m++) {
+        const ProjectedVertex v = exact_vertex(p, obj, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+        ok = ok && (0. != v.w);
+        t.q[m] = V3{v.x, v.y, v.z};
       }
-      s_pix[tid] = me;
+      if (ok) {
+        setup_projected(p.cam, t);
+        pixel_weights(t, __ldg(p.px + (pix % (unsigned int)p.cam.w)), __ldg(p.py + (pix / (unsigned int)p.cam.w)), me.w);
+      }
+      me.pix = pix;
+      me.i = (unsigned short)i; me.j = (unsigned short)j; me.k = (unsigned short)k;
+      me.obj = (unsigned char)obj;
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        me.edges[m] = (unsigned char)((edges >> (5 * m)) & 31u);
+        vkey[m] = vertex_key(obj, (unsigned int)i, (unsigned int)j, (unsigned int)k, me.edges[m]);
+      }
     }
-    __syncthreads();
-    for (unsigned int sub = 0; sub < SH_THREADS / SH_BATCH; sub++) {
-      if (base + sub * SH_BATCH >= n) break;                       /* uniform */
-      const ShadePixel *batch = s_pix + sub * SH_BATCH;
-      /* ---- S2: slots = (pixel, vertex, neighbour cube); count the triangles touching the shared edge ---- */
-      unsigned int mycount[SH_SLOTS / SH_THREADS];
 #pragma unroll
-      for (unsigned int r = 0; r < SH_SLOTS / SH_THREADS; r++) {
-        const unsigned int q = r * SH_THREADS + tid;
-        const unsigned int px = q / 12u, m = (q % 12u) >> 2, c = q & 3u;
-        const ShadePixel &sp = batch[px];
-        ShadeSlot slot;
-        slot.i = slot.j = slot.k = 0; slot.touch = 0; slot.obj = sp.obj; slot.code = 0;
-        int di, dj, dk;
-        unsigned int local;
-        if (sp.valid && edge_neighbour(sp.edges[m], c, di, dj, dk, local)) {
-          const long long ii = (long long)sp.i + di, jj = (long long)sp.j + dj, kk = (long long)sp.k + dk;
-          const unsigned int code = cube_code(p.view[sp.obj], ii, jj, kk);
-          slot.i = (unsigned short)ii; slot.j = (unsigned short)jj; slot.k = (unsigned short)kk;
-          slot.code = (unsigned char)code;
-          slot.touch = __ldg(p.tab.touch + code * 19u + local);
+    for (int m = 0; m < 3; m++) {
+      unsigned int slot = C3D_NO_SLOT;
+      bool inserted = false;
+      if (valid) {
+        unsigned int h = (unsigned int)((vkey[m] * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+        for (int probe = 0; probe < SH_PROBES; probe++) {
+          const unsigned long long old = atomicCAS(table + h, 0ull, vkey[m]);
+          if (0ull == old) { inserted = true; slot = h; break; }
+          if (old == vkey[m]) { slot = h; break; }
+          h = (h + 1u) & mask;
         }
-        s_slot[q] = slot;
-        mycount[r] = __popc((unsigned int)slot.touch);
+        if (C3D_NO_SLOT == slot) atomicAdd(overflowed, 1ull);
       }
-      /* ---- S3: exclusive scan of the slot counts in slot order (q = r * 128 + tid) ---- */
-      unsigned int total_items = 0u;
+      /* the first pixel to name a vertex lists it for k_shade_normals */
+      const unsigned int who = __ballot_sync(C3D_FULL_MASK, inserted);
+      if (0u != who) {
+        unsigned int at = 0u;
+        if (0u == lane) at = atomicAdd(counters + 1, (unsigned int)__popc(who));
+        at = __shfl_sync(C3D_FULL_MASK, at, 0);
+        if (inserted) vlist[at + __popc(who & ((1u << lane) - 1u))] = slot;
+      }
+      me.vslot[m] = slot;
+    }
+    if (valid) out[idx] = me;
+  }
+}
+
+/* ----------------------------------------------------------------- normals */
+
+/* the n-th (0-based) set bit of x */
+__device__ __forceinline__ unsigned int nth_set_bit(unsigned int x, unsigned int n) {
+  for (; n > 0u; n--) x &= x - 1u;
+  return (unsigned int)__ffs((int)x) - 1u;
+}
+
+__global__ void __launch_bounds__(128) k_shade_normals(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ table,
+                                                       const unsigned int *__restrict__ vlist, const unsigned int *__restrict__ counters,
+                                                       double *__restrict__ vn) {
+  const unsigned int lane = threadIdx.x & 31u, group = lane >> 3, sub = lane & 7u, lead = group << 3;
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned int nv = counters[1];
+  for (unsigned int base = warp * 4u; base < nv; base += nwarps * 4u) {      /* warp-uniform */
+    const unsigned int v = base + group;
+    const bool valid = v < nv;
+    unsigned int slot = 0u, obj = 0u, e = 18u;
+    long long ci = 0, cj = 0, ck = 0;
+    if (valid) {
+      slot = __ldg(vlist + v);
+      const unsigned long long key = table[slot];
+      const unsigned int type = (unsigned int)(key >> 48) & 7u;
+      obj = (unsigned int)(key >> 51) & 15u;
+      e = type < 3u ? 4u * type : (type < 6u ? 6u + 2u * type : 18u);      /* edge 0 / 4 / 8 / 12 / 14 / 16 / 18 of cube (ci, cj, ck) */
+      ck = (long long)((key >> 32) & 65535ull); cj = (long long)((key >> 16) & 65535ull); ci = (long long)(key & 65535ull);
+    }
+    /* lanes 0..3 of the group: the cubes sharing the edge, in the reference's visiting order */
+    long long ii = 0, jj = 0, kk = 0;
+    unsigned int code = 0u, touch = 0u;
+    {
+      int di, dj, dk;
+      unsigned int local;
+      if (valid && sub < 4u && edge_neighbour(e, sub, di, dj, dk, local)) {
+        ii = ci + di; jj = cj + dj; kk = ck + dk;
+        code = cube_code(p.view[obj], ii, jj, kk);
+        touch = __ldg(p.tab.touch + code * 19u + local);
+      }
+    }
+    const unsigned int cnt = __popc(touch);
+    const unsigned int c0 = __shfl_sync(C3D_FULL_MASK, cnt, lead), c1 = __shfl_sync(C3D_FULL_MASK, cnt, lead + 1u);
+    const unsigned int c2 = __shfl_sync(C3D_FULL_MASK, cnt, lead + 2u), c3 = __shfl_sync(C3D_FULL_MASK, cnt, lead + 3u);
+    const unsigned int total = c0 + c1 + c2 + c3;
+    const unsigned int most = __reduce_max_sync(C3D_FULL_MASK, total);
+    V3 sum = V3{0., 0., 0.};
+    for (unsigned int it0 = 0u; it0 < most; it0 += 8u) {
+      /* item it0 + sub = the within-th touching triangle of sharing cube c */
+      const unsigned int item = it0 + sub;
+      const bool have = valid && item < total;
+      const unsigned int c = item < c0 ? 0u : (item < c0 + c1 ? 1u : (item < c0 + c1 + c2 ? 2u : 3u));
+      const unsigned int within = item - (0u == c ? 0u : (1u == c ? c0 : (2u == c ? c0 + c1 : c0 + c1 + c2)));
+      const long long sii = __shfl_sync(C3D_FULL_MASK, ii, lead + c), sjj = __shfl_sync(C3D_FULL_MASK, jj, lead + c);
+      const long long skk = __shfl_sync(C3D_FULL_MASK, kk, lead + c);
+      const unsigned int scode = __shfl_sync(C3D_FULL_MASK, code, lead + c), stouch = __shfl_sync(C3D_FULL_MASK, touch, lead + c);
+      V3 term = V3{0., 0., 0.};
+      if (have) term = face_term(p, obj, sii, sjj, skk, scode, nth_set_bit(stouch, within));
+      /* add in (cube, triangle) order, average() of normal.c:6-43 */
 #pragma unroll
-      for (unsigned int r = 0; r < SH_SLOTS / SH_THREADS; r++) {
-        unsigned int incl = mycount[r];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const unsigned int up = __shfl_up_sync(C3D_FULL_MASK, incl, d);
-          if (lane >= (unsigned int)d) incl += up;
-        }
-        if (31u == lane) s_warp_total[wid] = incl;
-        __syncthreads();
-        unsigned int before = total_items;
-        for (unsigned int w = 0; w < wid; w++) before += s_warp_total[w];
-        unsigned int round_total = 0u;
-        for (unsigned int w = 0; w < SH_THREADS / 32; w++) round_total += s_warp_total[w];
-        s_first[r * SH_THREADS + tid] = before + incl - mycount[r];
-        total_items += round_total;
-        __syncthreads();
+      for (unsigned int t = 0u; t < 8u; t++) {
+        const V3 other = V3{__shfl_sync(C3D_FULL_MASK, term.x, lead + t), __shfl_sync(C3D_FULL_MASK, term.y, lead + t),
+                            __shfl_sync(C3D_FULL_MASK, term.z, lead + t)};
+        if (it0 + t < total) sum = v_add(sum, other);
       }
-      if (0u == tid) s_first[SH_SLOTS] = total_items;
-      const bool fits = total_items <= SH_ITEMS;                   /* uniform */
-      if (fits) {
-        /* ---- S3b: one item per touching triangle, in (slot, triangle) order ---- */
-#pragma unroll
-        for (unsigned int r = 0; r < SH_SLOTS / SH_THREADS; r++) {
-          const unsigned int q = r * SH_THREADS + tid;
-          unsigned int touch = s_slot[q].touch, at = s_first[q];
-          while (touch) {
-            const unsigned int s = (unsigned int)__ffs((int)touch) - 1u;
-            touch &= touch - 1u;
-            s_item[at++] = (unsigned short)((q << 4) | s);
-          }
-        }
-        __syncthreads();
-        /* ---- S4: the face terms, all threads ---- */
-        for (unsigned int it = tid; it < total_items; it += SH_THREADS) {
-          const unsigned int q = s_item[it] >> 4, s = s_item[it] & 15u;
-          const ShadeSlot slot = s_slot[q];
-          const V3 term = face_term(p, slot.obj, slot.i, slot.j, slot.k, slot.code, s);
-          s_term[it][0] = term.x; s_term[it][1] = term.y; s_term[it][2] = term.z;
-        }
-        __syncthreads();
-        /* ---- S5: per vertex, add the terms in order and normalise (normal.c:159) ---- */
-        if (tid < SH_BATCH * 3) {
-          const unsigned int q0 = tid * 4u;
-          V3 sum = V3{0., 0., 0.};
-          for (unsigned int it = s_first[q0]; it < s_first[q0 + 4u]; it++) {
-            sum = v_add(sum, V3{s_term[it][0], s_term[it][1], s_term[it][2]});
-          }
-          const V3 vn = v_unit(sum);
-          s_vn[tid][0] = vn.x; s_vn[tid][1] = vn.y; s_vn[tid][2] = vn.z;
-        }
-      } else {
-        /* more touching triangles than the shared buffer holds: the same sums, one thread per vertex */
-        if (0u == tid) atomicAdd(overflowed, 1ull);
-        if (tid < SH_BATCH * 3) {
-          V3 sum = V3{0., 0., 0.};
-          for (unsigned int q = tid * 4u; q < tid * 4u + 4u; q++) {
-            const ShadeSlot slot = s_slot[q];
-            unsigned int touch = slot.touch;
-            while (touch) {
-              const unsigned int s = (unsigned int)__ffs((int)touch) - 1u;
-              touch &= touch - 1u;
-              sum = v_add(sum, face_term(p, slot.obj, slot.i, slot.j, slot.k, slot.code, s));
-            }
-          }
-          const V3 vn = v_unit(sum);
-          s_vn[tid][0] = vn.x; s_vn[tid][1] = vn.y; s_vn[tid][2] = vn.z;
-        }
-      }
-      __syncthreads();
-      /* ---- S6: blend, light, truncate (render.c:137-159) ---- */
-      if (tid < SH_BATCH && batch[tid].valid) {
-        const ShadePixel &sp = batch[tid];
-        const V3 n0 = V3{s_vn[3 * tid][0], s_vn[3 * tid][1], s_vn[3 * tid][2]};
-        const V3 n1 = V3{s_vn[3 * tid + 1][0], s_vn[3 * tid + 1][1], s_vn[3 * tid + 1][2]};
-        const V3 n2 = V3{s_vn[3 * tid + 2][0], s_vn[3 * tid + 2][1], s_vn[3 * tid + 2][2]};
-        /* w0*n0 + (w1*n1 + w2*n2), render.c:137-146 */
-        const V3 nrm = v_unit(v_add(v_mul(sp.w[0], n0), v_add(v_mul(sp.w[1], n1), v_mul(sp.w[2], n2))));
-        const double factor = fmax(0.15, fabs(v_dot(nrm, v_of(p.cam.light))));
-        const FieldView &f = p.view[sp.obj];
-        const unsigned int r = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[0])) & 255u;
-        const unsigned int g = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[1])) & 255u;
-        const unsigned int b = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[2])) & 255u;
-        rgba[sp.pix] = 0xFF000000u | (b << 16) | (g << 8) | r;
-      }
-      __syncthreads();
+    }
+    if (valid && 0u == sub) {
+      const V3 unit = v_unit(sum);                                  /* normal.c:159 */
+      vn[3ull * slot + 0ull] = unit.x; vn[3ull * slot + 1ull] = unit.y; vn[3ull * slot + 2ull] = unit.z;
     }
   }
 }
 
+/* ------------------------------------------------------------------- blend */
+
+__global__ void __launch_bounds__(128) k_shade_blend(const __grid_constant__ FrameParams p, const ShadePix *__restrict__ in,
+                                                     const unsigned int *__restrict__ counters, const double *__restrict__ vn,
+                                                     unsigned int *__restrict__ rgba) {
+  const unsigned int n = counters[0];
+  for (unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const ShadePix sp = in[idx];
+    const FieldView &f = p.view[sp.obj];
+    V3 nv[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const unsigned int slot = sp.vslot[m];
+      if (C3D_NO_SLOT != slot) nv[m] = V3{vn[3ull * slot + 0ull], vn[3ull * slot + 1ull], vn[3ull * slot + 2ull]};
+      else nv[m] = vertex_normal(f, p.tab, (long long)sp.i, (long long)sp.j, (long long)sp.k, (unsigned int)sp.edges[m]);
+    }
+    /* w0*n0 + (w1*n1 + w2*n2), render.c:137-146 */
+    const V3 nrm = v_unit(v_add(v_mul(sp.w[0], nv[0]), v_add(v_mul(sp.w[1], nv[1]), v_mul(sp.w[2], nv[2]))));
+    const double factor = fmax(0.15, fabs(v_dot(nrm, v_of(p.cam.light))));
+    const unsigned int r = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[0])) & 255u;
+    const unsigned int g = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[1])) & 255u;
+    const unsigned int b = (unsigned int)__double2int_rz(r_mul(factor, (double)f.color[2])) & 255u;
+    rgba[sp.pix] = 0xFF000000u | (b << 16) | (g << 8) | r;
+  }
+}
+
 extern "C" int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
-                           unsigned int *rgba, size_t npix, unsigned int *work, unsigned int *nwork, unsigned long long *overflowed,
+                           unsigned int *rgba, size_t npix, const ShadeScratch *sc, unsigned long long *overflowed,
                            int sm_count, cudaStream_t s) {
-  const cudaError_t err = cudaMemsetAsync(nwork, 0, sizeof(unsigned int), s);
+  cudaError_t err = cudaMemsetAsync(sc->counters, 0, 2 * sizeof(unsigned int), s);
   if (cudaSuccess != err) return (int)err;
-  k_shade_select<<<sm_count * 8, 256, 0, s>>>(*p, lines_dev, canvas, depth_global, rgba, npix, work, nwork);
-  k_shade_smooth<<<sm_count * 6, SH_THREADS, 0, s>>>(*p, canvas, work, nwork, rgba, overflowed);
+  err = cudaMemsetAsync(sc->table, 0, ((size_t)sc->table_mask + 1u) * sizeof(unsigned long long), s);
+  if (cudaSuccess != err) return (int)err;
+  k_shade_select<<<sm_count * 8, 256, 0, s>>>(*p, lines_dev, canvas, depth_global, rgba, npix, sc->work, sc->counters);
+  k_shade_setup<<<sm_count * 12, 128, 0, s>>>(*p, canvas, sc->work, sc->counters, static_cast<ShadePix *>(sc->pix), sc->table, sc->table_mask,
+                                              sc->vlist, overflowed);
+  k_shade_normals<<<sm_count * 12, 128, 0, s>>>(*p, sc->table, sc->vlist, sc->counters, sc->vn);
+  k_shade_blend<<<sm_count * 12, 128, 0, s>>>(*p, static_cast<const ShadePix *>(sc->pix), sc->counters, sc->vn, rgba);
   return (int)cudaGetLastError();
 }
