@@ -113,8 +113,9 @@ struct ShadeScratch {
   void *pix;                     /* per listed pixel: weights, cube, vertex slots: npix x C3D_SHADE_PIX_BYTES */
   unsigned long long *table;     /* open-addressing set of the vertices (global cube edges) the listed pixels reference */
   unsigned int table_mask;       /* slots - 1 (a power of two) */
-  unsigned int *vlist;           /* occupied slots in order of first insertion: one word per slot */
-  double *vn;                    /* unit vertex normal of each slot: 3 doubles */
+  unsigned int *vlist;           /* occupied slots in order of first insertion: min(slots, 3 npix) words */
+  double *vn;                    /* unit normal of listed vertex v: 3 doubles each, vn_cap vertices */
+  unsigned int vn_cap;
 };
 
 #if defined(__cplusplus)

@@ -566,13 +566,19 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
     CUDA_OK(cudaMalloc(&ctx->shade.work, npix * 4));
     CUDA_OK(cudaMalloc(&ctx->shade.pix, npix * C3D_SHADE_PIX_BYTES));
     {
-      /* about one slot per pixel: ~20 pixels share a vertex at the benchmark's resolution, 3 per pixel is the worst case
-         (then some vertices do not fit and are computed per pixel, see k_shade_blend) */
+      /* four to eight slots per pixel: at the benchmark's resolution triangles are smaller than a pixel and 3.7 M winning
+         pixels name 6 M distinct vertices (load 0.18: probe sequences stay short, each probe is an atomic round trip);
+         3 per pixel is the worst case.  A vertex that finds no slot within SH_PROBES, or no room in the normal array
+         (1.5 per pixel), is computed per pixel instead (k_shade_blend) */
       size_t slots = 1u << 16;
-      while (slots < npix && slots < (1ull << 31)) slots <<= 1;
+      while (slots < 4 * npix && slots < (1ull << 28)) slots <<= 1;
+      /* the list is handed out in 256-entry chunks per warp (k_shade_setup): room for every resident warp's unused tail */
+      const size_t listed = std::min<size_t>(slots, 3 * npix + 32) + (size_t)ctx->sm_count * 64 * 256;
+      const size_t normals = std::min<size_t>(listed, npix + npix / 2 + (size_t)ctx->sm_count * 64 * 256);
       CUDA_OK(cudaMalloc(&ctx->shade.table, slots * sizeof(unsigned long long)));
-      CUDA_OK(cudaMalloc(&ctx->shade.vlist, slots * sizeof(unsigned int)));
-      CUDA_OK(cudaMalloc(&ctx->shade.vn, slots * 3 * sizeof(double)));
+      CUDA_OK(cudaMalloc(&ctx->shade.vlist, listed * sizeof(unsigned int)));
+      CUDA_OK(cudaMalloc(&ctx->shade.vn, normals * 3 * sizeof(double)));
+      ctx->shade.vn_cap = (unsigned int)normals;
       ctx->shade.table_mask = (unsigned int)(slots - 1);
     }
     CUDA_OK(cudaMalloc(&ctx->ppm_dev, npix * 3));

@@ -131,6 +131,7 @@ static_assert(sizeof(ShadePix) == C3D_SHADE_PIX_BYTES, "ShadePix layout");
 
 #define C3D_NO_SLOT 0xffffffffu
 #define SH_PROBES 32
+#define SH_CHUNK 256u                     /* vertex-list entries a warp reserves at a time (a multiple of 32, >= 64) */
 
 /* the global edge a cube-local edge id names: the cube whose edge 0 / 4 / 8 / 12 / 14 / 16 / 18 it is (the numbering of
    triangulate.c:15-32: 0-3 x edges at (dj, dk), 4-7 y edges at (di, dk), 8-11 z edges at (di, dj), 12/13 yz-face
@@ -164,6 +165,9 @@ __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ Fra
                                                      unsigned int *__restrict__ vlist, unsigned long long *__restrict__ overflowed) {
   const unsigned int lane = threadIdx.x & 31u;
   const unsigned int n = counters[0];
+  /* The vertex list is handed out in chunks of SH_CHUNK entries per warp: one counter for everybody costs a serialised
+     round trip per append (measured: 58 % of this kernel's stall samples).  Unused entries of a chunk hold C3D_NO_SLOT. */
+  unsigned int chunk_next = 0u, chunk_end = 0u;
   /* whole warps iterate together (ballots inside) */
   for (unsigned int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
     const unsigned int idx = base + lane;
@@ -205,110 +209,202 @@ __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ Fra
         vkey[m] = vertex_key(obj, (unsigned int)i, (unsigned int)j, (unsigned int)k, me.edges[m]);
       }
     }
+    /* the three vertices probe the table side by side: an atomic round trip costs about a microsecond, and a warp waits
+       for its slowest lane, so the probe sequences must overlap rather than add up */
+    unsigned int h[3];
+    bool done[3], inserted[3];
 #pragma unroll
     for (int m = 0; m < 3; m++) {
-      unsigned int slot = C3D_NO_SLOT;
-      bool inserted = false;
-      if (valid) {
-        unsigned int h = (unsigned int)((vkey[m] * 0x9E3779B97F4A7C15ull) >> 32) & mask;
-        for (int probe = 0; probe < SH_PROBES; probe++) {
-          const unsigned long long old = atomicCAS(table + h, 0ull, vkey[m]);
-          if (0ull == old) { inserted = true; slot = h; break; }
-          if (old == vkey[m]) { slot = h; break; }
-          h = (h + 1u) & mask;
+      h[m] = (unsigned int)((vkey[m] * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+      done[m] = !valid;
+      inserted[m] = false;
+    }
+    for (int probe = 0; probe < SH_PROBES; probe++) {
+      unsigned long long old[3] = {0ull, 0ull, 0ull};
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        if (!done[m]) old[m] = atomicCAS(table + h[m], 0ull, vkey[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        if (!done[m]) {
+          if (0ull == old[m]) { inserted[m] = true; me.vslot[m] = h[m]; done[m] = true; }
+          else if (old[m] == vkey[m]) { me.vslot[m] = h[m]; done[m] = true; }
+          else h[m] = (h[m] + 1u) & mask;
         }
-        if (C3D_NO_SLOT == slot) atomicAdd(overflowed, 1ull);
       }
+      if (done[0] && done[1] && done[2]) break;
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      if (valid && C3D_NO_SLOT == me.vslot[m]) atomicAdd(overflowed, 1ull);
       /* the first pixel to name a vertex lists it for k_shade_normals */
-      const unsigned int who = __ballot_sync(C3D_FULL_MASK, inserted);
+      const unsigned int who = __ballot_sync(C3D_FULL_MASK, inserted[m]);
       if (0u != who) {
-        unsigned int at = 0u;
-        if (0u == lane) at = atomicAdd(counters + 1, (unsigned int)__popc(who));
-        at = __shfl_sync(C3D_FULL_MASK, at, 0);
-        if (inserted) vlist[at + __popc(who & ((1u << lane) - 1u))] = slot;
+        const unsigned int cnt = (unsigned int)__popc(who);
+        if (chunk_next + cnt > chunk_end) {                     /* warp-uniform */
+          if (chunk_next + lane < chunk_end) vlist[chunk_next + lane] = C3D_NO_SLOT;      /* at most 31 entries are left */
+          unsigned int at = 0u;
+          if (0u == lane) at = atomicAdd(counters + 1, (unsigned int)SH_CHUNK);
+          chunk_next = __shfl_sync(C3D_FULL_MASK, at, 0);
+          chunk_end = chunk_next + SH_CHUNK;
+        }
+        if (inserted[m]) vlist[chunk_next + __popc(who & ((1u << lane) - 1u))] = me.vslot[m];
+        chunk_next += cnt;
       }
-      me.vslot[m] = slot;
     }
     if (valid) out[idx] = me;
   }
+  for (unsigned int at = chunk_next + lane; at < chunk_end; at += 32u) vlist[at] = C3D_NO_SLOT;
 }
 
 /* ----------------------------------------------------------------- normals */
 
-/* the n-th (0-based) set bit of x */
-__device__ __forceinline__ unsigned int nth_set_bit(unsigned int x, unsigned int n) {
-  for (; n > 0u; n--) x &= x - 1u;
-  return (unsigned int)__ffs((int)x) - 1u;
+#define SH_THREADS 128
+#define SH_VERTS 96                        /* vertices per batch */
+#define SH_SLOTS (SH_VERTS * 4)            /* up to 4 cubes share an edge */
+#define SH_ITEMS 1024                      /* face terms kept in shared memory per batch */
+
+struct ShadeSlot {             /* one cube sharing the edge of one vertex */
+  unsigned short i, j, k;
+  unsigned short touch;        /* triangles of that cube with a vertex on the shared edge (bit s) */
+  unsigned char obj, code;
+};
+
+/*
+ * Cooperative: a block takes SH_VERTS listed vertices; it enumerates the (vertex, sharing cube) slots, expands them into
+ * one item per touching triangle, computes the items' face terms with ALL threads (the expensive part: three edge cuts,
+ * a cross product, a square root and four divisions in fp64 each), and adds them up per vertex in the reference's order.
+ */
+/* the normal of listed vertex v goes to vn[v]; its table slot, whose key nobody needs any more, is overwritten with v so
+   that the pixels (which hold slots) find it.  Vertices beyond the array (v >= vn_cap) are marked C3D_NO_SLOT and
+   computed per pixel. */
+__device__ __forceinline__ void store_normal(const V3 unit, const unsigned int v, const unsigned int slot, double *__restrict__ vn,
+                                             const unsigned int vn_cap, unsigned long long *__restrict__ table) {
+  if (v < vn_cap) {
+    vn[3ull * v + 0ull] = unit.x; vn[3ull * v + 1ull] = unit.y; vn[3ull * v + 2ull] = unit.z;
+    table[slot] = (unsigned long long)v;
+  } else {
+    table[slot] = (unsigned long long)C3D_NO_SLOT;
+  }
 }
 
-__global__ void __launch_bounds__(128) k_shade_normals(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ table,
-                                                       const unsigned int *__restrict__ vlist, const unsigned int *__restrict__ counters,
-                                                       double *__restrict__ vn) {
-  const unsigned int lane = threadIdx.x & 31u, group = lane >> 3, sub = lane & 7u, lead = group << 3;
-  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+__global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_constant__ FrameParams p, unsigned long long *__restrict__ table,
+                                                              const unsigned int *__restrict__ vlist, const unsigned int *__restrict__ counters,
+                                                              double *__restrict__ vn, const unsigned int vn_cap, unsigned long long *__restrict__ overflowed) {
+  __shared__ ShadeSlot s_slot[SH_SLOTS];
+  __shared__ unsigned int s_first[SH_SLOTS + 1];          /* first item of each slot */
+  __shared__ unsigned short s_item[SH_ITEMS];             /* slot << 4 | triangle */
+  __shared__ double s_term[SH_ITEMS][3];
+  __shared__ unsigned int s_warp_total[SH_THREADS / 32];
+  const unsigned int tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const unsigned int nv = counters[1];
-  for (unsigned int base = warp * 4u; base < nv; base += nwarps * 4u) {      /* warp-uniform */
-    const unsigned int v = base + group;
-    const bool valid = v < nv;
-    unsigned int slot = 0u, obj = 0u, e = 18u;
-    long long ci = 0, cj = 0, ck = 0;
-    if (valid) {
-      slot = __ldg(vlist + v);
-      const unsigned long long key = table[slot];
-      const unsigned int type = (unsigned int)(key >> 48) & 7u;
-      obj = (unsigned int)(key >> 51) & 15u;
-      e = type < 3u ? 4u * type : (type < 6u ? 6u + 2u * type : 18u);      /* edge 0 / 4 / 8 / 12 / 14 / 16 / 18 of cube (ci, cj, ck) */
-      ck = (long long)((key >> 32) & 65535ull); cj = (long long)((key >> 16) & 65535ull); ci = (long long)(key & 65535ull);
-    }
-    /* lanes 0..3 of the group: the cubes sharing the edge, in the reference's visiting order */
-    long long ii = 0, jj = 0, kk = 0;
-    unsigned int code = 0u, touch = 0u;
-    {
-      int di, dj, dk;
-      unsigned int local;
-      if (valid && sub < 4u && edge_neighbour(e, sub, di, dj, dk, local)) {
-        ii = ci + di; jj = cj + dj; kk = ck + dk;
-        code = cube_code(p.view[obj], ii, jj, kk);
-        touch = __ldg(p.tab.touch + code * 19u + local);
-      }
-    }
-    const unsigned int cnt = __popc(touch);
-    const unsigned int c0 = __shfl_sync(C3D_FULL_MASK, cnt, lead), c1 = __shfl_sync(C3D_FULL_MASK, cnt, lead + 1u);
-    const unsigned int c2 = __shfl_sync(C3D_FULL_MASK, cnt, lead + 2u), c3 = __shfl_sync(C3D_FULL_MASK, cnt, lead + 3u);
-    const unsigned int total = c0 + c1 + c2 + c3;
-    const unsigned int most = __reduce_max_sync(C3D_FULL_MASK, total);
-    V3 sum = V3{0., 0., 0.};
-    for (unsigned int it0 = 0u; it0 < most; it0 += 8u) {
-      /* item it0 + sub = the within-th touching triangle of sharing cube c */
-      const unsigned int item = it0 + sub;
-      const bool have = valid && item < total;
-      const unsigned int c = item < c0 ? 0u : (item < c0 + c1 ? 1u : (item < c0 + c1 + c2 ? 2u : 3u));
-      const unsigned int within = item - (0u == c ? 0u : (1u == c ? c0 : (2u == c ? c0 + c1 : c0 + c1 + c2)));
-      const long long sii = __shfl_sync(C3D_FULL_MASK, ii, lead + c), sjj = __shfl_sync(C3D_FULL_MASK, jj, lead + c);
-      const long long skk = __shfl_sync(C3D_FULL_MASK, kk, lead + c);
-      const unsigned int scode = __shfl_sync(C3D_FULL_MASK, code, lead + c), stouch = __shfl_sync(C3D_FULL_MASK, touch, lead + c);
-      V3 term = V3{0., 0., 0.};
-      if (have) term = face_term(p, obj, sii, sjj, skk, scode, nth_set_bit(stouch, within));
-      /* add in (cube, triangle) order, average() of normal.c:6-43 */
+  for (unsigned int base = blockIdx.x * SH_VERTS; base < nv; base += gridDim.x * SH_VERTS) {
+    /* ---- slots = (vertex, sharing cube) in the reference's visiting order; count the triangles touching the edge ---- */
+    unsigned int mycount[SH_SLOTS / SH_THREADS];
 #pragma unroll
-      for (unsigned int t = 0u; t < 8u; t++) {
-        const V3 other = V3{__shfl_sync(C3D_FULL_MASK, term.x, lead + t), __shfl_sync(C3D_FULL_MASK, term.y, lead + t),
-                            __shfl_sync(C3D_FULL_MASK, term.z, lead + t)};
-        if (it0 + t < total) sum = v_add(sum, other);
+    for (unsigned int r = 0; r < SH_SLOTS / SH_THREADS; r++) {
+      const unsigned int q = r * SH_THREADS + tid;
+      const unsigned int v = base + (q >> 2), c = q & 3u;
+      ShadeSlot slot;
+      slot.i = slot.j = slot.k = 0; slot.touch = 0; slot.obj = 0; slot.code = 0;
+      const unsigned int at = v < nv ? __ldg(vlist + v) : C3D_NO_SLOT;
+      if (C3D_NO_SLOT != at) {
+        const unsigned long long key = table[at];
+        const unsigned int type = (unsigned int)(key >> 48) & 7u, obj = (unsigned int)(key >> 51) & 15u;
+        const unsigned int e = type < 3u ? 4u * type : (type < 6u ? 6u + 2u * type : 18u);   /* edge 0 / 4 / 8 / 12 / 14 / 16 / 18 of that cube */
+        int di, dj, dk;
+        unsigned int local;
+        slot.obj = (unsigned char)obj;
+        if (edge_neighbour(e, c, di, dj, dk, local)) {
+          const long long ii = (long long)(key & 65535ull) + di, jj = (long long)((key >> 16) & 65535ull) + dj, kk = (long long)((key >> 32) & 65535ull) + dk;
+          const unsigned int code = cube_code(p.view[obj], ii, jj, kk);
+          slot.i = (unsigned short)ii; slot.j = (unsigned short)jj; slot.k = (unsigned short)kk;
+          slot.code = (unsigned char)code;
+          slot.touch = __ldg(p.tab.touch + code * 19u + local);
+        }
+      }
+      s_slot[q] = slot;
+      mycount[r] = __popc((unsigned int)slot.touch);
+    }
+    /* ---- exclusive scan of the slot counts in slot order (q = r * 128 + tid) ---- */
+    unsigned int total_items = 0u;
+#pragma unroll
+    for (unsigned int r = 0; r < SH_SLOTS / SH_THREADS; r++) {
+      unsigned int incl = mycount[r];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int up = __shfl_up_sync(C3D_FULL_MASK, incl, d);
+        if (lane >= (unsigned int)d) incl += up;
+      }
+      if (31u == lane) s_warp_total[wid] = incl;
+      __syncthreads();
+      unsigned int before = total_items;
+      for (unsigned int w = 0; w < wid; w++) before += s_warp_total[w];
+      unsigned int round_total = 0u;
+      for (unsigned int w = 0; w < SH_THREADS / 32; w++) round_total += s_warp_total[w];
+      s_first[r * SH_THREADS + tid] = before + incl - mycount[r];
+      total_items += round_total;
+      __syncthreads();
+    }
+    if (0u == tid) s_first[SH_SLOTS] = total_items;
+    const bool fits = total_items <= SH_ITEMS;                   /* uniform */
+    if (fits) {
+      /* ---- one item per touching triangle, in (slot, triangle) order ---- */
+#pragma unroll
+      for (unsigned int r = 0; r < SH_SLOTS / SH_THREADS; r++) {
+        const unsigned int q = r * SH_THREADS + tid;
+        unsigned int touch = s_slot[q].touch, at = s_first[q];
+        while (touch) {
+          const unsigned int s = (unsigned int)__ffs((int)touch) - 1u;
+          touch &= touch - 1u;
+          s_item[at++] = (unsigned short)((q << 4) | s);
+        }
+      }
+      __syncthreads();
+      /* ---- the face terms, all threads ---- */
+      for (unsigned int it = tid; it < total_items; it += SH_THREADS) {
+        const unsigned int q = s_item[it] >> 4, s = s_item[it] & 15u;
+        const ShadeSlot slot = s_slot[q];
+        const V3 term = face_term(p, slot.obj, slot.i, slot.j, slot.k, slot.code, s);
+        s_term[it][0] = term.x; s_term[it][1] = term.y; s_term[it][2] = term.z;
+      }
+      __syncthreads();
+      /* ---- per vertex, add the terms in order and normalise (average(), normal.c:6-43, 159) ---- */
+      if (tid < SH_VERTS && base + tid < nv && C3D_NO_SLOT != __ldg(vlist + base + tid)) {
+        const unsigned int q0 = tid * 4u;
+        V3 sum = V3{0., 0., 0.};
+        for (unsigned int it = s_first[q0]; it < s_first[q0 + 4u]; it++) {
+          sum = v_add(sum, V3{s_term[it][0], s_term[it][1], s_term[it][2]});
+        }
+        store_normal(v_unit(sum), base + tid, __ldg(vlist + base + tid), vn, vn_cap, table);
+      }
+    } else {
+      /* more touching triangles than the shared buffer holds: the same sums, one thread per vertex */
+      if (0u == tid) atomicAdd(overflowed, 1ull);
+      if (tid < SH_VERTS && base + tid < nv && C3D_NO_SLOT != __ldg(vlist + base + tid)) {
+        V3 sum = V3{0., 0., 0.};
+        for (unsigned int q = tid * 4u; q < tid * 4u + 4u; q++) {
+          const ShadeSlot slot = s_slot[q];
+          unsigned int touch = slot.touch;
+          while (touch) {
+            const unsigned int s = (unsigned int)__ffs((int)touch) - 1u;
+            touch &= touch - 1u;
+            sum = v_add(sum, face_term(p, slot.obj, slot.i, slot.j, slot.k, slot.code, s));
+          }
+        }
+        store_normal(v_unit(sum), base + tid, __ldg(vlist + base + tid), vn, vn_cap, table);
       }
     }
-    if (valid && 0u == sub) {
-      const V3 unit = v_unit(sum);                                  /* normal.c:159 */
-      vn[3ull * slot + 0ull] = unit.x; vn[3ull * slot + 1ull] = unit.y; vn[3ull * slot + 2ull] = unit.z;
-    }
+    __syncthreads();
   }
 }
 
 /* ------------------------------------------------------------------- blend */
 
 __global__ void __launch_bounds__(128) k_shade_blend(const __grid_constant__ FrameParams p, const ShadePix *__restrict__ in,
-                                                     const unsigned int *__restrict__ counters, const double *__restrict__ vn,
-                                                     unsigned int *__restrict__ rgba) {
+                                                     const unsigned int *__restrict__ counters, const unsigned long long *__restrict__ table,
+                                                     const double *__restrict__ vn, unsigned int *__restrict__ rgba) {
   const unsigned int n = counters[0];
   for (unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const ShadePix sp = in[idx];
@@ -317,7 +413,8 @@ __global__ void __launch_bounds__(128) k_shade_blend(const __grid_constant__ Fra
 #pragma unroll
     for (int m = 0; m < 3; m++) {
       const unsigned int slot = sp.vslot[m];
-      if (C3D_NO_SLOT != slot) nv[m] = V3{vn[3ull * slot + 0ull], vn[3ull * slot + 1ull], vn[3ull * slot + 2ull]};
+      const unsigned int v = C3D_NO_SLOT != slot ? (unsigned int)table[slot] : C3D_NO_SLOT;
+      if (C3D_NO_SLOT != v) nv[m] = V3{vn[3ull * v + 0ull], vn[3ull * v + 1ull], vn[3ull * v + 2ull]};
       else nv[m] = vertex_normal(f, p.tab, (long long)sp.i, (long long)sp.j, (long long)sp.k, (unsigned int)sp.edges[m]);
     }
     /* w0*n0 + (w1*n1 + w2*n2), render.c:137-146 */
@@ -330,6 +427,13 @@ __global__ void __launch_bounds__(128) k_shade_blend(const __grid_constant__ Fra
   }
 }
 
+/* resident blocks of a kernel on this device (grid-stride kernels are launched with exactly that many) */
+template <typename K> static int resident_blocks(K kernel, const int threads, const int sm_count) {
+  int per_sm = 0;
+  if (cudaSuccess != cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) || per_sm < 1) per_sm = 4;
+  return per_sm * sm_count;
+}
+
 extern "C" int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
                            unsigned int *rgba, size_t npix, const ShadeScratch *sc, unsigned long long *overflowed,
                            int sm_count, cudaStream_t s) {
@@ -338,9 +442,9 @@ extern "C" int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const
   err = cudaMemsetAsync(sc->table, 0, ((size_t)sc->table_mask + 1u) * sizeof(unsigned long long), s);
   if (cudaSuccess != err) return (int)err;
   k_shade_select<<<sm_count * 8, 256, 0, s>>>(*p, lines_dev, canvas, depth_global, rgba, npix, sc->work, sc->counters);
-  k_shade_setup<<<sm_count * 12, 128, 0, s>>>(*p, canvas, sc->work, sc->counters, static_cast<ShadePix *>(sc->pix), sc->table, sc->table_mask,
-                                              sc->vlist, overflowed);
-  k_shade_normals<<<sm_count * 12, 128, 0, s>>>(*p, sc->table, sc->vlist, sc->counters, sc->vn);
-  k_shade_blend<<<sm_count * 12, 128, 0, s>>>(*p, static_cast<const ShadePix *>(sc->pix), sc->counters, sc->vn, rgba);
+  k_shade_setup<<<resident_blocks(k_shade_setup, 128, sm_count), 128, 0, s>>>(*p, canvas, sc->work, sc->counters, static_cast<ShadePix *>(sc->pix),
+                                                                              sc->table, sc->table_mask, sc->vlist, overflowed);
+  k_shade_normals<<<resident_blocks(k_shade_normals, SH_THREADS, sm_count), SH_THREADS, 0, s>>>(*p, sc->table, sc->vlist, sc->counters, sc->vn, sc->vn_cap, overflowed);
+  k_shade_blend<<<resident_blocks(k_shade_blend, 128, sm_count), 128, 0, s>>>(*p, static_cast<const ShadePix *>(sc->pix), sc->counters, sc->table, sc->vn, rgba);
   return (int)cudaGetLastError();
 }
