@@ -104,19 +104,44 @@ __device__ __forceinline__ unsigned int cube_code(const FieldView &f, const long
   return code;
 }
 
-/* area * face_normal of triangle s of a cube (triangulate.c:75-93, normal.c:39-40) */
-__device__ __forceinline__ V3 face_term(const FrameParams &p, const unsigned int obj, const long long i, const long long j, const long long k,
-                                        const unsigned int code, const unsigned int s) {
-  const FieldView &f = p.view[obj];
-  const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
-  V3 v[3], fn;
-  double area;
+/* area * face_normal of triangle s of a cube (triangulate.c:75-93, normal.c:39-40).  The same arithmetic as
+   cut_edge_global() + face_normal() (c3d_device.cuh), with the loads hoisted: the cube's six coordinates once instead of
+   per vertex, element type decided once. */
+template <typename T>
+__device__ __forceinline__ V3 face_term_of(const FieldView &f, const unsigned int pairs, const long long i, const long long j, const long long k) {
+  const T *__restrict__ at = static_cast<const T *>(f.data) + (k * f.sz + j * f.sy + i);
+  const double x0 = __ldg(f.g[0] + i), x1 = __ldg(f.g[0] + i + 1);
+  const double y0 = __ldg(f.g[1] + j), y1 = __ldg(f.g[1] + j + 1);
+  const double z0 = __ldg(f.g[2] + k), z1 = __ldg(f.g[2] + k + 1);
+  V3 v[3];
 #pragma unroll
-  for (int m = 0; m < 3; m++) v[m] = cut_edge_global(f, i, j, k, f.thr, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+  for (int m = 0; m < 3; m++) {
+    const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
+    const double v0 = (double)__ldg(at + ((tail & 1u) + ((tail & 2u) ? f.sy : 0ll) + ((tail & 4u) ? f.sz : 0ll)));
+    const double v1 = (double)__ldg(at + ((head & 1u) + ((head & 2u) ? f.sy : 0ll) + ((head & 4u) ? f.sz : 0ll)));
+    const V3 p0 = V3{(tail & 1u) ? x1 : x0, (tail & 2u) ? y1 : y0, (tail & 4u) ? z1 : z0};
+    /* triangulate.c:40-73 */
+    const double dv = r_sub(v1, v0);
+    if (fabs(dv) < 1.e-8) {
+      v[m] = p0;
+    } else {
+      const double factor = r_div(r_sub(f.thr, v0), dv);
+      const V3 p1 = V3{(head & 1u) ? x1 : x0, (head & 2u) ? y1 : y0, (head & 4u) ? z1 : z0};
+      v[m] = v_add(p0, v_mul(factor, v_sub(p1, p0)));
+    }
+  }
+  V3 fn;
+  double area;
   face_normal(v, fn, area);
   return v_mul(area, fn);
 }
 
+__device__ __forceinline__ V3 face_term(const FrameParams &p, const unsigned int obj, const long long i, const long long j, const long long k,
+                                        const unsigned int code, const unsigned int s) {
+  const FieldView &f = p.view[obj];
+  const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
+  return 4 == f.elem_bytes ? face_term_of<float>(f, pairs, i, j, k) : face_term_of<double>(f, pairs, i, j, k);
+}
 
 /* ------------------------------------------------------------------- setup */
 
