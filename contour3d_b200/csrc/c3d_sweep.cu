@@ -494,20 +494,41 @@ __device__ __forceinline__ bool patch_irregular(const FieldView &f, const unsign
     const float *data = (const float *)f.data;
     const bool vec = (0 == (f.sy & 3)) && (0 == (f.sz & 3)) && (0 == ((uintptr_t)data & 15)) && nx >= 4;   /* x is a multiple of 4 */
     float amin = FLT_MAX, amax = 0.f, sum = 0.f;
+    if (vec) {
+      /* all rows of a plane are requested before any is looked at (rows that are not needed, or lie beyond the array, re-read
+         a needed one): the test is bound by the latency of these scattered loads, not by their number */
+      const int last = (int)((f.n[1] - 1 - (long long)j) < 8 ? (f.n[1] - 1 - (long long)j) : 8);
+      const int fallback = __ffs((int)need) - 1;
+#pragma unroll
+      for (int dz = 0; dz < 2; dz++) {
+        const float *plane = data + ((long long)k + dz) * f.sz + (long long)j * f.sy + (long long)x;
+        float4 q[9];
+        float e[9];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          const int rr = (((need >> r) & 1u) && r <= last) ? r : fallback;
+          const float *row = plane + (long long)rr * f.sy;
+          q[r] = __ldg(reinterpret_cast<const float4 *>(row));
+          e[r] = __ldg(row + (nx > 4 ? 4 : 3));
+        }
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          const float a0 = fabsf(q[r].x - thr32), a1 = fabsf(q[r].y - thr32), a2 = fabsf(q[r].z - thr32), a3 = fabsf(q[r].w - thr32), a4 = fabsf(e[r] - thr32);
+          amin = fminf(amin, fminf(fminf(a0, a1), fminf(fminf(a2, a3), a4)));
+          amax = fmaxf(amax, fmaxf(fmaxf(a0, a1), fmaxf(fmaxf(a2, a3), a4)));
+          sum += (a0 + a1) + (a2 + a3) + a4;             /* NaN / inf detector (fminf / fmaxf would drop a NaN) */
+        }
+      }
+      return !(sum <= FLT_MAX) || !(amin > 1.1e-6f * amax + thr_err);
+    }
     for (int dz = 0; dz < 2; dz++) {
       for (int r = 0; r < 9; r++) {
         if ((long long)j + r >= f.n[1]) break;
         if (0u == ((need >> r) & 1u)) continue;
         const float *row = data + ((long long)k + dz) * f.sz + ((long long)j + r) * f.sy + (long long)x;
         float v[5];
-        if (vec) {
-          const float4 q = __ldg(reinterpret_cast<const float4 *>(row));
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-          v[4] = nx > 4 ? __ldg(row + 4) : q.w;
-        } else {
 #pragma unroll
-          for (int c = 0; c < 5; c++) v[c] = __ldg(row + (c < nx ? c : 0));
-        }
+        for (int c = 0; c < 5; c++) v[c] = __ldg(row + (c < nx ? c : 0));
 #pragma unroll
         for (int c = 0; c < 5; c++) {
           const float a = fabsf(v[c] - thr32);
