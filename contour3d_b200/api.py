@@ -50,17 +50,62 @@ class Scene(C.Structure):
     ]
 
 
+class Positions(C.Structure):
+    """c3d_positions_t: a coordinate converter tabulated over the extended local array"""
+    _fields_ = [("table", C.POINTER(C.c_double) * 3), ("stride", (C.c_size_t * 3) * 3)]
+
+
 class ContourDesc(C.Structure):
     _fields_ = [
         ("field", C.c_void_p),
         ("grids", C.POINTER(C.c_double) * 3),
         ("threshold", C.c_double),
         ("color", C.c_uint8 * 3),
+        ("positions", C.POINTER(Positions)),
     ]
 
 
 class LineDesc(C.Structure):
-    _fields_ = [("edges", (C.c_double * 3) * 2), ("nitems", C.c_size_t), ("width", C.c_double), ("color", C.c_uint8 * 3)]
+    _fields_ = [("edges", (C.c_double * 3) * 2), ("nitems", C.c_size_t), ("width", C.c_double), ("color", C.c_uint8 * 3),
+                ("points", C.POINTER(C.c_double))]
+
+
+CONVERTER_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+
+def positions_probe(convert, grids, offset, count, max_bytes=1 << 30):
+    """c3d_positions_probe on a Python function (x, y, z) -> (X, Y, Z); host only, no device needed.
+    Returns (identity, tables, strides): tables are numpy copies of the three component tables (None when identity)."""
+    def tramp(pin, pout, _user):
+        out = convert(pin[0], pin[1], pin[2])
+        pout[0], pout[1], pout[2] = float(out[0]), float(out[1]), float(out[2])
+
+    cb = CONVERTER_FN(tramp)
+    gs = [np.ascontiguousarray(g, dtype=np.float64) for g in grids]
+    garr = (C.POINTER(C.c_double) * 3)(*[g.ctypes.data_as(C.POINTER(C.c_double)) for g in gs])
+    off = (C.c_size_t * 3)(*[int(v) for v in offset])
+    cnt = (C.c_size_t * 3)(*[int(v) for v in count])
+    pos = Positions()
+    ident = C.c_int(1)
+    fn = lib().c3d_positions_probe
+    fn.restype = C.c_int
+    fn.argtypes = [CONVERTER_FN, C.c_void_p, C.POINTER(C.POINTER(C.c_double) * 3), C.POINTER(C.c_size_t * 3), C.POINTER(C.c_size_t * 3),
+                   C.c_size_t, C.POINTER(Positions), C.POINTER(C.c_int)]
+    rc = fn(cb, None, C.byref(garr), C.byref(off), C.byref(cnt), int(max_bytes), C.byref(pos), C.byref(ident))
+    if rc != 0:
+        raise RuntimeError("c3d_positions_probe failed (see stderr)")
+    if ident.value:
+        return True, None, None
+    strides = [[int(pos.stride[c][a]) for a in range(3)] for c in range(3)]
+    tables = []
+    for c in range(3):
+        n = 1 + sum((int(count[a]) - 1) * strides[c][a] for a in range(3))
+        tables.append(np.ctypeslib.as_array(pos.table[c], shape=(n,)).copy())
+    free = lib().c3d_positions_free
+    free.restype = None
+    free.argtypes = [C.POINTER(Positions)]
+    free(C.byref(pos))
+    return False, tables, strides
 
 
 class Timings(C.Structure):
@@ -127,7 +172,7 @@ _compat = None
 
 EXPORTS = [
     "c3d_nccl_unique_id", "c3d_context_create", "c3d_context_destroy", "c3d_context_device", "c3d_context_stream",
-    "c3d_context_synchronize", "c3d_decomp_make", "c3d_decomp_local", "c3d_field_create", "c3d_field_destroy",
+    "c3d_context_synchronize", "c3d_positions_probe", "c3d_positions_free", "c3d_decomp_make", "c3d_decomp_local", "c3d_field_create", "c3d_field_destroy",
     "c3d_field_upload", "c3d_field_geometry", "c3d_field_interior", "c3d_field_mark_dirty", "c3d_field_exchange",
     "c3d_field_download_ext", "c3d_field_synthesize", "c3d_frame_render", "c3d_frame_timings", "c3d_frame_canvas",
     "c3d_case_codes", "c3d_sweep", "c3d_tessellate", "c3d_version", "contour3d_execute",
@@ -312,6 +357,18 @@ class Context:
                 carr[n].grids[d] = g.ctypes.data_as(C.POINTER(C.c_double))
             carr[n].threshold = float(c["threshold"])
             carr[n].color[:] = list(c.get("color", (255, 255, 255)))
+            if c.get("positions") is not None:
+                # (tables, strides) over the field's EXTENDED local array, e.g. from positions_probe
+                tables, strides = c["positions"]
+                pos = Positions()
+                for comp in range(3):
+                    t = np.ascontiguousarray(tables[comp], dtype=np.float64)
+                    keep.append(t)
+                    pos.table[comp] = t.ctypes.data_as(C.POINTER(C.c_double))
+                    for a in range(3):
+                        pos.stride[comp][a] = int(strides[comp][a])
+                keep.append(pos)
+                carr[n].positions = C.pointer(pos)
         larr = (LineDesc * max(1, len(lines)))()
         for n, l in enumerate(lines):
             larr[n].edges[0][:] = l["edges"][0]
@@ -319,6 +376,10 @@ class Context:
             larr[n].nitems = int(l["nitems"])
             larr[n].width = float(l["width"])
             larr[n].color[:] = list(l.get("color", (255, 255, 255)))
+            if l.get("points") is not None:
+                pts = np.ascontiguousarray(l["points"], dtype=np.float64).reshape(int(l["nitems"]), 3)
+                keep.append(pts)
+                larr[n].points = pts.ctypes.data_as(C.POINTER(C.c_double))
         out = None
         ptr = None
         if want_rgb and self.rank == 0:

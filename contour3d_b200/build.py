@@ -80,11 +80,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 sys.stderr.write(p.stderr)
         objs.append(obj)
-    src = os.path.join(CSRC, "contour3d_execute.c")
-    obj = os.path.join(OBJ, "contour3d_execute.o")
-    if force or _newer(obj, [src] + headers):
-        _run([cc, "-std=c99", "-O2", "-Wall", "-Wextra", "-fPIC"] + inc + mpi_inc + ["-c", src, "-o", obj])
-    objs.append(obj)
+    for name in ("contour3d_execute.c", "c3d_positions.c"):
+        src = os.path.join(CSRC, name)
+        obj = os.path.join(OBJ, name[:-2] + ".o")
+        if force or _newer(obj, [src] + headers):
+            # -ffp-contract=off: the line points of a converted poly-line follow the reference's -std=c99 arithmetic
+            _run([cc, "-std=c99", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-fPIC"] + inc + mpi_inc + ["-c", src, "-o", obj])
+        objs.append(obj)
     if force or _newer(LIB, objs):
         # `sdecomp` and the MPI_* symbols stay undefined: the embedding program
         # (or libc3d_sdecomp_compat.so) provides them
@@ -99,7 +101,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         link = ["-L", PKG, "-lcontour3d_b200", "-Wl,-rpath,$ORIGIN"]
         if not have_real_mpi():
             link += ["-lc3d_sdecomp_compat"]
-        _run([cc, "-std=gnu11", "-O2", "-D_POSIX_C_SOURCE=200809L"] + inc + mpi_inc + ["-o", CASE, src] + link + ["-lm"])
+        _run([cc, "-std=c99", "-O3", "-D_POSIX_C_SOURCE=200809L"] + inc + mpi_inc + ["-o", CASE, src] + link + ["-lm"])  # the reference driver's flags (oracle/Makefile): the built-in converters must round alike
     return LIB
 
 

@@ -8,7 +8,8 @@ contour / line objects, global fields).  The same file is consumed by
 Layout (little endian, no implicit padding):
   header   char magic[8]="C3DCASE1"; u64 n[3], width, height, ncontours, nlines,
            elem_bytes (4|8), nfields; f64 camera[3], look_at[3], light[3],
-           center[3], local_x[3], local_y[3]; u8 bg[3], pad[5]
+           center[3], local_x[3], local_y[3]; u8 bg[3], converter (0 identity, 1 cylindrical,
+           2 stretched, 3 twisted: functions built into c3d_case_main.c), pad[4]
   grids    f64 x[n0], y[n1], z[n2]
   contours ncontours x { u64 field; f64 threshold; u8 color[3], pad[5] }
   lines    nlines x { f64 edges[6]; u64 nitems; f64 width; u8 color[3], pad[5] }
@@ -65,6 +66,7 @@ def write_case(path, scene: dict, grids, fields, contours, lines=()):
         h[key] = scene[key]
     h["look_at"] = scene.get("look_at", (0.0, 0.0, 0.0))
     h["bg"] = scene.get("bg", (0, 0, 0))
+    h["pad"][0] = int(scene.get("converter", 0))    # 0 identity, 1 cylindrical, 2 stretched, 3 twisted (c3d_case_main.c)
     cs = np.zeros(len(contours), dtype=CONTOUR)
     for n, c in enumerate(contours):
         cs[n]["field"] = c.get("field", 0)
@@ -101,7 +103,7 @@ def read_case(path):
         dt = np.float32 if int(h["elem_bytes"]) == 4 else np.float64
         fields = [np.fromfile(fp, dtype=dt, count=nx * ny * nz).reshape(nz, ny, nx) for _ in range(int(h["nfields"]))]
     scene = {k: tuple(float(v) for v in h[k]) for k in ("camera", "look_at", "light", "center", "local_x", "local_y")}
-    scene.update(width=int(h["width"]), height=int(h["height"]), bg=tuple(int(v) for v in h["bg"]))
+    scene.update(width=int(h["width"]), height=int(h["height"]), bg=tuple(int(v) for v in h["bg"]), converter=int(h["pad"][0]))
     contours = [dict(field=int(c["field"]), threshold=float(c["threshold"]), color=tuple(int(v) for v in c["color"])) for c in cs]
     lines = [
         dict(edges=(tuple(l["edges"][:3]), tuple(l["edges"][3:])), nitems=int(l["nitems"]), width=float(l["width"]),

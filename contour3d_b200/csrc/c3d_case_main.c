@@ -10,8 +10,9 @@
  * reference sources (-> oracle/_ref/ref_driver, the CPU baseline).
  *
  * The case file (contour3d_b200/casefile.py) holds the scene, the grids, the
- * contour / line objects and one or more global fields (fp32 or fp64, x
- * fastest).  Every rank reads its own X1 pencil, widening fp32 to double
+ * contour / line objects, one or more global fields (fp32 or fp64, x
+ * fastest) and the coordinate converter every object uses (0 identity,
+ * 1 cylindrical, 2 stretched, 3 twisted: built-in functions below).  Every rank reads its own X1 pencil, widening fp32 to double
  * exactly, fills the public structs and calls contour3d_execute
  * (include/contour3d.h:58-86).  Rank 0 prints one JSON line with the wall
  * time of contour3d_execute (max over ranks, field I/O excluded).
@@ -29,7 +30,32 @@
 #include "sdecomp.h"
 #include "contour3d.h"
 
+#include <math.h>
+
+/* coordinate converters a case file can ask for (header byte pad[0]); the same functions run inside the unmodified
+   reference (ref_driver) and behind the drop-in (c3d_case), which tabulates them for the device */
 static contour3d_vector_t identity(const contour3d_vector_t o) { return o; }
+/* 1: annular sector, (r, theta, z) -> Cartesian: depends on two directions in two components */
+static contour3d_vector_t cylindrical(const contour3d_vector_t o) {
+  const double r = 0.75 + 0.5 * o.x, theta = 1.5 * o.y;
+  const contour3d_vector_t c = {r * cos(theta) - 0.75, r * sin(theta), o.z};
+  return c;
+}
+/* 2: stretched grid, separable */
+static contour3d_vector_t stretched(const contour3d_vector_t o) {
+  const contour3d_vector_t c = {o.x + 0.3 * o.x * o.x * o.x, 1.2 * o.y, o.z - 0.2 * o.z * o.z};
+  return c;
+}
+/* 3: twisted column: every component depends on all three directions */
+static contour3d_vector_t twisted(const contour3d_vector_t o) {
+  const double a = 0.8 * o.z;
+  const contour3d_vector_t c = {o.x * cos(a) - o.y * sin(a) + 0.02 * o.z * o.y, o.x * sin(a) + o.y * cos(a), o.z + 0.05 * sin(3. * o.x) * o.y};
+  return c;
+}
+typedef contour3d_vector_t (*converter_t)(const contour3d_vector_t);
+static converter_t converter_of(const int kind) {
+  return 1 == kind ? cylindrical : (2 == kind ? stretched : (3 == kind ? twisted : identity));
+}
 
 typedef struct {
   char magic[8];
@@ -111,7 +137,7 @@ int main(int argc, char **argv) {
   for (uint64_t n = 0; n < h.ncontours; n++) {
     cobjs[n].pencil = SDECOMP_X1PENCIL;
     for (int d = 0; d < 3; d++) { cobjs[n].glsizes[d] = h.n[d]; cobjs[n].grids[d] = grids[d]; }
-    cobjs[n].converter = identity;
+    cobjs[n].converter = converter_of(h.pad[0]);
     cobjs[n].threshold = cc[n].threshold;
     cobjs[n].color.r = cc[n].color[0]; cobjs[n].color.g = cc[n].color[1]; cobjs[n].color.b = cc[n].color[2];
     cobjs[n].array = fields[cc[n].field];
@@ -124,7 +150,7 @@ int main(int argc, char **argv) {
       lobjs[n].edges[e].z = cl[n].edges[3 * e + 2];
     }
     lobjs[n].nitems = cl[n].nitems;
-    lobjs[n].converter = identity;
+    lobjs[n].converter = converter_of(h.pad[0]);
     lobjs[n].color.r = cl[n].color[0]; lobjs[n].color.g = cl[n].color[1]; lobjs[n].color.b = cl[n].color[2];
     lobjs[n].width = cl[n].width;
   }

@@ -54,11 +54,21 @@ __device__ __forceinline__ double ld_value(const FieldView &f, const long long i
   return 4 == f.elem_bytes ? (double)__ldg((const float *)f.data + idx) : __ldg((const double *)f.data + idx);
 }
 
-/* eight corner scalars + the two coordinates per axis (identity converter);
+/* Cartesian position of grid point (i, j, k) under a tabulated coordinate converter (PosMap, c3d_internal.h) */
+__device__ __forceinline__ V3 mapped_pos(const PosMap *__restrict__ m, const long long i, const long long j, const long long k) {
+  return V3{__ldg(m->pos[0] + (i * m->ps[0][0] + j * m->ps[0][1] + k * m->ps[0][2])),
+            __ldg(m->pos[1] + (i * m->ps[1][0] + j * m->ps[1][1] + k * m->ps[1][2])),
+            __ldg(m->pos[2] + (i * m->ps[2][0] + j * m->ps[2][1] + k * m->ps[2][2]))};
+}
+
+/* eight corner scalars + the two coordinates per axis (identity converter) or the
+   cube's place in the position tables (any other converter);
    triangulate.c:156-173, 302-317 */
 struct Cube {
   double val[8];
   double px[2], py[2], pz[2];
+  const PosMap *map;
+  long long i, j, k;
 };
 
 __device__ __forceinline__ void load_cube(const FieldView &f, const long long i, const long long j, const long long k, Cube &c) {
@@ -67,9 +77,14 @@ __device__ __forceinline__ void load_cube(const FieldView &f, const long long i,
   for (int n = 0; n < 8; n++) {
     c.val[n] = ld_value(f, base + (n & 1) + ((n >> 1) & 1) * f.sy + (n >> 2) * f.sz);
   }
-  c.px[0] = __ldg(f.g[0] + i); c.px[1] = __ldg(f.g[0] + i + 1);
-  c.py[0] = __ldg(f.g[1] + j); c.py[1] = __ldg(f.g[1] + j + 1);
-  c.pz[0] = __ldg(f.g[2] + k); c.pz[1] = __ldg(f.g[2] + k + 1);
+  c.map = f.map;
+  c.i = i; c.j = j; c.k = k;
+  c.px[0] = c.px[1] = c.py[0] = c.py[1] = c.pz[0] = c.pz[1] = 0.;
+  if (nullptr == f.map) {
+    c.px[0] = __ldg(f.g[0] + i); c.px[1] = __ldg(f.g[0] + i + 1);
+    c.py[0] = __ldg(f.g[1] + j); c.py[1] = __ldg(f.g[1] + j + 1);
+    c.pz[0] = __ldg(f.g[2] + k); c.pz[1] = __ldg(f.g[2] + k + 1);
+  }
 }
 
 /* corner bits: bit n set when thr < value[n] (strict), triangulate.c:176-179 */
@@ -81,6 +96,7 @@ __device__ __forceinline__ unsigned int corner_code(const Cube &c, const double 
 }
 
 __device__ __forceinline__ V3 corner_pos(const Cube &c, const unsigned int n) {
+  if (nullptr != c.map) return mapped_pos(c.map, c.i + (n & 1u), c.j + ((n >> 1) & 1u), c.k + (n >> 2));
   return V3{c.px[n & 1u], c.py[(n >> 1) & 1u], c.pz[(n >> 2) & 1u]};
 }
 
@@ -97,17 +113,31 @@ __device__ __forceinline__ V3 cut_edge(const Cube &c, const double thr, const un
 
 /* the same vertex straight from global memory (no register-indexed cube copy):
    used where a thread needs one triangle of a cube, not all of them */
-__device__ __forceinline__ V3 cut_edge_global(const FieldView &f, const long long i, const long long j, const long long k,
-                                              const double thr, const unsigned int tail, const unsigned int head) {
+/* MAPPED = false compiles the converter-table branch out (the raster's hot path when no object of the frame has one) */
+template <bool MAPPED>
+__device__ __forceinline__ V3 cut_edge_global_t(const FieldView &f, const long long i, const long long j, const long long k,
+                                                const double thr, const unsigned int tail, const unsigned int head) {
   const long long base = k * f.sz + j * f.sy + i;
   const double v0 = ld_value(f, base + (tail & 1u) + ((tail >> 1) & 1u) * f.sy + (tail >> 2) * f.sz);
   const double v1 = ld_value(f, base + (head & 1u) + ((head >> 1) & 1u) * f.sy + (head >> 2) * f.sz);
-  const V3 p0 = V3{__ldg(f.g[0] + i + (tail & 1u)), __ldg(f.g[1] + j + ((tail >> 1) & 1u)), __ldg(f.g[2] + k + (tail >> 2))};
   const double dv = r_sub(v1, v0);
+  if (MAPPED && nullptr != f.map) {      /* converted coordinates: interpolation happens in Cartesian space (triangulate.c:165-170) */
+    const V3 m0 = mapped_pos(f.map, i + (tail & 1u), j + ((tail >> 1) & 1u), k + (tail >> 2));
+    if (fabs(dv) < 1.e-8) return m0;
+    const double mfactor = r_div(r_sub(thr, v0), dv);
+    const V3 m1 = mapped_pos(f.map, i + (head & 1u), j + ((head >> 1) & 1u), k + (head >> 2));
+    return v_add(m0, v_mul(mfactor, v_sub(m1, m0)));
+  }
+  const V3 p0 = V3{__ldg(f.g[0] + i + (tail & 1u)), __ldg(f.g[1] + j + ((tail >> 1) & 1u)), __ldg(f.g[2] + k + (tail >> 2))};
   if (fabs(dv) < 1.e-8) return p0;
   const double factor = r_div(r_sub(thr, v0), dv);
   const V3 p1 = V3{__ldg(f.g[0] + i + (head & 1u)), __ldg(f.g[1] + j + ((head >> 1) & 1u)), __ldg(f.g[2] + k + (head >> 2))};
   return v_add(p0, v_mul(factor, v_sub(p1, p0)));
+}
+
+__device__ __forceinline__ V3 cut_edge_global(const FieldView &f, const long long i, const long long j, const long long k,
+                                              const double thr, const unsigned int tail, const unsigned int head) {
+  return cut_edge_global_t<true>(f, i, j, k, thr, tail, head);
 }
 
 __device__ __forceinline__ void triangle_vertices(const Cube &c, const double thr, const unsigned int pairs, V3 v[3]) {
@@ -303,11 +333,16 @@ __device__ __forceinline__ void submit_fragment(Pixel *slot, const unsigned long
 /* triangle vertex on the cube edge tail -> head (triangulate.c:40-73), projected (project.c:9-67);
    returned by value (registers), .w = 1 when the projection accepted the point */
 struct ProjectedVertex { double x, y, z, w; };
-static __device__ __noinline__ ProjectedVertex exact_vertex(const FrameParams &p, const unsigned int obj, const long long i, const long long j,
-                                                            const long long k, const unsigned int tail, const unsigned int head) {
+template <bool MAPPED>
+static __device__ __noinline__ ProjectedVertex exact_vertex_t(const FrameParams &p, const unsigned int obj, const long long i, const long long j,
+                                                              const long long k, const unsigned int tail, const unsigned int head) {
   const FieldView &f = p.view[obj];
   V3 q = V3{0., 0., 0.};
-  const bool ok = project(p.cam, cut_edge_global(f, i, j, k, f.thr, tail, head), q);
+  const bool ok = project(p.cam, cut_edge_global_t<MAPPED>(f, i, j, k, f.thr, tail, head), q);
   return ProjectedVertex{q.x, q.y, q.z, ok ? 1. : 0.};
+}
+__device__ __forceinline__ ProjectedVertex exact_vertex(const FrameParams &p, const unsigned int obj, const long long i, const long long j,
+                                                        const long long k, const unsigned int tail, const unsigned int head) {
+  return exact_vertex_t<true>(p, obj, i, j, k, tail, head);
 }
 

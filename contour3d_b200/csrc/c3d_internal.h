@@ -18,6 +18,25 @@ struct DevTables {
   const uint16_t *touch;
 };
 
+/* Cartesian positions of the grid points of a contour object whose coordinate converter is not the identity
+   (include/contour3d.h:31-33; the reference calls it for every cube corner, triangulate.c:156-173): component c of point
+   (i, j, k) of the extended local array is pos[c][i * ps[c][0] + j * ps[c][1] + k * ps[c][2]].  The tables are filled on the
+   host with the caller's own function; a stride of 0 marks a direction the component does not depend on. */
+struct PosMap {
+  const double *pos[3];
+  const float *posf[3];    /* the same rounded to fp32 (conservative visibility pre-tests only) */
+  long long ps[3][3];
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void mapped_posf(const PosMap *__restrict__ m, const long long i, const long long j, const long long k,
+                                            float &x, float &y, float &z) {
+  x = __ldg(m->posf[0] + (i * m->ps[0][0] + j * m->ps[0][1] + k * m->ps[0][2]));
+  y = __ldg(m->posf[1] + (i * m->ps[1][0] + j * m->ps[1][1] + k * m->ps[1][2]));
+  z = __ldg(m->posf[2] + (i * m->ps[2][0] + j * m->ps[2][1] + k * m->ps[2][2]));
+}
+#endif
+
 /* one contour object as the kernels see it: the extended local array */
 struct FieldView {
   const void *data;        /* first point of the extended array */
@@ -26,6 +45,7 @@ struct FieldView {
   long long sy, sz;        /* row / plane strides in elements */
   const double *g[3];      /* device coordinates of exactly those points */
   const float *gf[3];      /* the same rounded to fp32 (conservative visibility pre-tests only) */
+  const PosMap *map;       /* device pointer; nullptr: identity converter, positions are (g[0][i], g[1][j], g[2][k]) */
   double thr;              /* iso value; classification is thr < value (strict) */
   float thr_ge;            /* fp32 fields: smallest float f with (double)f > thr, so thr < v <=> v >= thr_ge */
   unsigned char color[3];
@@ -43,6 +63,7 @@ struct Cam {
 struct LineDev {
   double e0[3], delta[3];  /* first point and per-segment step (line.c:138-140) */
   double half_width_sq;    /* pow(0.5 * width, 2), line.c:87 */
+  const double *points;    /* device; nullptr: identity converter (points are e0 + n * delta), else nitems x 3 converted points */
   unsigned long long first_segment; /* index of this line's first segment in the frame-wide numbering */
   unsigned long long nsegments;
   unsigned char color[3];

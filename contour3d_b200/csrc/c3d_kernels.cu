@@ -281,6 +281,7 @@ extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int
  * Z-buffer: one 128-bit CAS per surviving fragment on (ord(depth), key); see
  * submit_fragment().
  */
+template <bool MAPPED>
 __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsigned long long entry, const unsigned int s,
                                                 Pixel *__restrict__ canvas) {
   const unsigned int obj = C3D_ENTRY_OBJ(entry), code = C3D_ENTRY_CODE(entry);
@@ -291,7 +292,7 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
      within reach of the instruction cache while its warps sit in different phases */
 #pragma unroll
   for (int m = 0; m < 3; m++) {
-    const ProjectedVertex v = exact_vertex(p, obj, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+    const ProjectedVertex v = exact_vertex_t<MAPPED>(p, obj, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
     if (0. == v.w) return;                          /* render.c:62-72 */
     t.q[m] = V3{v.x, v.y, v.z};
   }
@@ -401,6 +402,7 @@ __device__ __forceinline__ bool hiz_hidden(const HiZ &z, const CullCam &q, const
  * fp32 error (0.25 pixel, 1e-4 relative depth); anything doubtful is kept.
  * With a depth complexity of ~20 most cubes of a turbulent field are hidden.
  */
+template <bool MAPPED>
 __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned long long entry, const Pixel *__restrict__ canvas, const HiZ &hiz) {
   /* A triangle whose vertices have collapsed onto one cube corner is drawn by the reference as a blob: the
      clamped area (render.c:103-106) makes all three weights +-0, every pixel of the +-1 pixel box passes the
@@ -411,28 +413,47 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
   const CullCam &q = p.cull;
   const FieldView &f = p.view[C3D_ENTRY_OBJ(entry)];
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
-  float an[2], al[2], am[2], bn[2], bl[2], bm[2], cn[2], cl[2], cm[2];
-#pragma unroll
-  for (int e = 0; e < 2; e++) {
-    const float rx = __ldg(f.gf[0] + i + e) - q.cam[0];
-    const float ry = __ldg(f.gf[1] + j + e) - q.cam[1];
-    const float rz = __ldg(f.gf[2] + k + e) - q.cam[2];
-    an[e] = q.n[0] * rx; al[e] = q.lxs[0] * rx; am[e] = q.lys[0] * rx;
-    bn[e] = q.n[1] * ry; bl[e] = q.lxs[1] * ry; bm[e] = q.lys[1] * ry;
-    cn[e] = q.n[2] * rz; cl[e] = q.lxs[2] * rz; cm[e] = q.lys[2] * rz;
-  }
   float xlo = 3.e38f, xhi = -3.e38f, ylo = 3.e38f, yhi = -3.e38f, znear = -3.e38f, tlo = 3.e38f, thi = -3.e38f;
+  if (MAPPED && nullptr != f.map) {
+    /* tabulated converter: the eight corners are arbitrary points; every triangle vertex still lies on a segment between
+       two of them (triangulate.c:40-73), i.e. inside their hull */
+#pragma unroll 1
+    for (int c = 0; c < 8; c++) {
+      float rx, ry, rz;
+      mapped_posf(f.map, i + (c & 1), j + ((c >> 1) & 1), k + (c >> 2), rx, ry, rz);
+      rx -= q.cam[0]; ry -= q.cam[1]; rz -= q.cam[2];
+      const float nr = q.n[0] * rx + q.n[1] * ry + q.n[2] * rz;
+      const float t = __fdividef(q.c, nr);
+      const float sx = q.ax + t * (q.lxs[0] * rx + q.lxs[1] * ry + q.lxs[2] * rz);
+      const float sy = q.ay + t * (q.lys[0] * rx + q.lys[1] * ry + q.lys[2] * rz);
+      xlo = fminf(xlo, sx); xhi = fmaxf(xhi, sx);
+      ylo = fminf(ylo, sy); yhi = fmaxf(yhi, sy);
+      znear = fmaxf(znear, nr);
+      tlo = fminf(tlo, t); thi = fmaxf(thi, t);
+    }
+  } else {
+    float an[2], al[2], am[2], bn[2], bl[2], bm[2], cn[2], cl[2], cm[2];
 #pragma unroll
-  for (int c = 0; c < 8; c++) {
-    const int a = c & 1, b = (c >> 1) & 1, d = c >> 2;
-    const float nr = an[a] + bn[b] + cn[d];
-    const float t = __fdividef(q.c, nr);
-    const float sx = q.ax + t * (al[a] + bl[b] + cl[d]);
-    const float sy = q.ay + t * (am[a] + bm[b] + cm[d]);
-    xlo = fminf(xlo, sx); xhi = fmaxf(xhi, sx);
-    ylo = fminf(ylo, sy); yhi = fmaxf(yhi, sy);
-    znear = fmaxf(znear, nr);
-    tlo = fminf(tlo, t); thi = fmaxf(thi, t);
+    for (int e = 0; e < 2; e++) {
+      const float rx = __ldg(f.gf[0] + i + e) - q.cam[0];
+      const float ry = __ldg(f.gf[1] + j + e) - q.cam[1];
+      const float rz = __ldg(f.gf[2] + k + e) - q.cam[2];
+      an[e] = q.n[0] * rx; al[e] = q.lxs[0] * rx; am[e] = q.lys[0] * rx;
+      bn[e] = q.n[1] * ry; bl[e] = q.lxs[1] * ry; bm[e] = q.lys[1] * ry;
+      cn[e] = q.n[2] * rz; cl[e] = q.lxs[2] * rz; cm[e] = q.lys[2] * rz;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int a = c & 1, b = (c >> 1) & 1, d = c >> 2;
+      const float nr = an[a] + bn[b] + cn[d];
+      const float t = __fdividef(q.c, nr);
+      const float sx = q.ax + t * (al[a] + bl[b] + cl[d]);
+      const float sy = q.ay + t * (am[a] + bm[b] + cm[d]);
+      xlo = fminf(xlo, sx); xhi = fmaxf(xhi, sx);
+      ylo = fminf(ylo, sy); yhi = fmaxf(yhi, sy);
+      znear = fmaxf(znear, nr);
+      tlo = fminf(tlo, t); thi = fmaxf(thi, t);
+    }
   }
   /* every corner strictly beyond the screen plane as seen from the camera (project.c:44-46 accepts 0 < t < 1;
      then all n.ray share the sign of c and the cube projects inside the hull of its corners), else the
@@ -464,6 +485,7 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
  * stays below 0.01 pixel on screens up to 2^20 pixels wide; 0.05 pixel is added on top.  Anything that
  * does not fit these assumptions (ferr > 0.02, vertices near the screen plane, NaN) keeps the triangle.
  */
+template <bool MAPPED>
 __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsigned long long entry, const unsigned int s,
                                                 const Pixel *__restrict__ canvas) {
   const CullCam &q = p.cull;
@@ -486,8 +508,15 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsi
     /* a vertex that may sit within 1e-5 of a cube corner: the triangle may have collapsed to a point, which the
        reference draws as its whole +-1 pixel box (see cube_hidden); leave those to the exact path */
     if (!(fr - ferr > 1.e-5f && fr + ferr < 0.99999f)) return false;
-    const float x0 = __ldg(f.gf[0] + i + (tail & 1u)), y0 = __ldg(f.gf[1] + j + ((tail >> 1) & 1u)), z0 = __ldg(f.gf[2] + k + (tail >> 2));
-    const float ex = __ldg(f.gf[0] + i + (head & 1u)) - x0, ey = __ldg(f.gf[1] + j + ((head >> 1) & 1u)) - y0, ez = __ldg(f.gf[2] + k + (head >> 2)) - z0;
+    float x0, y0, z0, ex, ey, ez;
+    if (MAPPED && nullptr != f.map) {
+      mapped_posf(f.map, i + (tail & 1u), j + ((tail >> 1) & 1u), k + (tail >> 2), x0, y0, z0);
+      mapped_posf(f.map, i + (head & 1u), j + ((head >> 1) & 1u), k + (head >> 2), ex, ey, ez);
+      ex -= x0; ey -= y0; ez -= z0;
+    } else {
+      x0 = __ldg(f.gf[0] + i + (tail & 1u)); y0 = __ldg(f.gf[1] + j + ((tail >> 1) & 1u)); z0 = __ldg(f.gf[2] + k + (tail >> 2));
+      ex = __ldg(f.gf[0] + i + (head & 1u)) - x0; ey = __ldg(f.gf[1] + j + ((head >> 1) & 1u)) - y0; ez = __ldg(f.gf[2] + k + (head >> 2)) - z0;
+    }
     const float rx = x0 + fr * ex - q.cam[0], ry = y0 + fr * ey - q.cam[1], rz = z0 + fr * ez - q.cam[2];
     const float nr = q.n[0] * rx + q.n[1] * ry + q.n[2] * rz;
     const float t = __fdividef(q.c, nr);
@@ -515,7 +544,7 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsi
 #define C3D_TRI_ENTRY(q) ((q) & 0x0fffffffffffffffull)
 #define C3D_TRI_INDEX(q) ((unsigned int)((q) >> 60))
 
-template <int MINB>
+template <int MINB, bool MAPPED>
 __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ list,
                                                      const unsigned long long *__restrict__ count, const unsigned long long capacity,
                                                      Pixel *__restrict__ canvas, unsigned long long *__restrict__ culled,
@@ -538,7 +567,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
     if (base + lane < n) {
       entry = __ldg(list + base + lane);
       ntri = __ldg(p.tab.count + C3D_ENTRY_CODE(entry));
-      if (p.cull.enabled && cube_hidden(p, entry, canvas, hiz)) ntri = 0u;
+      if (p.cull.enabled && cube_hidden<MAPPED>(p, entry, canvas, hiz)) ntri = 0u;
     }
     const unsigned int alive = __ballot_sync(C3D_FULL_MASK, ntri > 0u);
     hidden_total += __popc(__ballot_sync(C3D_FULL_MASK, base + lane < n)) - __popc(alive);
@@ -570,7 +599,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
         const unsigned long long e = s_entry[wid][src];
         const unsigned int s = t0 + lane - s_first[wid][src];
         mine = C3D_TRI_PACK(e, s);
-        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden(p, e, s, canvas));
+        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden<MAPPED>(p, e, s, canvas));
       }
       const unsigned int kept = __ballot_sync(C3D_FULL_MASK, keep);
       hidden_tris += __popc(__ballot_sync(C3D_FULL_MASK, t0 + lane < total)) - __popc(kept);
@@ -585,14 +614,14 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
         if (lane + 32u < queued) s_queue[wid][lane] = rest;
         queued -= 32u;
         __syncwarp();
-        raster_triangle(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), canvas);
+        raster_triangle<MAPPED>(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), canvas);
       }
     }
   }
   __syncwarp();
   if (lane < queued) {
     const unsigned long long q = s_queue[wid][lane];
-    raster_triangle(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), canvas);
+    raster_triangle<MAPPED>(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), canvas);
   }
   if (0u == lane && nullptr != culled) {
     if (hidden_total > 0u) atomicAdd(culled, (unsigned long long)hidden_total);
@@ -613,10 +642,19 @@ extern "C" int c3d_k_raster(const FrameParams *p, const unsigned long long *list
   HiZ hiz;
   hiz.tile = hiz_tiles;
   hiz.tw = (int)((p->cam.w + C3D_HIZ_TILE - 1) / C3D_HIZ_TILE);
-  if (occ >= 8) k_raster<8><<<sm_count * 16, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end);
-  else if (occ >= 6) k_raster<6><<<sm_count * 12, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end);
-  else if (occ >= 5) k_raster<5><<<sm_count * 10, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end);
-  else k_raster<4><<<sm_count * 8, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end);
+  /* the converter-table branches are compiled out unless an object of this frame has a tabulated converter */
+  bool mapped = false;
+  for (unsigned int n = 0; n < p->ncontours; n++) mapped = mapped || (nullptr != p->view[n].map);
+#define C3D_RASTER_LAUNCH(MINB, PER_SM) \
+  do { \
+    if (mapped) k_raster<MINB, true><<<sm_count * PER_SM, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end); \
+    else k_raster<MINB, false><<<sm_count * PER_SM, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end); \
+  } while (0)
+  if (occ >= 8) C3D_RASTER_LAUNCH(8, 16);
+  else if (occ >= 6) C3D_RASTER_LAUNCH(6, 12);
+  else if (occ >= 5) C3D_RASTER_LAUNCH(5, 10);
+  else C3D_RASTER_LAUNCH(4, 8);
+#undef C3D_RASTER_LAUNCH
   return (int)cudaGetLastError();
 }
 
@@ -676,8 +714,14 @@ __global__ void __launch_bounds__(128) k_lines(const Cam cam, const LineDev *__r
   if (seg >= ln.nsegments) return;
   /* s = head + n * delta, e = head + (n + 1) * delta (line.c:157-158) */
   const V3 e0 = v_of(ln.e0), dl = v_of(ln.delta);
-  const V3 ps = v_add(e0, v_mul((double)seg, dl));
-  const V3 pe = v_add(e0, v_mul((double)(seg + 1ull), dl));
+  V3 ps, pe;
+  if (nullptr != ln.points) {       /* converted on the host with the caller's function (line.c:39-40) */
+    ps = V3{__ldg(ln.points + 3ull * seg), __ldg(ln.points + 3ull * seg + 1ull), __ldg(ln.points + 3ull * seg + 2ull)};
+    pe = V3{__ldg(ln.points + 3ull * seg + 3ull), __ldg(ln.points + 3ull * seg + 4ull), __ldg(ln.points + 3ull * seg + 5ull)};
+  } else {
+    ps = v_add(e0, v_mul((double)seg, dl));
+    pe = v_add(e0, v_mul((double)(seg + 1ull), dl));
+  }
   V3 p0, p1;
   if (!project(cam, ps, p0)) return;
   if (!project(cam, pe, p1)) return;

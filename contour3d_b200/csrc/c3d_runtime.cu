@@ -141,8 +141,10 @@ struct c3d_context {
   FieldView *views_dev;
   LineDev *lines_dev;
   size_t lines_cap;
-  double *grids_dev;
+  double *grids_dev;             /* stage-level entry points: one view's grid coordinates */
   size_t grids_cap;
+  char *arena_dev, *arena_host;  /* per-frame descriptors: converter maps, lines, grid coordinates, converter tables (device; pinned staging of the small part) */
+  size_t arena_cap, arena_host_cap;
   void *halo_buf;
   size_t halo_cap;
   cudaEvent_t ev[EV_COUNT];
@@ -248,7 +250,8 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   if (ctx->ppm_host) cudaFreeHost(ctx->ppm_host);
   cudaFree(ctx->list); cudaFree(ctx->records); cudaFree(ctx->tile_cursor); cudaFree(ctx->bucket_hist); cudaFree(ctx->bucket_cursors); cudaFree(ctx->counts_dev);
   if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
-  cudaFree(ctx->views_dev); cudaFree(ctx->lines_dev); cudaFree(ctx->grids_dev); cudaFree(ctx->halo_buf);
+  cudaFree(ctx->views_dev); cudaFree(ctx->lines_dev); cudaFree(ctx->grids_dev); cudaFree(ctx->halo_buf); cudaFree(ctx->arena_dev);
+  if (ctx->arena_host) cudaFreeHost(ctx->arena_host);
   for (int e = 0; e < EV_COUNT; e++) cudaEventDestroy(ctx->ev[e]);
   for (int e = 0; e <= C3D_MAX_OBJECTS; e++) cudaEventDestroy(ctx->ev_sweep[e]);
   for (int e = 0; e < 2 * C3D_MAX_OBJECTS; e++) cudaEventDestroy(ctx->ev_upload[e]);
@@ -530,9 +533,130 @@ static int make_view(c3d_context *ctx, const c3d_field *f, const double *const g
     atf += f->ext[d];
   }
   LAUNCH_OK(c3d_k_to_float(grid_slot, (float *)(grid_slot + total), total, ctx->stream));
+  v->map = NULL;
   v->thr = threshold;
   v->thr_ge = smallest_float_above(threshold);
   v->color[0] = color[0]; v->color[1] = color[1]; v->color[2] = color[2];
+  return 0;
+}
+
+static size_t round_up(const size_t v, const size_t a) { return (v + a - 1) / a * a; }
+
+/* entries of the converter table of component c (c3d_positions_t, include/contour3d_b200.h) */
+static size_t table_length(const c3d_field *f, const c3d_positions_t *pos, const int c) {
+  size_t len = 1;
+  for (int a = 0; a < 3; a++) len += (f->ext[a] - 1) * pos->stride[c][a];
+  return len;
+}
+
+/*
+ * Everything the kernels read besides the arrays, in ONE device arena filled with as few copies as possible
+ * (a dozen small pageable copies cost more host time than the clear of a 4K canvas):
+ *   [PosMap x nc][LineDev x nl] [doubles: grid coordinates of every object | converter tables | converted line points]
+ *   [floats: the same grid coordinates and tables rounded, for the visibility pre-tests]
+ * The maps, lines and grid coordinates are staged in pinned memory and travel in one copy; tables and line points
+ * (arbitrarily large, caller-owned) are copied from where they lie.
+ */
+static int stage_frame(c3d_context *ctx, const size_t nc, const c3d_contour_t *contours, const size_t nl, const c3d_line_t *lines,
+                       std::vector<LineDev> &hl, FieldView *views, const LineDev **lines_dev) {
+  cudaStream_t s = ctx->stream;
+  const size_t maps_bytes = round_up(nc * sizeof(PosMap), 256), lines_bytes = round_up(nl * sizeof(LineDev), 256);
+  size_t grid_doubles = 0, table_doubles = 0, point_doubles = 0;
+  for (size_t n = 0; n < nc; n++) {
+    const c3d_field *f = contours[n].field;
+    for (int d = 0; d < 3; d++) {
+      if ((long long)f->ext[d] - 1 > C3D_MAX_AXIS) return c3d_error("extended array too large in direction %d (%zu points)", d, f->ext[d]);
+      if (NULL == contours[n].grids[d]) return c3d_error("grid coordinates of direction %d are missing", d);
+    }
+    grid_doubles += f->ext[0] + f->ext[1] + f->ext[2];
+    if (NULL != contours[n].positions) {
+      for (int c = 0; c < 3; c++) {
+        if (NULL == contours[n].positions->table[c]) return c3d_error("contour object %zu: converter table %d is missing", n, c);
+        table_doubles += table_length(f, contours[n].positions, c);
+      }
+    }
+  }
+  for (size_t n = 0; n < nl; n++) {
+    if (NULL != lines[n].points) point_doubles += 3 * lines[n].nitems;
+  }
+  const size_t doubles_at = maps_bytes + lines_bytes;
+  const size_t floats_at = round_up(doubles_at + (grid_doubles + table_doubles + point_doubles) * sizeof(double), 256);
+  const size_t total = floats_at + (grid_doubles + table_doubles) * sizeof(float) + 256;
+  const size_t staged = doubles_at + grid_doubles * sizeof(double);
+  if (0 != ensure_bytes((void **)&ctx->arena_dev, &ctx->arena_cap, total)) return 1;
+  if (staged > ctx->arena_host_cap) {
+    if (ctx->arena_host) cudaFreeHost(ctx->arena_host);
+    ctx->arena_host = NULL;
+    ctx->arena_host_cap = 0;
+    CUDA_OK(cudaMallocHost(&ctx->arena_host, staged + 4096));
+    ctx->arena_host_cap = staged + 4096;
+  }
+  PosMap *maps_host = (PosMap *)ctx->arena_host;
+  PosMap *maps_dev = (PosMap *)ctx->arena_dev;
+  double *dbl_host = (double *)(ctx->arena_host + doubles_at);
+  double *dbl_dev = (double *)(ctx->arena_dev + doubles_at);
+  float *flt_dev = (float *)(ctx->arena_dev + floats_at);
+  size_t at = 0, tab_at = grid_doubles;
+  for (size_t n = 0; n < nc; n++) {
+    const c3d_field *f = contours[n].field;
+    FieldView *v = &views[n];
+    v->data = f->data;
+    v->elem_bytes = f->elem_bytes;
+    for (int d = 0; d < 3; d++) v->n[d] = (long long)f->ext[d];
+    v->sy = (long long)f->ext[0];
+    v->sz = (long long)(f->ext[0] * f->ext[1]);
+    for (int d = 0; d < 3; d++) {
+      memcpy(dbl_host + at, contours[n].grids[d] + f->ext_off[d], f->ext[d] * sizeof(double));
+      v->g[d] = dbl_dev + at;
+      v->gf[d] = flt_dev + at;
+      at += f->ext[d];
+    }
+    v->map = NULL;
+    if (NULL != contours[n].positions) {
+      const c3d_positions_t *pos = contours[n].positions;
+      PosMap *m = &maps_host[n];
+      for (int c = 0; c < 3; c++) {
+        const size_t len = table_length(f, pos, c);
+        CUDA_OK(cudaMemcpyAsync(dbl_dev + tab_at, pos->table[c], len * sizeof(double), cudaMemcpyHostToDevice, s));
+        m->pos[c] = dbl_dev + tab_at;
+        m->posf[c] = flt_dev + tab_at;
+        for (int a = 0; a < 3; a++) m->ps[c][a] = (long long)pos->stride[c][a];
+        tab_at += len;
+      }
+      v->map = &maps_dev[n];
+    }
+    v->thr = contours[n].threshold;
+    v->thr_ge = smallest_float_above(contours[n].threshold);
+    v->color[0] = contours[n].color[0]; v->color[1] = contours[n].color[1]; v->color[2] = contours[n].color[2];
+  }
+  /* lines: deltas = (1 / (npoints - 1)) * (tail - head), line.c:138-140 */
+  LineDev *lines_host = (LineDev *)(ctx->arena_host + maps_bytes);
+  unsigned long long first = 0;
+  size_t pts_at = grid_doubles + table_doubles;
+  for (size_t n = 0; n < nl; n++) {
+    const c3d_line_t *l = &lines[n];
+    if (l->nitems < 2) return c3d_error("give more than two points to draw a line, received %zu", l->nitems);
+    const double inv = 1. / (double)(l->nitems - 1);
+    for (int d = 0; d < 3; d++) {
+      hl[n].e0[d] = l->edges[0][d];
+      hl[n].delta[d] = inv * (l->edges[1][d] - l->edges[0][d]);
+    }
+    hl[n].half_width_sq = pow(0.5 * l->width, 2.);
+    hl[n].points = NULL;
+    if (NULL != l->points) {
+      CUDA_OK(cudaMemcpyAsync(dbl_dev + pts_at, l->points, 3 * l->nitems * sizeof(double), cudaMemcpyHostToDevice, s));
+      hl[n].points = dbl_dev + pts_at;
+      pts_at += 3 * l->nitems;
+    }
+    hl[n].first_segment = first;
+    hl[n].nsegments = l->nitems - 1;
+    hl[n].color[0] = l->color[0]; hl[n].color[1] = l->color[1]; hl[n].color[2] = l->color[2];
+    first += l->nitems - 1;
+    lines_host[n] = hl[n];
+  }
+  *lines_dev = (const LineDev *)(ctx->arena_dev + maps_bytes);
+  if (staged > 0) CUDA_OK(cudaMemcpyAsync(ctx->arena_dev, ctx->arena_host, staged, cudaMemcpyHostToDevice, s));
+  LAUNCH_OK(c3d_k_to_float(dbl_dev, flt_dev, grid_doubles + table_doubles, s));
   return 0;
 }
 
@@ -673,16 +797,6 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_HALO], s));
   /* descriptors */
-  size_t grid_elems = 0;
-  for (size_t n = 0; n < nc; n++) {
-    const c3d_field *f = contours[n].field;
-    grid_elems += grid_slot_doubles(f);
-  }
-  {
-    size_t cap = ctx->grids_cap * sizeof(double);
-    if (0 != ensure_bytes((void **)&ctx->grids_dev, &cap, (grid_elems + 8) * sizeof(double))) return 1;
-    ctx->grids_cap = cap / sizeof(double);
-  }
   FrameParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.cam = cam;
@@ -694,43 +808,9 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   fp.pyf = fp.pxf + scene->width;
   fp.ncontours = (unsigned int)nc;
   FieldView *views = fp.view;
-  {
-    double *slot = ctx->grids_dev;
-    for (size_t n = 0; n < nc; n++) {
-      const c3d_field *f = contours[n].field;
-      for (int d = 0; d < 3; d++) {
-        if ((long long)f->ext[d] - 1 > C3D_MAX_AXIS) return c3d_error("extended array too large in direction %d (%zu points)", d, f->ext[d]);
-      }
-      if (0 != make_view(ctx, f, contours[n].grids, contours[n].threshold, contours[n].color, slot, &views[n])) return 1;
-      slot += grid_slot_doubles(f);
-    }
-  }
   std::vector<LineDev> hl(nl);
-  {
-    unsigned long long first = 0;
-    for (size_t n = 0; n < nl; n++) {
-      const c3d_line_t *l = &lines[n];
-      if (l->nitems < 2) return c3d_error("give more than two points to draw a line, received %zu", l->nitems);
-      /* deltas = (1 / (npoints - 1)) * (tail - head), line.c:138-140 */
-      const double inv = 1. / (double)(l->nitems - 1);
-      for (int d = 0; d < 3; d++) {
-        hl[n].e0[d] = l->edges[0][d];
-        hl[n].delta[d] = inv * (l->edges[1][d] - l->edges[0][d]);
-      }
-      hl[n].half_width_sq = pow(0.5 * l->width, 2.);
-      hl[n].first_segment = first;
-      hl[n].nsegments = l->nitems - 1;
-      hl[n].color[0] = l->color[0]; hl[n].color[1] = l->color[1]; hl[n].color[2] = l->color[2];
-      first += l->nitems - 1;
-    }
-    if (nl > ctx->lines_cap) {
-      cudaFree(ctx->lines_dev);
-      ctx->lines_dev = NULL;
-      CUDA_OK(cudaMalloc(&ctx->lines_dev, nl * sizeof(LineDev)));
-      ctx->lines_cap = nl;
-    }
-    if (nl > 0) CUDA_OK(cudaMemcpyAsync(ctx->lines_dev, hl.data(), nl * sizeof(LineDev), cudaMemcpyHostToDevice, s));
-  }
+  const LineDev *lines_dev = NULL;
+  if (0 != stage_frame(ctx, nc, contours, nl, lines, hl, views, &lines_dev)) return 1;
   /* work buffers of the frame: patch records from the tiled sweeps, then one list entry per cut cube */
   if (nc > 0 && 0 == ctx->list_cap) {
     size_t want = 0;
@@ -811,6 +891,27 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     double near_depth = -DBL_MAX, far_depth = DBL_MAX;
     for (size_t n = 0; n < nc; n++) {
       const c3d_field *f = contours[n].field;
+      if (NULL != contours[n].positions) {
+        /* converted coordinates: bound each component by the extremes of its table (a box around the mapped block) */
+        double lo = 0., hi = 0.;
+        for (int c = 0; c < 3; c++) {
+          const size_t len = table_length(f, contours[n].positions, c);
+          const double *tab = contours[n].positions->table[c];
+          double tmin = DBL_MAX, tmax = -DBL_MAX;
+          for (size_t q = 0; q < len; q++) {
+            if (tab[q] < tmin) tmin = tab[q];
+            if (tab[q] > tmax) tmax = tab[q];
+          }
+          const double a = cam.normal[c] * (tmin - cam.cam[c]), b = cam.normal[c] * (tmax - cam.cam[c]);
+          lo += std::min(a, b);
+          hi += std::max(a, b);
+        }
+        if (hi >= lo) {         /* NaN-free */
+          near_depth = std::max(near_depth, hi);
+          far_depth = std::min(far_depth, lo);
+        }
+        continue;
+      }
       for (int c = 0; c < 8; c++) {
         double depth = 0.;
         for (int d = 0; d < 3; d++) {
@@ -851,7 +952,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_RASTER], s));
   /* 3. lines: drawn after the contours in the reference (main.c:119-129); their keys are larger, so they win ties */
-  LAUNCH_OK(c3d_k_lines(&cam, ctx->lines_dev, hl.data(), nl, nc, ctx->canvas, s));
+  LAUNCH_OK(c3d_k_lines(&cam, lines_dev, hl.data(), nl, nc, ctx->canvas, s));
   if (nl > 0) launches += 1;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_LINES], s));
   CUDA_OK(cudaEventRecord(ctx->ev[EV_RESOLVE], s));
@@ -865,7 +966,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
   /* 5. shade only what survived */
-  LAUNCH_OK(c3d_k_shade(&fp, ctx->lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, &ctx->shade,
+  LAUNCH_OK(c3d_k_shade(&fp, lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, &ctx->shade,
                         ctx->counts_dev + CNT_SHADE_SPILL, ctx->sm_count, s));
   launches += 4;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));

@@ -140,6 +140,14 @@ __device__ __forceinline__ V3 face_term(const FrameParams &p, const unsigned int
                                         const unsigned int code, const unsigned int s) {
   const FieldView &f = p.view[obj];
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
+  if (nullptr != f.map) {      /* tabulated converter: corner positions come from the tables, one vertex at a time */
+    V3 v[3], fn;
+    double area;
+#pragma unroll
+    for (int m = 0; m < 3; m++) v[m] = cut_edge_global(f, i, j, k, f.thr, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+    face_normal(v, fn, area);
+    return v_mul(area, fn);
+  }
   return 4 == f.elem_bytes ? face_term_of<float>(f, pairs, i, j, k) : face_term_of<double>(f, pairs, i, j, k);
 }
 

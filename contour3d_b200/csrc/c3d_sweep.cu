@@ -418,9 +418,13 @@ struct DepthOrder {
 __device__ __forceinline__ unsigned int depth_bucket(const FrameParams &p, const DepthOrder &o, const unsigned int obj, const unsigned int x,
                                                      const unsigned int j, const unsigned int k) {
   const FieldView &f = p.view[obj];
-  const float rx = (float)__ldg(f.g[0] + x) - p.cull.cam[0];
-  const float ry = (float)__ldg(f.g[1] + j) - p.cull.cam[1];
-  const float rz = (float)__ldg(f.g[2] + k) - p.cull.cam[2];
+  float rx, ry, rz;
+  if (nullptr != f.map) {
+    mapped_posf(f.map, (long long)x, (long long)j, (long long)k, rx, ry, rz);
+  } else {
+    rx = (float)__ldg(f.g[0] + x); ry = (float)__ldg(f.g[1] + j); rz = (float)__ldg(f.g[2] + k);
+  }
+  rx -= p.cull.cam[0]; ry -= p.cull.cam[1]; rz -= p.cull.cam[2];
   const float nr = p.cull.n[0] * rx + p.cull.n[1] * ry + p.cull.n[2] * rz;
   const float b = (o.near_depth - nr) * o.scale;
   return (unsigned int)fminf(fmaxf(b, 0.f), (float)(C3D_DEPTH_BUCKETS - 1));    /* NaN -> 0 */

@@ -10,8 +10,11 @@
  *
  * Differences a caller can observe (all documented in DESIGN.md):
  *  - `array` may be a host or a device pointer;
- *  - `converter` must be the identity map (NULL is accepted as identity);
- *    anything else is rejected, there is no host fallback;
+ *  - `converter` is evaluated on the host, once per grid point at most, and
+ *    tabulated for the kernels (c3d_positions.c): any deterministic function
+ *    works as long as its tables fit CONTOUR3D_CONVERTER_MAX_BYTES (default
+ *    4 GiB; a function of all three coordinates in every component needs
+ *    24 bytes per point).  NULL is accepted as the identity;
  *  - arrays on Y/Z pencils (not x-fastest; the reference mis-indexes them,
  *    extend.c:199-208) and local extents too small to tessellate are rejected;
  *  - a process-wide context (stream, NCCL communicator, canvases) is created
@@ -141,14 +144,42 @@ static int acquire_field(const c3d_decomp_t *decomp, const size_t glsizes[CONTOU
   return 0;
 }
 
-static int is_identity(contour3d_vector_t (*converter)(const contour3d_vector_t), const double probes[][3], const size_t nprobes) {
-  if (NULL == converter) return 1;
-  for (size_t n = 0; n < nprobes; n++) {
-    const contour3d_vector_t in = {probes[n][0], probes[n][1], probes[n][2]};
-    const contour3d_vector_t out = converter(in);
-    if (0 != memcmp(&in, &out, sizeof(in))) return 0;
+/* the callback of include/contour3d.h:31-33 behind the plain-double signature of c3d_positions_probe */
+typedef struct { contour3d_vector_t (*fn)(const contour3d_vector_t); } converter_box_t;
+
+static void call_converter(const double in[3], double out[3], void *user) {
+  const converter_box_t *box = user;
+  const contour3d_vector_t arg = {in[0], in[1], in[2]};
+  const contour3d_vector_t res = box->fn(arg);
+  out[0] = res.x; out[1] = res.y; out[2] = res.z;
+}
+
+static size_t converter_max_bytes(void) {
+  const char *env = getenv("CONTOUR3D_CONVERTER_MAX_BYTES");
+  if (NULL != env && '\0' != *env) return (size_t)strtoull(env, NULL, 10);
+  return (size_t)4 << 30;
+}
+
+/* the points of a poly-line, converted: s_n = head + n * deltas (line.c:138-140,157-158; e_n == s_(n+1) bit for bit).
+   *points stays NULL when the converter leaves every point unchanged. */
+static int convert_line(const contour3d_line_obj_t *obj, double **points) {
+  *points = NULL;
+  if (NULL == obj->converter || obj->nitems < 2) return 0;
+  double *p = malloc(3 * obj->nitems * sizeof(double));
+  if (NULL == p) return log_error("out of host memory");
+  const double w = 1. / (obj->nitems - 1);
+  const contour3d_vector_t head = obj->edges[0];
+  const contour3d_vector_t deltas = {w * (obj->edges[1].x - head.x), w * (obj->edges[1].y - head.y), w * (obj->edges[1].z - head.z)};
+  int identity = 1;
+  for (size_t n = 0; n < obj->nitems; n++) {
+    const contour3d_vector_t s = {head.x + n * deltas.x, head.y + n * deltas.y, head.z + n * deltas.z};
+    const contour3d_vector_t c = obj->converter(s);
+    if (0 != memcmp(&s, &c, sizeof(s))) identity = 0;
+    p[3 * n + 0] = c.x; p[3 * n + 1] = c.y; p[3 * n + 2] = c.z;
   }
-  return 1;
+  if (identity) free(p);
+  else *points = p;
+  return 0;
 }
 
 int contour3d_execute (
@@ -170,7 +201,11 @@ int contour3d_execute (
   c3d_field_t *fields[MAX_OBJECTS] = {NULL};
   int cached[MAX_OBJECTS] = {0};
   c3d_contour_t contours[MAX_OBJECTS];
+  c3d_positions_t positions[MAX_OBJECTS];
+  int has_positions[MAX_OBJECTS] = {0};
+  converter_box_t boxes[MAX_OBJECTS];
   c3d_line_t *lines = NULL;
+  double **line_points = NULL;
   int status = 1;
   if (NULL == sdecomp_info || NULL == camera_position || NULL == light_direction || NULL == screen_sizes
       || NULL == screen_center || NULL == screen_local || NULL == bg_color || NULL == fname) {
@@ -199,16 +234,6 @@ int contour3d_execute (
     }
     if (NULL == obj->array || NULL == obj->grids[0] || NULL == obj->grids[1] || NULL == obj->grids[2]) {
       log_error("contour object %zu: array or grids missing", n);
-      goto done;
-    }
-    const double probes[4][3] = {
-      {obj->grids[0][0], obj->grids[1][0], obj->grids[2][0]},
-      {obj->grids[0][obj->glsizes[0] - 1], obj->grids[1][obj->glsizes[1] - 1], obj->grids[2][obj->glsizes[2] - 1]},
-      {obj->grids[0][obj->glsizes[0] / 2], obj->grids[1][obj->glsizes[1] / 3], obj->grids[2][obj->glsizes[2] / 5]},
-      {0.3183098861837907, -2.718281828459045, 1.4142135623730951},
-    };
-    if (!is_identity(obj->converter, probes, 4)) {
-      log_error("contour object %zu: a non-identity coordinate converter cannot be called from the device", n);
       goto done;
     }
     /* what contour/extend.c:160-181, 216-221 asks SimpleDecomp */
@@ -247,24 +272,46 @@ int contour3d_execute (
       contours[n].field = fields[n];
     }
     for (int d = 0; d < 3; d++) contours[n].grids[d] = obj->grids[d];
+    /* the coordinate converter, tabulated over the points of the extended local array (c3d_positions.c) */
+    contours[n].positions = NULL;
+    if (NULL != obj->converter) {
+      size_t reuse = n;
+      for (size_t m = 0; m < n; m++) {
+        if (contours[m].field == contours[n].field && contour3d_contour_objs[m].converter == obj->converter
+            && 0 == memcmp(contour3d_contour_objs[m].grids, obj->grids, sizeof(obj->grids))) {
+          reuse = m;
+          break;
+        }
+      }
+      if (reuse < n) {
+        contours[n].positions = contours[reuse].positions;
+      } else {
+        size_t ext[3], ext_off[3], mysizes[3], offsets[3];
+        int identity = 1;
+        if (0 != c3d_field_geometry(contours[n].field, ext, ext_off, mysizes, offsets)) goto done;
+        boxes[n].fn = obj->converter;
+        if (0 != c3d_positions_probe(call_converter, &boxes[n], obj->grids, ext_off, ext, converter_max_bytes(), &positions[n], &identity)) {
+          log_error("contour object %zu: the coordinate converter could not be tabulated", n);
+          goto done;
+        }
+        if (!identity) {
+          has_positions[n] = 1;
+          contours[n].positions = &positions[n];
+        }
+      }
+    }
     contours[n].threshold = obj->threshold;
     contours[n].color[0] = obj->color.r; contours[n].color[1] = obj->color.g; contours[n].color[2] = obj->color.b;
   }
   if (num_lines > 0) {
     lines = calloc(num_lines, sizeof(c3d_line_t));
-    if (NULL == lines) { log_error("out of host memory"); goto done; }
+    line_points = calloc(num_lines, sizeof(double *));
+    if (NULL == lines || NULL == line_points) { log_error("out of host memory"); goto done; }
   }
   for (size_t n = 0; n < num_lines; n++) {
     const contour3d_line_obj_t *obj = contour3d_line_objs + n;
-    const double probes[3][3] = {
-      {obj->edges[0].x, obj->edges[0].y, obj->edges[0].z},
-      {obj->edges[1].x, obj->edges[1].y, obj->edges[1].z},
-      {0.3183098861837907, -2.718281828459045, 1.4142135623730951},
-    };
-    if (!is_identity(obj->converter, probes, 3)) {
-      log_error("line object %zu: a non-identity coordinate converter cannot be called from the device", n);
-      goto done;
-    }
+    if (0 != convert_line(obj, &line_points[n])) goto done;
+    lines[n].points = line_points[n];
     lines[n].edges[0][0] = obj->edges[0].x; lines[n].edges[0][1] = obj->edges[0].y; lines[n].edges[0][2] = obj->edges[0].z;
     lines[n].edges[1][0] = obj->edges[1].x; lines[n].edges[1][1] = obj->edges[1].y; lines[n].edges[1][2] = obj->edges[1].z;
     lines[n].nitems = obj->nitems;
@@ -290,6 +337,11 @@ done:
               t.upload, t.sweep, t.expand, t.raster, t.shade, t.reduce, t.download, t.upload + t.total);
     }
   }
+  for (size_t n = 0; n < MAX_OBJECTS; n++) {
+    if (has_positions[n]) c3d_positions_free(&positions[n]);
+  }
+  for (size_t n = 0; NULL != line_points && n < num_lines; n++) free(line_points[n]);
+  free(line_points);
   free(lines);
   return status;
 }

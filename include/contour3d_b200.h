@@ -47,21 +47,34 @@ typedef struct {
   uint8_t bg[3];
 } c3d_scene_t;
 
-/* reference: contour3d_contour_obj_t (include/contour3d.h:22-40); the array is
-   a c3d_field_t, the converter is the identity */
+/* reference: the `converter` callback of a contour object (include/contour3d.h:31-33), which the reference calls
+   on every cube corner (triangulate.c:156-173).  Device code cannot call a host function, so the host tabulates it:
+   component c of the Cartesian position of point (i, j, k) of the field's EXTENDED local array (c3d_field_geometry)
+   is table[c][i * stride[c][0] + j * stride[c][1] + k * stride[c][2]]; stride 0 = independent of that direction.
+   contour3d_execute() builds these by probing the callback (c3d_positions_probe); the values are the callback's own,
+   so the geometry is bit-identical to the reference's whatever the function computes. */
+typedef struct {
+  const double *table[3];     /* HOST pointers */
+  size_t stride[3][3];
+} c3d_positions_t;
+
+/* reference: contour3d_contour_obj_t (include/contour3d.h:22-40); the array is a c3d_field_t */
 typedef struct {
   const c3d_field_t *field;
   const double *grids[3];     /* HOST pointers, global coordinates (glsizes[d] each) */
   double threshold;
   uint8_t color[3];
+  const c3d_positions_t *positions;   /* NULL: identity converter, positions are the grid coordinates themselves */
 } c3d_contour_t;
 
-/* reference: contour3d_line_obj_t (include/contour3d.h:42-56), identity converter */
+/* reference: contour3d_line_obj_t (include/contour3d.h:42-56) */
 typedef struct {
   double edges[2][3];
   size_t nitems;
   double width;
   uint8_t color[3];
+  const double *points;       /* NULL: identity converter; else HOST array of nitems x 3 doubles: converter(edges[0] + n * delta),
+                                 n = 0 .. nitems-1, delta as in line.c:138-140,157-158 (contour3d_execute fills it) */
 } c3d_line_t;
 
 /* same 208-byte record as the oracle's dump (oracle/c3d_oracle.h) */
@@ -162,6 +175,21 @@ int c3d_sweep(c3d_context_t *ctx, const c3d_field_t *field, double threshold, in
    sorted by (cube, tri).  Writes min(*count, capacity) records. */
 int c3d_tessellate(c3d_context_t *ctx, const c3d_field_t *field, const double *const grids[3], double threshold,
                    size_t capacity, c3d_triangle_t *host_out, uint64_t *count);
+
+/* ---- coordinate converters (host side, needs no device) ---- */
+
+/* the callback type of include/contour3d.h:31-33 / 49-51 on plain doubles: xyz in, xyz out */
+typedef void (*c3d_converter_fn)(const double in[3], double out[3], void *user);
+
+/* Tabulates `convert` over the grid points [offset[d], offset[d] + count[d]) of `grids` (global coordinates):
+   finds which output component depends on which direction (bitwise comparison over sample lines through the block),
+   fills one table per component of the smallest dimensionality that reproduces the function on a scattered
+   verification sample, and returns them in *out (malloc'ed: release with c3d_positions_free).  *identity = 1 and
+   out->table[] = NULL when the function returns its argument unchanged everywhere it was evaluated.
+   max_bytes bounds the total size of the tables (a full 3-D dependence costs 8 bytes x points per component). */
+int c3d_positions_probe(c3d_converter_fn convert, void *user, const double *const grids[3], const size_t offset[3],
+                        const size_t count[3], size_t max_bytes, c3d_positions_t *out, int *identity);
+void c3d_positions_free(c3d_positions_t *p);
 
 /* library / build information, e.g. "contour3d_b200 0.1 sm_100a" */
 const char *c3d_version(void);

@@ -242,6 +242,43 @@ def test_dropin_contour3d_execute_host_buffers(ctx, tmp_path):
     _assert_image(api.read_ppm(out), g["image"])
 
 
+@pytest.mark.parametrize("kind,name", [(1, "cylindrical"), (2, "stretched"), (3, "twisted")])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_dropin_coordinate_converter_matches_the_reference(ctx, tmp_path, kind, name, dtype):
+    """Non-identity `converter` callbacks (include/contour3d.h:31-33): the SAME C program on the public API
+    (c3d_case_main.c, converters built in) linked against the unmodified reference (CPU) and against the drop-in
+    (callback tabulated on the host, kernels on the GPU) must write the same PPM, byte for byte."""
+    import subprocess
+
+    from oracle import reference
+
+    if not reference.available():
+        pytest.skip("oracle/_ref not built")
+    n = 36
+    f = scenes.noise(n, seed=11 + kind).astype(dtype)
+    g = scenes.uniform_grids(n, n, n)
+    scene = scenes.scene(400, 225)
+    scene["converter"] = kind
+    contours = [dict(field=0, threshold=float(np.float32(-0.15)), color=(250, 200, 60)), dict(field=0, threshold=float(np.float32(0.2)), color=(60, 200, 250))]
+    case = str(tmp_path / f"{name}.bin")
+    casefile.write_case(case, scene, g, [f], contours, scenes.box_lines(nitems=24, width=3.0))
+    want_ppm, got_ppm = str(tmp_path / "ref.ppm"), str(tmp_path / "ours.ppm")
+    reference.run_case(case, want_ppm, ranks=2, dims=(1, 2, 1))
+    exe = os.path.join(os.path.dirname(api.__file__), "c3d_case")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT", "MASTER_ADDR")}
+    env["MINIMPI_NP"] = "1"
+    proc = subprocess.run([exe, case, got_ppm], env=env, capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout[-1000:] + proc.stderr[-2000:]
+    want, got = api.read_ppm(want_ppm), api.read_ppm(got_ppm)
+    assert (want != np.array(scene.get("bg", (0, 0, 0)), dtype=np.uint8)).any(), "the converted surface is off screen: the case tests nothing"
+    _assert_image(got, want)
+    # and it is not the identity image
+    scene["converter"] = 0
+    casefile.write_case(case, scene, g, [f], contours, scenes.box_lines(nitems=24, width=3.0))
+    reference.run_case(case, want_ppm, ranks=1)
+    assert (api.read_ppm(want_ppm) != want).any()
+
+
 def test_dropin_rejects_what_it_cannot_honour(ctx, tmp_path, capfd):
     g = load_golden("frame_gyroid32.npz")
     grids = [g["gx"], g["gy"], g["gz"]]

@@ -118,3 +118,36 @@ def test_minimpi_fork_mode_bcast_and_reduce(tmp_path):
         env.pop(k, None)
     out = subprocess.run([str(exe)], env=env, capture_output=True, text=True, check=True).stdout
     assert out.strip() == "ok 3"
+
+
+def test_converter_probe_finds_the_dependence_structure():
+    """c3d_positions_probe (host only): which output component depends on which direction, tables bit-equal to the function"""
+    import math
+
+    g = [np.linspace(-0.5, 0.5, 14), np.linspace(-0.5, 0.5, 11), np.linspace(-0.5, 0.5, 9)]
+    off, cnt = (2, 1, 0), (10, 9, 9)
+
+    def check(fn, want_strides):
+        ident, tabs, st = api.positions_probe(fn, g, off, cnt)
+        assert not ident
+        assert st == want_strides, st
+        rng = np.random.default_rng(0)
+        for _ in range(200):
+            i, j, k = (int(rng.integers(0, cnt[d])) for d in range(3))
+            want = fn(g[0][off[0] + i], g[1][off[1] + j], g[2][off[2] + k])
+            got = tuple(tabs[c][i * st[c][0] + j * st[c][1] + k * st[c][2]] for c in range(3))
+            assert got == tuple(float(v) for v in want)
+
+    assert api.positions_probe(lambda x, y, z: (x, y, z), g, off, cnt)[0]
+    check(lambda x, y, z: (1.5 * x, y - 0.2 * y * y, z + 1.0), [[1, 0, 0], [0, 1, 0], [0, 0, 1]])                     # separable
+    check(lambda r, t, z: ((0.75 + r) * math.cos(t), (0.75 + r) * math.sin(t), z), [[1, 10, 0], [1, 10, 0], [0, 0, 1]])  # cylindrical
+    check(lambda x, y, z: (x * math.cos(z) - y * math.sin(z), x * math.sin(z) + y * math.cos(z), z + 0.1 * x * y),
+          [[1, 10, 90], [1, 10, 90], [1, 10, 90]])                                                                    # twisted
+    check(lambda x, y, z: (0.25, y, z + x), [[0, 0, 0], [0, 1, 0], [1, 0, 10]])                                       # constant component
+
+
+def test_converter_probe_respects_the_memory_bound(capfd):
+    g = [np.linspace(0, 1, 20)] * 3
+    with pytest.raises(RuntimeError):
+        api.positions_probe(lambda x, y, z: (x + y * z, y, z), g, (0, 0, 0), (20, 20, 20), max_bytes=1000)
+    assert "CONTOUR3D_CONVERTER_MAX_BYTES" in capfd.readouterr().err

@@ -10,4 +10,4 @@ import json,sys
 d=json.loads(open('gpurun_out/${TAG}_bench.json').read().strip().splitlines()[-1])
 print('ms/step %.3f' % d['ms_per_step'], {k: round(v,3) for k,v in d['stages_ms'].items()}, 'spills', d['shade_spills'], 'roofline %.3f' % d['roofline']['frac'])
 "
-[ -n "$2" ] && bash tools/gpu_kernel_times.sh $TAG "$2" ${3:-0} ${4:-40}
+if [ -n "$2" ]; then bash tools/gpu_kernel_times.sh $TAG "$2" ${3:-0} ${4:-40}; fi
