@@ -70,6 +70,17 @@ class LineDesc(C.Structure):
                 ("points", C.POINTER(C.c_double))]
 
 
+def camera_from_angles(elevation, azimuth, roll=0.0, camera_distance=2.0, screen_distance=1.0, screen_width=16.0 / 9.0, screen_height=1.0) -> dict:
+    """c3d_camera_from_angles -> dict(camera, center, local_x, local_y) (the CameraAdjuster construction); host only"""
+    s = Scene()
+    fn = lib().c3d_camera_from_angles
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_double] * 7 + [C.POINTER(Scene)]
+    if 0 != fn(elevation, azimuth, roll, camera_distance, screen_distance, screen_width, screen_height, C.byref(s)):
+        raise ValueError("c3d_camera_from_angles: lengths must be positive")
+    return {k: tuple(getattr(s, k)) for k in ("camera", "center", "local_x", "local_y")}
+
+
 CONVERTER_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
 
 
@@ -172,7 +183,7 @@ _compat = None
 
 EXPORTS = [
     "c3d_nccl_unique_id", "c3d_context_create", "c3d_context_destroy", "c3d_context_device", "c3d_context_stream",
-    "c3d_context_synchronize", "c3d_positions_probe", "c3d_positions_free", "c3d_decomp_make", "c3d_decomp_local", "c3d_field_create", "c3d_field_destroy",
+    "c3d_context_synchronize", "c3d_positions_probe", "c3d_positions_free", "c3d_camera_from_angles", "c3d_decomp_make", "c3d_decomp_local", "c3d_field_create", "c3d_field_destroy",
     "c3d_field_upload", "c3d_field_geometry", "c3d_field_interior", "c3d_field_mark_dirty", "c3d_field_exchange",
     "c3d_field_download_ext", "c3d_field_synthesize", "c3d_frame_render", "c3d_frame_timings", "c3d_frame_canvas",
     "c3d_case_codes", "c3d_sweep", "c3d_tessellate", "c3d_version", "contour3d_execute",

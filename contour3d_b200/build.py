@@ -80,7 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 sys.stderr.write(p.stderr)
         objs.append(obj)
-    for name in ("contour3d_execute.c", "c3d_positions.c"):
+    for name in ("contour3d_execute.c", "c3d_positions.c", "c3d_camera.c"):
         src = os.path.join(CSRC, name)
         obj = os.path.join(OBJ, name[:-2] + ".o")
         if force or _newer(obj, [src] + headers):

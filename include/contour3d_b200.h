@@ -191,6 +191,16 @@ int c3d_positions_probe(c3d_converter_fn convert, void *user, const double *cons
                         const size_t count[3], size_t max_bytes, c3d_positions_t *out, int *identity);
 void c3d_positions_free(c3d_positions_t *p);
 
+/* ---- camera helper (host side) ---- */
+
+/* Fills camera, center, local_x, local_y of *scene from viewing angles in degrees, the way the reference's
+   CameraAdjuster tool does (CameraAdjuster/src/config.ts:140-192): camera at distance camera_distance from the origin,
+   tilted by elevation about x, turned by azimuth about z; screen vectors of lengths screen_width / screen_height with
+   the same rotations plus roll about the screen normal; screen centre on the origin-camera line at screen_distance.
+   light, width, height and bg are left as they are.  Returns non-zero on non-positive lengths. */
+int c3d_camera_from_angles(double elevation_deg, double azimuth_deg, double roll_deg, double camera_distance, double screen_distance,
+                           double screen_width, double screen_height, c3d_scene_t *scene);
+
 /* library / build information, e.g. "contour3d_b200 0.1 sm_100a" */
 const char *c3d_version(void);
 

@@ -151,3 +151,20 @@ def test_converter_probe_respects_the_memory_bound(capfd):
     with pytest.raises(RuntimeError):
         api.positions_probe(lambda x, y, z: (x + y * z, y, z), g, (0, 0, 0), (20, 20, 20), max_bytes=1000)
     assert "CONTOUR3D_CONVERTER_MAX_BYTES" in capfd.readouterr().err
+
+
+def test_camera_helper_reproduces_the_demo_camera():
+    """c3d_camera_from_angles follows CameraAdjuster/src/config.ts:140-192; elevation 60, azimuth 30, d = 2 is the camera
+    of the reference's demo (src/main.c: position (0.8660254, -1.5, 1.0), screen centre = position / 2)"""
+    c = api.camera_from_angles(60.0, 30.0, 0.0, camera_distance=2.0, screen_distance=1.0, screen_width=4.0 / 3.0, screen_height=1.0)
+    assert np.allclose(c["camera"], (0.8660254037844386, -1.5, 1.0), atol=1e-12)
+    assert np.allclose(c["center"], np.array(c["camera"]) / 2, atol=1e-15)
+    lx, ly, cam = (np.array(c[k]) for k in ("local_x", "local_y", "camera"))
+    assert abs(lx @ ly) < 1e-12 and abs(np.linalg.norm(lx) - 4.0 / 3.0) < 1e-12 and abs(np.linalg.norm(ly) - 1.0) < 1e-12
+    normal = np.cross(lx, ly) / np.linalg.norm(np.cross(lx, ly))
+    assert np.allclose(normal, cam / np.linalg.norm(cam), atol=1e-12)          # the screen faces the camera
+    assert abs(lx[2]) < 1e-12                                                  # no roll: the horizontal vector stays horizontal
+    rolled = api.camera_from_angles(60.0, 30.0, 90.0, 2.0, 1.0, 4.0 / 3.0, 1.0)
+    assert np.allclose(np.array(rolled["local_x"]) / (4.0 / 3.0), ly, atol=1e-12)
+    with pytest.raises(ValueError):
+        api.camera_from_angles(10.0, 10.0, camera_distance=0.0)
