@@ -328,13 +328,14 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
       unsigned int maybe = 0u;
       for (int dj = 0; dj <= nj; dj++) {
         const float py = __ldg(p.pyf + j0 + dj);
-        const float dy0 = py - fay[0], dy1 = py - fay[1], dy2 = py - fay[2];
+        /* row terms of the three edge functions; the fused form below has three roundings instead of four, within the same bound */
+        const float r0 = (py - fay[0]) * fex[0], r1 = (py - fay[1]) * fex[1], r2 = (py - fay[2]) * fex[2];
         unsigned int bit = 1u << (8 * dj);
         for (int di = 0; di <= ni; di++, bit <<= 1) {
           const float px = __ldg(p.pxf + i0 + di);
-          const float e0 = (px - fax[0]) * fey[0] - dy0 * fex[0];
-          const float e1 = (px - fax[1]) * fey[1] - dy1 * fex[1];
-          const float e2 = (px - fax[2]) * fey[2] - dy2 * fex[2];
+          const float e0 = __fmaf_rn(px - fax[0], fey[0], -r0);
+          const float e1 = __fmaf_rn(px - fax[1], fey[1], -r1);
+          const float e2 = __fmaf_rn(px - fax[2], fey[2], -r2);
           if (!(e0 < ntol[0] || e1 < ntol[1] || e2 < ntol[2])) maybe |= bit;
         }
       }
@@ -495,16 +496,27 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsi
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
   const long long base = k * f.sz + j * f.sy + i;
   const float thr = (float)f.thr;
+  /* the cube's six grid coordinates once, not per vertex (identity converter) */
+  float gx0 = 0.f, gx1 = 0.f, gy0 = 0.f, gy1 = 0.f, gz0 = 0.f, gz1 = 0.f;
+  if (!(MAPPED && nullptr != f.map)) {
+    gx0 = __ldg(f.gf[0] + i); gx1 = __ldg(f.gf[0] + i + 1);
+    gy0 = __ldg(f.gf[1] + j); gy1 = __ldg(f.gf[1] + j + 1);
+    gz0 = __ldg(f.gf[2] + k); gz1 = __ldg(f.gf[2] + k + 1);
+  }
   float xlo = 3.e38f, xhi = -3.e38f, ylo = 3.e38f, yhi = -3.e38f, znear = -3.e38f, zslack = 0.f;
+  /* fp32 with explicit fused multiply-adds (the translation unit is compiled with -fmad=false for the exact fp64 path;
+     here fewer roundings only help) and ONE reciprocal per vertex: rcp is within 1 ulp and the product adds half an ulp,
+     so the factor is off by < 2e-7 on top of the bound below -- covered by the extra 3e-7 in ferr */
 #pragma unroll 1
   for (int m = 0; m < 3; m++) {
     const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
-    const float v0 = (float)ld_value(f, base + (tail & 1u) + ((tail >> 1) & 1u) * f.sy + (tail >> 2) * f.sz);
-    const float v1 = (float)ld_value(f, base + (head & 1u) + ((head >> 1) & 1u) * f.sy + (head >> 2) * f.sz);
+    const float v0 = (float)ld_value(f, base + ((tail & 1u) + ((tail & 2u) ? f.sy : 0ll) + ((tail & 4u) ? f.sz : 0ll)));
+    const float v1 = (float)ld_value(f, base + ((head & 1u) + ((head & 2u) ? f.sy : 0ll) + ((head & 4u) ? f.sz : 0ll)));
     const float dv = v1 - v0;
-    const float ferr = 2.e-7f * (fabsf(thr) + fabsf(v0) + fabsf(v1)) / fabsf(dv);
+    const float inv = __frcp_rn(dv);
+    const float ferr = 2.00002e-7f * (fabsf(thr) + fabsf(v0) + fabsf(v1)) * fabsf(inv) + 3.e-7f;
     if (!(ferr < 0.02f) || !(fabsf(dv) > 1.e-7f)) return false;    /* incl. the |dv| < 1e-8 branch of triangulate.c:62-71 */
-    const float fr = fminf(fmaxf((thr - v0) / dv, 0.f), 1.f);
+    const float fr = fminf(fmaxf((thr - v0) * inv, 0.f), 1.f);
     /* a vertex that may sit within 1e-5 of a cube corner: the triangle may have collapsed to a point, which the
        reference draws as its whole +-1 pixel box (see cube_hidden); leave those to the exact path */
     if (!(fr - ferr > 1.e-5f && fr + ferr < 0.99999f)) return false;
@@ -514,21 +526,22 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsi
       mapped_posf(f.map, i + (head & 1u), j + ((head >> 1) & 1u), k + (head >> 2), ex, ey, ez);
       ex -= x0; ey -= y0; ez -= z0;
     } else {
-      x0 = __ldg(f.gf[0] + i + (tail & 1u)); y0 = __ldg(f.gf[1] + j + ((tail >> 1) & 1u)); z0 = __ldg(f.gf[2] + k + (tail >> 2));
-      ex = __ldg(f.gf[0] + i + (head & 1u)) - x0; ey = __ldg(f.gf[1] + j + ((head >> 1) & 1u)) - y0; ez = __ldg(f.gf[2] + k + (head >> 2)) - z0;
+      x0 = (tail & 1u) ? gx1 : gx0; y0 = (tail & 2u) ? gy1 : gy0; z0 = (tail & 4u) ? gz1 : gz0;
+      ex = ((head & 1u) ? gx1 : gx0) - x0; ey = ((head & 2u) ? gy1 : gy0) - y0; ez = ((head & 4u) ? gz1 : gz0) - z0;
     }
-    const float rx = x0 + fr * ex - q.cam[0], ry = y0 + fr * ey - q.cam[1], rz = z0 + fr * ez - q.cam[2];
-    const float nr = q.n[0] * rx + q.n[1] * ry + q.n[2] * rz;
+    const float rx = __fmaf_rn(fr, ex, x0) - q.cam[0], ry = __fmaf_rn(fr, ey, y0) - q.cam[1], rz = __fmaf_rn(fr, ez, z0) - q.cam[2];
+    const float nr = __fmaf_rn(q.n[2], rz, __fmaf_rn(q.n[1], ry, q.n[0] * rx));
     const float t = __fdividef(q.c, nr);
     if (!(t > 1.e-4f && t < 0.9999f)) return false;
-    const float rl = rx * q.lxs[0] + ry * q.lxs[1] + rz * q.lxs[2];
-    const float rm = rx * q.lys[0] + ry * q.lys[1] + rz * q.lys[2];
+    const float rl = __fmaf_rn(rz, q.lxs[2], __fmaf_rn(ry, q.lxs[1], rx * q.lxs[0]));
+    const float rm = __fmaf_rn(rz, q.lys[2], __fmaf_rn(ry, q.lys[1], rx * q.lys[0]));
     /* pixel coordinates: pixel i has its centre at X = i */
-    const float X = (0.5f + q.ax + t * rl) * q.W - 0.5f, Y = (0.5f + q.ay + t * rm) * q.H - 0.5f;
+    const float X = __fmaf_rn(__fmaf_rn(t, rl, 0.5f + q.ax), q.W, -0.5f), Y = __fmaf_rn(__fmaf_rn(t, rm, 0.5f + q.ay), q.H, -0.5f);
     const float span = ferr * (fabsf(ex) + fabsf(ey) + fabsf(ez));
     const float tc = t * q.inv_abs_c;
-    const float mx = 0.05f + 1.5f * span * t * q.W * (q.lx_norm + fabsf(rl) * tc);
-    const float my = 0.05f + 1.5f * span * t * q.H * (q.ly_norm + fabsf(rm) * tc);
+    const float st = 1.5f * span * t;
+    const float mx = __fmaf_rn(st * q.W, __fmaf_rn(fabsf(rl), tc, q.lx_norm), 0.05f);
+    const float my = __fmaf_rn(st * q.H, __fmaf_rn(fabsf(rm), tc, q.ly_norm), 0.05f);
     xlo = fminf(xlo, X - mx); xhi = fmaxf(xhi, X + mx);
     ylo = fminf(ylo, Y - my); yhi = fmaxf(yhi, Y + my);
     znear = fmaxf(znear, nr);
