@@ -37,11 +37,18 @@ __global__ void __launch_bounds__(256) k_shade_select(const __grid_constant__ Fr
                                                       const Pixel *__restrict__ canvas, const unsigned long long *__restrict__ depth_global,
                                                       unsigned int *__restrict__ rgba, const size_t npix, unsigned int *__restrict__ work,
                                                       unsigned int *__restrict__ nwork) {
+  /* a warp takes a tile of 8 x 4 pixels, so that the work list is ordered by screen tiles: the 32 pixels a warp of
+     k_shade_setup handles then share cubes, vertices and cache lines (rows of 3840 pixels do not) */
   const unsigned int lane = threadIdx.x & 31u;
-  for (size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; base < npix; base += (size_t)gridDim.x * blockDim.x) {
-    const size_t pix = base + lane;
+  const unsigned int w = (unsigned int)p.cam.w, h = (unsigned int)p.cam.h;
+  const unsigned int tiles_x = (w + 7u) >> 3, tiles_y = (h + 3u) >> 2;
+  const unsigned int ntiles = tiles_x * tiles_y;
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned int tile = warp; tile < ntiles; tile += nwarps) {
+    const unsigned int pi = (tile % tiles_x) * 8u + (lane & 7u), pj = (tile / tiles_x) * 4u + (lane >> 3);
+    const size_t pix = (size_t)pj * w + pi;
     bool mine = false;
-    if (pix < npix) {
+    if (pi < w && pj < h && pix < npix) {
       const ulonglong2 px = *reinterpret_cast<const ulonglong2 *>(canvas + pix);
       unsigned int out = 0u;     /* 0 = nothing from this rank: background, or another rank is nearer */
       if (0ull != px.y && (nullptr == depth_global || px.x == depth_global[pix])) {
