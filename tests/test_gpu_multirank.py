@@ -28,3 +28,38 @@ def test_multi_gpu_image_equals_single_rank_oracle(world, dims):
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
     assert "ok" in proc.stdout
+
+
+@pytest.mark.parametrize("kind,dims", [(0, (1, 1, 2)), (1, (1, 2, 1)), (3, (1, 1, 2))])
+def test_dropin_program_two_ranks_matches_the_reference(tmp_path, kind, dims):
+    """The drop-in exactly as a solver would use it: a C program on the public API (c3d_case_main.c), two MPI ranks (the
+    fork-mode stand-in, compat/minimpi), one GPU each, NCCL id broadcast with MPI_Bcast inside contour3d_execute, SimpleDecomp
+    getters for the pencils -- against the same program linked with the unmodified reference on the CPU.  kind != 0:
+    non-identity coordinate converter, tabulated per rank over its own extended block."""
+    import numpy as np
+
+    from contour3d_b200 import api, casefile, scenes
+    from oracle import reference
+
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    if not reference.available():
+        pytest.skip("oracle/_ref not built")
+    n = 40
+    f = scenes.noise(n, seed=5 + kind)
+    g = scenes.uniform_grids(n, n, n)
+    scene = scenes.scene(400, 225)
+    scene["converter"] = kind
+    contours = [dict(field=0, threshold=float(np.float32(-0.1)), color=(250, 200, 60)), dict(field=0, threshold=float(np.float32(0.25)), color=(60, 200, 250))]
+    case = str(tmp_path / "case.bin")
+    casefile.write_case(case, scene, g, [f], contours, scenes.box_lines(nitems=24, width=3.0))
+    want_ppm, got_ppm = str(tmp_path / "ref.ppm"), str(tmp_path / "ours.ppm")
+    reference.run_case(case, want_ppm, ranks=1)
+    exe = os.path.join(os.path.dirname(api.__file__), "c3d_case")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT", "MASTER_ADDR")}
+    env["MINIMPI_NP"] = "2"
+    proc = subprocess.run([exe, case, got_ppm, str(dims[1]), str(dims[2])], env=env, capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout[-1000:] + proc.stderr[-2000:]
+    want, got = api.read_ppm(want_ppm), api.read_ppm(got_ppm)
+    assert (want != 0).any()
+    assert np.array_equal(got, want), f"{int((got != want).any(axis=2).sum())} pixels differ from the reference image"
