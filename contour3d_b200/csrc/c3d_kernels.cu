@@ -281,9 +281,13 @@ extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int
  * Z-buffer: one 128-bit CAS per surviving fragment on (ord(depth), key); see
  * submit_fragment().
  */
+/* pixel box imin | imax << 16 | jmin << 32 | jmax << 48 that certainly holds every pixel centre a triangle can cover
+   (triangle_hidden), or C3D_NO_BOX when the pre-test did not get that far */
+#define C3D_NO_BOX 0xffffffffffffffffull
+
 template <bool MAPPED>
 __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsigned long long entry, const unsigned int s,
-                                                Pixel *__restrict__ canvas) {
+                                                const unsigned long long box, Pixel *__restrict__ canvas) {
   const unsigned int obj = C3D_ENTRY_OBJ(entry), code = C3D_ENTRY_CODE(entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
@@ -320,7 +324,13 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
       ntol[m] = -((float)tol * 1.000001f + 1.e-37f);       /* NaN / inf propagate: then nothing is dropped */
     }
   }
-  const int jmin = (int)t.jmin, jmax = (int)t.jmax, imin = (int)t.imin, imax = (int)t.imax;
+  int jmin = (int)t.jmin, jmax = (int)t.jmax, imin = (int)t.imin, imax = (int)t.imax;
+  if (C3D_NO_BOX != box) {
+    /* the reference searches its +-1 pixel box (render.c:81-89), 9-16 pixels for a sub-pixel triangle; the pre-test has
+       already bounded where a pixel centre can lie inside the triangle, usually one or two pixels */
+    imin = max(imin, (int)(box & 65535ull)); imax = min(imax, (int)((box >> 16) & 65535ull));
+    jmin = max(jmin, (int)((box >> 32) & 65535ull)); jmax = min(jmax, (int)(box >> 48));
+  }
   for (int j0 = jmin; j0 <= jmax; j0 += 4) {
     const int nj = min(jmax - j0, 3);
     for (int i0 = imin; i0 <= imax; i0 += 8) {
@@ -488,7 +498,8 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
  */
 template <bool MAPPED>
 __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsigned long long entry, const unsigned int s,
-                                                const Pixel *__restrict__ canvas) {
+                                                const Pixel *__restrict__ canvas, unsigned long long &box) {
+  box = C3D_NO_BOX;
   const CullCam &q = p.cull;
   const unsigned int code = C3D_ENTRY_CODE(entry);
   const FieldView &f = p.view[C3D_ENTRY_OBJ(entry)];
@@ -548,6 +559,13 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsi
     zslack = fmaxf(zslack, span);
   }
   if (!(xlo > -1.e6f && xhi < 1.e6f && ylo > -1.e6f && yhi < 1.e6f)) return false;
+  /* the pixels whose centre lies inside the box (screens are below 2^16 pixels per side here: make_cull) */
+  {
+    const int imin = max(0, (int)ceilf(xlo)), imax = min(q.w - 1, (int)floorf(xhi));
+    const int jmin = max(0, (int)ceilf(ylo)), jmax = min(q.h - 1, (int)floorf(yhi));
+    if (imax < imin || jmax < jmin) return true;              /* no pixel centre inside: nothing can be drawn */
+    box = (unsigned long long)imin | ((unsigned long long)imax << 16) | ((unsigned long long)jmin << 32) | ((unsigned long long)jmax << 48);
+  }
   const double zcap = (double)znear + (1.e-4 * fabs((double)znear) + 1.e-6 + 2. * (double)zslack);
   return region_hidden(canvas, q, xlo, xhi, ylo, yhi, true, ord_of(zcap));
 }
@@ -565,6 +583,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
   __shared__ unsigned long long s_entry[4][32];
   __shared__ unsigned int s_first[4][32];
   __shared__ unsigned long long s_queue[4][64];       /* triangles that passed the pre-test, waiting for a full warp */
+  __shared__ unsigned long long s_qbox[4][64];        /* ... and the pixel boxes the pre-test left them */
   unsigned long long n = *count;
   if (n > capacity) n = capacity;
   const unsigned int lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -607,34 +626,39 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
       const unsigned int before = __popc(__ballot_sync(C3D_FULL_MASK, ntri > 0u && excl < t0));
       const unsigned int src = (before + __popc(starts & (0xffffffffu >> (31u - lane))) - 1u) & 31u;
       bool keep = false;
-      unsigned long long mine = 0ull;
+      unsigned long long mine = 0ull, mybox = C3D_NO_BOX;
       if (t0 + lane < total) {
         const unsigned long long e = s_entry[wid][src];
         const unsigned int s = t0 + lane - s_first[wid][src];
         mine = C3D_TRI_PACK(e, s);
-        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden<MAPPED>(p, e, s, canvas));
+        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden<MAPPED>(p, e, s, canvas, mybox));
       }
       const unsigned int kept = __ballot_sync(C3D_FULL_MASK, keep);
       hidden_tris += __popc(__ballot_sync(C3D_FULL_MASK, t0 + lane < total)) - __popc(kept);
-      if (keep) s_queue[wid][queued + __popc(kept & ((1u << lane) - 1u))] = mine;
+      if (keep) {
+        const unsigned int at = queued + __popc(kept & ((1u << lane) - 1u));
+        s_queue[wid][at] = mine;
+        s_qbox[wid][at] = mybox;
+      }
       queued += __popc(kept);
       __syncwarp();
       if (queued >= 32u) {
         /* a full warp of triangles that need the exact treatment */
-        const unsigned long long q = s_queue[wid][lane];
+        const unsigned long long q = s_queue[wid][lane], qb = s_qbox[wid][lane];
         const unsigned long long rest = (lane + 32u < queued) ? s_queue[wid][lane + 32u] : 0ull;
+        const unsigned long long restb = (lane + 32u < queued) ? s_qbox[wid][lane + 32u] : 0ull;
         __syncwarp();
-        if (lane + 32u < queued) s_queue[wid][lane] = rest;
+        if (lane + 32u < queued) { s_queue[wid][lane] = rest; s_qbox[wid][lane] = restb; }
         queued -= 32u;
         __syncwarp();
-        raster_triangle<MAPPED>(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), canvas);
+        raster_triangle<MAPPED>(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), qb, canvas);
       }
     }
   }
   __syncwarp();
   if (lane < queued) {
     const unsigned long long q = s_queue[wid][lane];
-    raster_triangle<MAPPED>(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), canvas);
+    raster_triangle<MAPPED>(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), s_qbox[wid][lane], canvas);
   }
   if (0u == lane && nullptr != culled) {
     if (hidden_total > 0u) atomicAdd(culled, (unsigned long long)hidden_total);

@@ -775,7 +775,7 @@ static void make_cull(const Cam *c, CullCam *q) {
   const char *env = getenv("CONTOUR3D_NO_CULL");
   const bool off = NULL != env && '\0' != *env && '0' != *env;
   /* needs finite, non-degenerate constants and a screen that fits the int / float arithmetic of the test */
-  q->enabled = !off && fabs(c->d - c->nc) > 1.e-9 && isfinite(q->ax) && isfinite(q->ay) && c->w < (1 << 20) && c->h < (1 << 20);
+  q->enabled = !off && fabs(c->d - c->nc) > 1.e-9 && isfinite(q->ax) && isfinite(q->ay) && c->w < 65535 && c->h < 65535;   /* pixel boxes travel as 16-bit fields (C3D_NO_BOX, c3d_kernels.cu) */
 }
 
 static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t nc, const c3d_contour_t *contours,
