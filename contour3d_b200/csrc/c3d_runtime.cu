@@ -697,7 +697,10 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
       size_t slots = 1u << 16;
       while (slots < 4 * npix && slots < (1ull << 28)) slots <<= 1;
       /* the list is handed out in 256-entry chunks per warp (k_shade_setup): room for every resident warp's unused tail */
-      const size_t listed = std::min<size_t>(slots, 3 * npix + 32) + (size_t)ctx->sm_count * 64 * 256;
+      /* a chunk holds at least 225 useful entries (a warp abandons at most 31 when its next 32 do not fit), the last chunk of
+         every warp may stay almost empty: entries <= vertices * 256 / 225 + warps * 256 */
+      const size_t most = std::min<size_t>(slots, 3 * npix + 32);
+      const size_t listed = most + most / 7 + (size_t)ctx->sm_count * 64 * 256;
       const size_t normals = std::min<size_t>(listed, npix + npix / 2 + (size_t)ctx->sm_count * 64 * 256);
       CUDA_OK(cudaMalloc(&ctx->shade.table, slots * sizeof(unsigned long long)));
       CUDA_OK(cudaMalloc(&ctx->shade.vlist, listed * sizeof(unsigned int)));
