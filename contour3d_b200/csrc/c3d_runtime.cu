@@ -706,6 +706,11 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
       CUDA_OK(cudaMalloc(&ctx->shade.vlist, listed * sizeof(unsigned int)));
       CUDA_OK(cudaMalloc(&ctx->shade.vn, normals * 3 * sizeof(double)));
       ctx->shade.vn_cap = (unsigned int)normals;
+      {
+        /* test hook: a tiny normal array pushes vertices onto the per-pixel path of k_shade_blend */
+        const char *env = getenv("CONTOUR3D_SHADE_NORMALS_CAP");
+        if (NULL != env && '\0' != *env && (size_t)strtoull(env, NULL, 10) < normals) ctx->shade.vn_cap = (unsigned int)strtoull(env, NULL, 10);
+      }
       ctx->shade.table_mask = (unsigned int)(slots - 1);
     }
     CUDA_OK(cudaMalloc(&ctx->ppm_dev, npix * 3));

@@ -229,6 +229,23 @@ def test_frame_hiz_refresh_does_not_change_the_image(cuts, monkeypatch):
         own.destroy()
 
 
+def test_frame_shading_without_room_for_normals(monkeypatch):
+    """Vertices that find no room in the normal array are smoothed per pixel (vertex_normal, the serial path of
+    k_shade_blend): forced here by a tiny array; the image must not change."""
+    monkeypatch.setenv("CONTOUR3D_SHADE_NORMALS_CAP", "100")
+    own = api.Context(device=0)
+    try:
+        f = scenes.noise(40, seed=4)
+        g = scenes.uniform_grids(40, 40, 40)
+        scene = scenes.scene(320, 180)
+        contours = [dict(threshold=float(np.float32(t)), color=c) for t, c in ((-0.2, (255, 120, 80)), (0.15, (80, 120, 255)))]
+        img, want, depth, odepth, _ = _render_both(own, scene, [f], g, contours, [])
+        _assert_image(img, want)
+        assert np.array_equal(depth, odepth)
+    finally:
+        own.destroy()
+
+
 def test_dropin_contour3d_execute_host_buffers(ctx, tmp_path):
     """the public entry point, host double arrays in, PPM file out; config 1 in miniature"""
     g = load_golden("frame_sines24.npz")
