@@ -359,3 +359,22 @@ def test_full_size_properties_512(ctx):
         assert (a.reshape(-1, 3).max(axis=1) > 0).mean() > 0.2
     finally:
         f.destroy()
+
+
+def test_full_size_visibility_shortcuts_change_nothing():
+    """config 2's size (512^3, 1920x1080), five cameras: the frame with every visibility shortcut of the raster (front-to-back
+    order, cube / triangle occlusion tests, candidate pixel boxes) against the frame without them (CONTOUR3D_NO_CULL):
+    depth, winner key and colour of every pixel must be identical.  The oracle cannot referee frames of this size in
+    seconds; the shortcut-free pipeline is what the small-size parity tests pin to it."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gpu_shortcut_check", os.path.join(os.path.dirname(GOLDEN), "..", "tools", "gpu_shortcut_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res = mod.frames(["CONTOUR3D_NO_CULL"], 512, 1920, 1080)
+    assert len(res) == 5
+    for name, r in res.items():
+        (ia, da, ka, _, dropped), (ib, db, kb, _, none) = r["on"], r["off"]
+        assert dropped > 0 and none == 0, name
+        assert np.array_equal(ka, kb) and np.array_equal(da, db, equal_nan=True) and np.array_equal(ia, ib), name
+        assert (ka != 0).mean() > 0.1, name
