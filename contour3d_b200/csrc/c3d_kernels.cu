@@ -3,10 +3,14 @@
  * launchers.  Compiled with -gencode arch=compute_100a,code=sm_100a.
  *
  *   k_sweep      streaming classification of the scalar field + compaction of
- *                active cubes (the HBM-bound kernel; 4 B/voxel for fp32)
- *   k_raster     per-cube tessellation + projection + bounding-box raster into
- *                a 64-bit atomic z-buffer (pass 1) / winner-key buffer (pass 2)
- *   k_lines      the same two passes for poly-line segments
+ *                active cubes for arrays the TMA path cannot take (rows not
+ *                16-byte aligned); the main sweep is c3d_sweep.cu
+ *   k_raster     per-cube occlusion test, per-triangle pre-test, exact fp64
+ *                tessellation + projection + coverage of the survivors into a
+ *                z-buffer of (depth, winner key) pairs updated by ONE 128-bit
+ *                compare-and-swap per fragment (single pass)
+ *   k_hiz_build  coarse z-buffer between parts of the raster (optional)
+ *   k_lines      poly-line segments into the same z-buffer
  *   (deferred shading lives in c3d_shade.cu, the tiled sweep in c3d_sweep.cu)
  *   k_pack       y-flip + RGB byte packing (PPM payload)
  *   + halo pack/unpack, debug/inspection kernels, synthetic fields

@@ -162,6 +162,18 @@ def test_frame_lines_only_and_background(ctx):
     assert (img == np.array([7, 8, 9], dtype=np.uint8)).all(axis=2).any()
 
 
+def test_frame_without_contour_objects(ctx):
+    """num_contours = 0 is legal (src/contour3d/main.c:105-117 simply loops zero times): lines only, then nothing at all"""
+    scene = scenes.scene(96, 64, bg=(10, 20, 30))
+    lines = scenes.box_lines(nitems=7, width=3.0, color=(200, 100, 50))
+    img = ctx.render(scene, [], lines)
+    rgb, _, _ = oracle.frame(scene, [], lines, nthreads=1)
+    _assert_image(img, rgb[::-1])
+    assert (img == np.array([200, 100, 50], dtype=np.uint8)).all(axis=2).any()
+    img = ctx.render(scene, [], [])
+    assert (img == np.array([10, 20, 30], dtype=np.uint8)).all()
+
+
 def test_frame_partly_off_screen_and_behind_camera(ctx):
     """triangles whose vertices fail projection are dropped silently (render.c:62-72), bbox clamps to the screen"""
     f, g = scenes.sines(24, seed=9)
