@@ -265,6 +265,38 @@ def ours(args):
     voxels = size ** 3 * len(ISOVALUES)
     value = voxels * args.steps / (elapsed_ms * 1e-3) / 1e9
 
+    # ---- the exchange steps on their own (N > 1): NVLink / NVSwitch throughput of the halo and of the image reduction ----
+    collectives = None
+    if world > 1:
+        iters = 10
+        ar_ms, rd_ms = ctx.collectives_probe(width, height, iters)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        field.exchange()
+        h0.record(stream)
+        for _ in range(iters):
+            field.exchange()
+        h1.record(stream)
+        barrier()
+        halo_ms = h0.elapsed_time(h1) / iters
+        faces = (1 if rank > 0 else 0) + (1 if rank < world - 1 else 0)           # z slabs: interior faces of this rank
+        halo_bytes = 2 * faces * 2 * field.ext[0] * field.ext[1] * 4             # 2 planes out + 2 planes in per face, fp32
+        npix = width * height
+        mine = {"depth_allreduce_ms": ar_ms, "rgba_reduce_ms": rd_ms, "halo_ms": halo_ms, "halo_bytes": halo_bytes}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        ar = max(g["depth_allreduce_ms"] for g in gathered)
+        rd = max(g["rgba_reduce_ms"] for g in gathered)
+        hm = max(g["halo_ms"] for g in gathered)
+        hb = max(g["halo_bytes"] for g in gathered)
+        collectives = {
+            "depth_allreduce": {"bytes": 8 * npix, "ms": ar, "algbw_GBps": 8 * npix / (ar * 1e-3) / 1e9,
+                                "busbw_GBps": 2.0 * (world - 1) / world * 8 * npix / (ar * 1e-3) / 1e9},
+            "rgba_reduce": {"bytes": 4 * npix, "ms": rd, "algbw_GBps": 4 * npix / (rd * 1e-3) / 1e9},
+            "halo_exchange": {"bytes_per_interior_rank": hb, "ms": hm, "GBps_per_rank": hb / (hm * 1e-3) / 1e9},
+            "note": "ncclAllReduce(max, uint64) / ncclReduce(max, uint32) / ncclSend+Recv of 2 planes per face, timed alone with CUDA events, max over ranks",
+        }
+
     # ---- e2e arm: contour3d_execute with host double arrays, PPM to /dev/shm ----
     e2e = None
     if not args.no_e2e:
@@ -301,6 +333,7 @@ def ours(args):
             "cpu_baseline": cpu,
             "stages_ms": {k: v / args.steps for k, v in stage_sum.items()},
             "stages_ms_per_rank": per_rank,
+            "collectives": collectives,
             "active_cubes": active, "culled_cubes": t["culled_cubes"], "culled_triangles": t["culled_triangles"], "shade_spills": t["shade_spills"],
         }
         print(json.dumps(line))

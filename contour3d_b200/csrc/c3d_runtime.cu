@@ -1122,6 +1122,33 @@ extern "C" int c3d_frame_canvas(c3d_context_t *ctx, double *host_depth, uint64_t
   return 0;
 }
 
+extern "C" int c3d_frame_collectives_probe(c3d_context_t *ctx, size_t width, size_t height, int iters, float *allreduce_ms, float *reduce_ms) {
+  if (NULL == ctx || NULL == allreduce_ms || NULL == reduce_ms || iters < 1 || 0 == width * height) return c3d_error("c3d_frame_collectives_probe: bad argument");
+  *allreduce_ms = *reduce_ms = 0.f;
+  if (ctx->size < 2) return 0;
+  CUDA_OK(cudaSetDevice(ctx->device));
+  if (0 != ensure_canvas(ctx, width, height)) return 1;
+  const size_t npix = width * height;
+  cudaStream_t s = ctx->stream;
+  CUDA_OK(cudaMemsetAsync(ctx->depth_local, 0, npix * 8, s));
+  CUDA_OK(cudaMemsetAsync(ctx->rgba, 0, npix * 4, s));
+  /* warm-up round (also lines the ranks up), then the timed rounds */
+  NCCL_OK(g_nccl.AllReduce(ctx->depth_local, ctx->depth_global, npix, ncclUint64, ncclMax, ctx->comm, s));
+  NCCL_OK(g_nccl.Reduce(ctx->rgba, ctx->rgba, npix, ncclUint32, ncclMax, 0, ctx->comm, s));
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_START], s));
+  for (int it = 0; it < iters; it++) NCCL_OK(g_nccl.AllReduce(ctx->depth_local, ctx->depth_global, npix, ncclUint64, ncclMax, ctx->comm, s));
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
+  for (int it = 0; it < iters; it++) NCCL_OK(g_nccl.Reduce(ctx->rgba, ctx->rgba, npix, ncclUint32, ncclMax, 0, ctx->comm, s));
+  CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE1], s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  float a = 0.f, b = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&a, ctx->ev[EV_START], ctx->ev[EV_REDUCE0]));
+  CUDA_OK(cudaEventElapsedTime(&b, ctx->ev[EV_REDUCE0], ctx->ev[EV_REDUCE1]));
+  *allreduce_ms = a / (float)iters;
+  *reduce_ms = b / (float)iters;
+  return 0;
+}
+
 /* ------------------------------------------------------------ stage level */
 
 static int stage_view(c3d_context *ctx, const c3d_field *f, const double *const grids[3], const double thr, FieldView *v) {

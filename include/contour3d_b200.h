@@ -160,6 +160,12 @@ int c3d_frame_timings(const c3d_context_t *ctx, c3d_timings_t *out);
    depth as double (-DBL_MAX where empty), winner key (0 = background) */
 int c3d_frame_canvas(c3d_context_t *ctx, double *host_depth, uint64_t *host_key);
 
+/* The frame's two image collectives on their own (measurement: NVLink / NVSwitch throughput of the reduction that replaces
+   MPI_Reduce of output.c:82): `iters` x ncclAllReduce(max) over a width x height plane of 64-bit depths, then `iters` x
+   ncclReduce(max) of the 32-bit colour plane to rank 0, each timed with CUDA events after a warm-up round; milliseconds
+   per call.  Collective: every rank of the context's communicator must call it.  comm_size 1: both times are 0. */
+int c3d_frame_collectives_probe(c3d_context_t *ctx, size_t width, size_t height, int iters, float *allreduce_ms, float *reduce_ms);
+
 /* ---- stage-level entry points (parity tests, mesh export) ---- */
 
 /* replaces the classification of triangulate_tetrahedron (triangulate.c:145-152,176-192):
