@@ -168,3 +168,33 @@ def test_camera_helper_reproduces_the_demo_camera():
     assert np.allclose(np.array(rolled["local_x"]) / (4.0 / 3.0), ly, atol=1e-12)
     with pytest.raises(ValueError):
         api.camera_from_angles(10.0, 10.0, camera_distance=0.0)
+
+
+def test_converter_probe_rejects_a_function_that_is_not_one(capfd):
+    """a callback that returns different values for the same argument cannot be tabulated (nor rendered reproducibly)"""
+    import itertools
+
+    counter = itertools.count()
+    g = [np.linspace(0, 1, 6)] * 3
+    with pytest.raises(RuntimeError):
+        api.positions_probe(lambda x, y, z: (x + 1e-3 * next(counter), y, z), g, (0, 0, 0), (6, 6, 6))
+    assert "does not return the same value" in capfd.readouterr().err
+
+
+def test_converter_probe_keeps_nan_and_signed_zero_bit_patterns():
+    g = [np.array([-1.0, 0.0, 1.0]), np.array([0.0, 1.0]), np.array([2.0, 3.0])]
+    fn = lambda x, y, z: (float("nan") if x == 0.0 else -0.0 * x, y, z)      # noqa: E731
+    ident, tabs, st = api.positions_probe(fn, g, (0, 0, 0), (3, 2, 2))
+    assert not ident and st[0] == [1, 0, 0]
+    assert np.isnan(tabs[0][1]) and np.signbit(tabs[0][2]) and not np.signbit(tabs[0][0])
+
+
+def test_casefile_carries_the_converter_kind(tmp_path):
+    f = scenes.gyroid(6)
+    g = scenes.uniform_grids(6, 6, 6)
+    sc = scenes.scene(32, 24)
+    sc["converter"] = 3
+    path = str(tmp_path / "c.bin")
+    casefile.write_case(path, sc, g, [f], [dict(field=0, threshold=0.1, color=(1, 2, 3))], [])
+    scene, *_ = casefile.read_case(path)
+    assert scene["converter"] == 3
