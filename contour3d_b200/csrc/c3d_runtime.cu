@@ -827,11 +827,16 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
       const size_t cubes = f->ext[0] * f->ext[1] * f->ext[2];
       want += std::max<size_t>(1u << 20, cubes / 16);
     }
+    {
+      /* test hook: a deliberately small first allocation exercises the grow-and-redo path below */
+      const char *env = getenv("CONTOUR3D_LIST_CAP");
+      if (NULL != env && '\0' != *env && strtoull(env, NULL, 10) >= 64) want = (size_t)strtoull(env, NULL, 10);
+    }
     CUDA_OK(cudaMalloc(&ctx->list, want * 8));
     ctx->list_cap = want;
   }
   if (nc > 0 && 0 == ctx->rec_cap) {
-    const size_t want = std::max<size_t>(1u << 18, ctx->list_cap / 4);
+    const size_t want = NULL != getenv("CONTOUR3D_LIST_CAP") ? std::max<size_t>(64, ctx->list_cap / 4) : std::max<size_t>(1u << 18, ctx->list_cap / 4);
     CUDA_OK(cudaMalloc(&ctx->records, want * 32));
     ctx->rec_cap = want;
   }

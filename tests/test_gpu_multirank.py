@@ -19,9 +19,12 @@ def _gpus():
 
 
 @pytest.mark.parametrize("world,dims", [(2, "1x1x2"), (2, "1x2x1"), (4, "1x2x2"), (4, "1x1x4"), (8, "1x4x2")])
-def test_multi_gpu_image_equals_single_rank_oracle(world, dims):
+def test_multi_gpu_image_equals_single_rank_oracle(world, dims, monkeypatch):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs")
+    if dims == "1x1x2":
+        # also the grow-and-redo path: the ranks overflow their tiny work buffers by different amounts and must agree to run again
+        monkeypatch.setenv("CONTOUR3D_LIST_CAP", "2000")
     port = 29500 + (os.getpid() + world * 7 + len(dims)) % 400
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tools", "multi_gpu_check.py"), dims]

@@ -258,6 +258,25 @@ def test_frame_shading_without_room_for_normals(monkeypatch):
         own.destroy()
 
 
+def test_frame_work_buffers_grow_and_the_frame_is_redone(monkeypatch):
+    """The number of cut cubes is unknown before the sweep: record and list buffers that overflow are grown
+    to the counted size and the frame runs again.  Forced here by a tiny first allocation."""
+    monkeypatch.setenv("CONTOUR3D_LIST_CAP", "300")
+    own = api.Context(device=0)
+    try:
+        f = scenes.noise(40, seed=8)
+        g = scenes.uniform_grids(40, 40, 40)
+        scene = scenes.scene(320, 180)
+        contours = [dict(threshold=float(np.float32(t)), color=c) for t, c in ((-0.2, (255, 120, 80)), (0.15, (80, 120, 255)))]
+        for _ in range(2):                                   # the second frame finds the grown buffers
+            img, want, depth, odepth, _ = _render_both(own, scene, [f], g, contours, scenes.box_lines(nitems=8, width=2.0))
+            _assert_image(img, want)
+            assert np.array_equal(depth, odepth)
+        assert sum(own.timings()["active_cubes"]) > 300
+    finally:
+        own.destroy()
+
+
 def test_dropin_contour3d_execute_host_buffers(ctx, tmp_path):
     """the public entry point, host double arrays in, PPM file out; config 1 in miniature"""
     g = load_golden("frame_sines24.npz")
