@@ -1,6 +1,6 @@
 """Access to the UNMODIFIED reference built into oracle/_ref by oracle/Makefile.
 
-TEST / BASELINE INFRASTRUCTURE ONLY (tests/, tools/make_golden.py, bench.py's
+TEST / BASELINE INFRASTRUCTURE ONLY (tests/, tests/golden/make_golden.py, bench.py's
 reference arm).  Nothing here reads /root/reference at run time: only the
 prebuilt binaries under oracle/_ref are used, so it also works on the GPU box.
 """

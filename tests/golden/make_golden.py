@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref).
 
-    python tools/make_golden.py
+    python tests/golden/make_golden.py
 
 Run in the development container (needs oracle/_ref, i.e. /root/reference at
 build time).  Each fixture stores its INPUT arrays next to the reference's
@@ -14,7 +14,7 @@ import tempfile
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from contour3d_b200 import casefile, scenes  # noqa: E402
 from oracle import reference  # noqa: E402

@@ -1,6 +1,6 @@
 """N-rank parity check, one process per GPU (launch with torch.distributed.run):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/multi_gpu_check.py [dims]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/multi_gpu_check.py [dims]
 
 Every rank uploads ITS pencil of a host field, the library exchanges halos over NCCL,
 renders, reduces; rank 0 compares the image with the oracle's single-rank image of the

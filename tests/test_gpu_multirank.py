@@ -27,7 +27,7 @@ def test_multi_gpu_image_equals_single_rank_oracle(world, dims, monkeypatch):
         monkeypatch.setenv("CONTOUR3D_LIST_CAP", "2000")
     port = 29500 + (os.getpid() + world * 7 + len(dims)) % 400
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tools", "multi_gpu_check.py"), dims]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py"), dims]
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
     assert "ok" in proc.stdout
