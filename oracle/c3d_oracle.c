@@ -726,3 +726,40 @@ int oracle_frame(const oracle_scene_t *s, size_t ncontours, const oracle_contour
   if (stats) *stats = total;
   return failed;
 }
+
+/* ---- coordinate converters for the tests ----
+ * The `converter` callback belongs to the caller (include/contour3d.h:31-33 of the reference); the oracle only calls it
+ * where the reference does (triangulate.c:165-170, line.c:39-40).  These three are the ones the case-file driver
+ * offers (contour3d_b200/csrc/c3d_case_main.c: cylindrical, stretched, twisted), restated here so that tests can
+ * hand the SAME functions to the oracle through its Python binding. */
+#include <math.h>
+
+static oracle_vec_t converter_cylindrical(const oracle_vec_t o) {
+  const double r = 0.75 + 0.5 * o.x, theta = 1.5 * o.y;
+  const oracle_vec_t c = {r * cos(theta) - 0.75, r * sin(theta), o.z};
+  return c;
+}
+static oracle_vec_t converter_stretched(const oracle_vec_t o) {
+  const oracle_vec_t c = {o.x + 0.3 * o.x * o.x * o.x, 1.2 * o.y, o.z - 0.2 * o.z * o.z};
+  return c;
+}
+static oracle_vec_t converter_twisted(const oracle_vec_t o) {
+  const double a = 0.8 * o.z;
+  const oracle_vec_t c = {o.x * cos(a) - o.y * sin(a) + 0.02 * o.z * o.y, o.x * sin(a) + o.y * cos(a), o.z + 0.05 * sin(3. * o.x) * o.y};
+  return c;
+}
+
+/* kind: 0 identity (NULL), 1 cylindrical, 2 stretched, 3 twisted -- the numbering of the case files */
+oracle_converter_t oracle_converter_of(int kind) {
+  return 1 == kind ? converter_cylindrical : (2 == kind ? converter_stretched : (3 == kind ? converter_twisted : NULL));
+}
+
+/* out[3n..] = converter(in[3n..]) for n points: lets a test tabulate the function without leaving C arithmetic */
+void oracle_convert_points(int kind, size_t n, const double *in, double *out) {
+  const oracle_converter_t fn = oracle_converter_of(kind);
+  for (size_t q = 0; q < n; q++) {
+    const oracle_vec_t o = {in[3 * q], in[3 * q + 1], in[3 * q + 2]};
+    const oracle_vec_t c = fn ? fn(o) : o;
+    out[3 * q] = c.x; out[3 * q + 1] = c.y; out[3 * q + 2] = c.z;
+  }
+}

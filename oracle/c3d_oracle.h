@@ -97,4 +97,8 @@ int oracle_frame(const oracle_scene_t *s, size_t ncontours, const oracle_contour
                  size_t nlines, const oracle_line_t *lines, int nthreads,
                  double *depth, uint8_t *rgb, oracle_stats_t *stats);
 
+/* the converters of the case-file driver (c3d_case_main.c), for tests: 0 identity (NULL), 1 cylindrical, 2 stretched, 3 twisted */
+oracle_converter_t oracle_converter_of(int kind);
+void oracle_convert_points(int kind, size_t n, const double *in, double *out);
+
 #endif /* C3D_ORACLE_H */

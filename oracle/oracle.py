@@ -115,8 +115,25 @@ def lib():
             C.POINTER(Scene), C.c_size_t, C.POINTER(Contour), C.c_size_t, C.POINTER(Line), C.c_int,
             C.c_void_p, C.c_void_p, C.POINTER(Stats),
         ]
+        L.oracle_converter_of.restype = C.c_void_p
+        L.oracle_converter_of.argtypes = [C.c_int]
+        L.oracle_convert_points.restype = None
+        L.oracle_convert_points.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def converter_ptr(kind: int):
+    """C function pointer of a built-in converter (0 identity -> None, 1 cylindrical, 2 stretched, 3 twisted: the case files' numbering)"""
+    return lib().oracle_converter_of(int(kind)) if kind else None
+
+
+def convert_points(kind: int, points) -> np.ndarray:
+    """the built-in converter applied to (n, 3) points, in C arithmetic (bit-identical to what the oracle / the case driver compute)"""
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    out = np.empty_like(pts)
+    lib().oracle_convert_points(int(kind), len(pts), pts.ctypes.data, out.ctypes.data)
+    return out
 
 
 def _dptr(a: np.ndarray):
@@ -131,7 +148,7 @@ class _Keep:
         self.refs = refs
 
 
-def make_contour(field: np.ndarray, grids, threshold: float, color=(255, 255, 255)) -> _Keep:
+def make_contour(field: np.ndarray, grids, threshold: float, color=(255, 255, 255), converter: int = 0) -> _Keep:
     """field: (nz, ny, nx) array (x fastest), widened to float64 exactly."""
     f = np.ascontiguousarray(field, dtype=np.float64)
     nz, ny, nx = f.shape
@@ -144,7 +161,7 @@ def make_contour(field: np.ndarray, grids, threshold: float, color=(255, 255, 25
     c.field = _dptr(f)
     c.threshold = float(threshold)
     c.color[:] = list(color)
-    c.converter = None
+    c.converter = converter_ptr(converter)
     return _Keep(c, (f, g))
 
 
@@ -168,7 +185,7 @@ def make_line(line: dict) -> Line:
     l.nitems = int(line["nitems"])
     l.width = float(line["width"])
     l.color[:] = list(line.get("color", (255, 255, 255)))
-    l.converter = None
+    l.converter = converter_ptr(line.get("converter", 0))
     return l
 
 
@@ -199,12 +216,12 @@ def tessellate(field, grids, threshold):
 def frame(scene: dict, contours, lines=(), nthreads: int = 1):
     """Render a whole frame.
 
-    contours: list of dicts {field, grids, threshold, color}
-    lines:    list of dicts {edges, nitems, width, color}
+    contours: list of dicts {field, grids, threshold, color[, converter: built-in kind 0..3]}
+    lines:    list of dicts {edges, nitems, width, color[, converter]}
     returns (rgb uint8 [H, W, 3] in canvas order (not flipped), depth float64 [H, W], stats)
     """
     s = make_scene(scene)
-    keeps = [make_contour(c["field"], c["grids"], c["threshold"], c.get("color", (255, 255, 255))) for c in contours]
+    keeps = [make_contour(c["field"], c["grids"], c["threshold"], c.get("color", (255, 255, 255)), c.get("converter", 0)) for c in contours]
     carr = (Contour * max(1, len(keeps)))()
     for n, k in enumerate(keeps):
         carr[n] = k.struct

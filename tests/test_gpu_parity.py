@@ -327,6 +327,40 @@ def test_dropin_coordinate_converter_matches_the_reference(ctx, tmp_path, kind, 
     assert (api.read_ppm(want_ppm) != want).any()
 
 
+@pytest.mark.parametrize("kind", [1, 3])
+def test_frame_converter_tables_through_the_c_abi(ctx, kind):
+    """c3d_contour_t.positions / c3d_line_t.points handed in directly (what a non-C host would do): the tables come from
+    c3d_positions_probe on the built-in cylindrical / twisted converter, the image must equal the oracle's, which calls
+    the converter itself (pinned to the reference by tests/test_oracle_vs_reference.py)."""
+    n = 28
+    f = scenes.noise(n, seed=40 + kind)
+    g = scenes.uniform_grids(n, n, n)
+    scene = scenes.scene(320, 180)
+    ident, tables, strides = api.positions_probe(lambda x, y, z: tuple(oracle.convert_points(kind, [[x, y, z]])[0]), g, (0, 0, 0), (n, n, n))
+    assert not ident
+    lines = scenes.box_lines(nitems=10, width=2.0)
+    glines = []
+    for l in lines:
+        e0, e1 = (np.array(v, dtype=np.float64) for v in l["edges"])
+        delta = (1.0 / (l["nitems"] - 1)) * (e1 - e0)                    # line.c:138-140
+        pts = np.stack([e0 + float(m) * delta for m in range(l["nitems"])])   # line.c:157-158
+        glines.append(dict(l, points=oracle.convert_points(kind, pts)))
+    thr = [float(np.float32(-0.15)), float(np.float32(0.2))]
+    cols = [(250, 200, 60), (60, 200, 250)]
+    dev = ctx.field((n, n, n), dtype=f.dtype).upload(f)
+    try:
+        cs = [dict(field=dev, grids=g, threshold=t, color=c, positions=(tables, strides)) for t, c in zip(thr, cols)]
+        img = ctx.render(scene, cs, glines)
+        depth, _ = ctx.canvas(scene["width"], scene["height"])
+    finally:
+        dev.destroy()
+    ocs = [dict(field=f, grids=g, threshold=t, color=c, converter=kind) for t, c in zip(thr, cols)]
+    rgb, odepth, _ = oracle.frame(scene, ocs, [dict(l, converter=kind) for l in lines], nthreads=4)
+    assert (rgb != 0).any()
+    _assert_image(img, rgb[::-1])
+    assert np.array_equal(depth, odepth)
+
+
 def test_dropin_rejects_what_it_cannot_honour(ctx, tmp_path, capfd):
     g = load_golden("frame_gyroid32.npz")
     grids = [g["gx"], g["gy"], g["gz"]]

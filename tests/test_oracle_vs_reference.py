@@ -62,3 +62,27 @@ def test_reference_is_decomposition_invariant_and_matches_oracle(tmp_path, ranks
     rgb, _, _ = oracle.frame(scene, cs, lines, nthreads=1)
     frac, worst = image_diff(read_ppm(out), rgb[::-1])
     assert frac == 0.0, (frac, worst)
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_coordinate_converters_oracle_matches_reference(tmp_path, kind):
+    """non-identity `converter` callbacks (triangulate.c:165-170, line.c:39-40): the oracle calling the built-in
+    cylindrical / stretched / twisted functions == the unmodified reference calling the same functions (ref_driver)"""
+    from contour3d_b200 import api, casefile, scenes
+
+    n = 20
+    f = scenes.noise(n, seed=30 + kind)
+    g = scenes.uniform_grids(n, n, n)
+    scene = scenes.scene(200, 150)
+    scene["converter"] = kind
+    contours = [dict(field=0, threshold=float(np.float32(-0.1)), color=(250, 200, 60)), dict(field=0, threshold=float(np.float32(0.2)), color=(60, 200, 250))]
+    lines = scenes.box_lines(nitems=12, width=2.0)
+    case, ppm = str(tmp_path / "c.bin"), str(tmp_path / "ref.ppm")
+    casefile.write_case(case, scene, g, [f], contours, lines)
+    reference.run_case(case, ppm, ranks=2, dims=(1, 1, 2))
+    want = api.read_ppm(ppm)
+    ocs = [dict(field=f, grids=g, threshold=c["threshold"], color=c["color"], converter=kind) for c in contours]
+    ols = [dict(l, converter=kind) for l in lines]
+    rgb, _, _ = oracle.frame(scene, ocs, ols, nthreads=3)
+    assert (want != 0).any()
+    assert np.array_equal(rgb[::-1], want)
