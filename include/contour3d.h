@@ -40,7 +40,7 @@ typedef struct {
   sdecomp_pencil_t pencil;                 /* pencil the array lives on (X1 / X2: x fastest) */
   size_t glsizes[CONTOUR3D_NDIMS];         /* global number of grid points */
   double * grids[CONTOUR3D_NDIMS];         /* global rectilinear coordinates, glsizes[d] each */
-  contour3d_vector_t (* converter) (       /* orthogonal -> Cartesian; must be the identity map here */
+  contour3d_vector_t (* converter) (       /* orthogonal -> Cartesian; called on the host, tabulated for the device */
       const contour3d_vector_t orthogonal
   );
   double threshold;                        /* iso value */
