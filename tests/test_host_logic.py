@@ -198,3 +198,34 @@ def test_casefile_carries_the_converter_kind(tmp_path):
     casefile.write_case(path, sc, g, [f], [dict(field=0, threshold=0.1, color=(1, 2, 3))], [])
     scene, *_ = casefile.read_case(path)
     assert scene["converter"] == 3
+
+
+@pytest.mark.parametrize("ranks,dims", [(1, (0, 0, 0)), (2, (0, 0, 0)), (4, (0, 0, 0)), (6, (1, 3, 2)), (8, (0, 0, 0)), (8, (1, 1, 8)), (5, (1, 5, 1))])
+def test_sdecomp_standin_agrees_with_simpledecomp(tmp_path, ranks, dims):
+    """The SimpleDecomp stand-in of MPI-less hosts (c3d_sdecomp_compat.c) against the genuine SimpleDecomp (compiled into
+    oracle/_ref/libc3dref.so): process-grid sizes, ranks, neighbours, pencil sizes and offsets for all six pencils and
+    three directions, on every rank, under the fork-mode MPI stand-in.  Periodic in x and z, not in y."""
+    import subprocess
+
+    from oracle import reference
+
+    if not reference.available():
+        pytest.skip("oracle/_ref not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "csrc", "sdecomp_probe.c")
+    pkg = os.path.join(root, "contour3d_b200")
+    builds = {
+        "standin": ["-I", os.path.join(root, "include"), "-L", pkg, "-lc3d_sdecomp_compat", f"-Wl,-rpath,{pkg}"],
+        # the genuine library is declared by the stand-in header too (link-compatible by construction: same method-table layout)
+        "genuine": ["-I", os.path.join(root, "include"), "-L", reference.REF_DIR, "-l:libc3dref.so", f"-Wl,-rpath,{reference.REF_DIR}"],
+    }
+    out = {}
+    for name, flags in builds.items():
+        exe = str(tmp_path / f"probe_{name}")
+        subprocess.run(["gcc", "-std=gnu11", "-O1", "-I", os.path.join(root, "compat", "minimpi"), "-o", exe, src] + flags, check=True)
+        env = dict(os.environ, MINIMPI_NP=str(ranks))
+        prefix = str(tmp_path / f"out_{name}")
+        subprocess.run([exe] + [str(v) for v in dims] + ["37", "50", "41", prefix], check=True, env=env, timeout=60)
+        out[name] = [open(f"{prefix}.{r}").read() for r in range(ranks)]
+    assert out["standin"] == out["genuine"]
+    assert "nprocs" in out["genuine"][0]
