@@ -63,7 +63,7 @@ def have_real_mpi() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, h) for h in ("c3d_internal.h", "c3d_tables.h", "c3d_device.cuh")]
+    headers = [os.path.join(CSRC, h) for h in ("c3d_internal.h", "c3d_tables.h", "c3d_device.cuh", "c3d_peer.h")]
     headers += [os.path.join(INCLUDE, h) for h in ("contour3d_b200.h", "contour3d.h", "sdecomp.h")]
     headers += [os.path.join(MINIMPI, "mpi.h")]
     inc = ["-I", INCLUDE, "-I", CSRC]
@@ -71,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cc = "mpicc" if have_real_mpi() else "gcc"
     mpi_inc = [] if have_real_mpi() else ["-I", MINIMPI]
     objs = []
-    for name in ("c3d_kernels.cu", "c3d_sweep.cu", "c3d_shade.cu", "c3d_runtime.cu"):
+    for name in ("c3d_kernels.cu", "c3d_sweep.cu", "c3d_shade.cu", "c3d_peer.cu", "c3d_runtime.cu"):
         src = os.path.join(CSRC, name)
         obj = os.path.join(OBJ, name + ".o")
         if force or _newer(obj, [src] + headers):

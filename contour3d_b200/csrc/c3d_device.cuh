@@ -334,15 +334,27 @@ __device__ __forceinline__ void submit_fragment(Pixel *slot, const unsigned long
    returned by value (registers), .w = 1 when the projection accepted the point */
 struct ProjectedVertex { double x, y, z, w; };
 template <bool MAPPED>
-static __device__ __noinline__ ProjectedVertex exact_vertex_t(const FrameParams &p, const unsigned int obj, const long long i, const long long j,
+static __device__ __noinline__ ProjectedVertex exact_vertex_t(const Cam &cam, const FieldView &f, const long long i, const long long j,
                                                               const long long k, const unsigned int tail, const unsigned int head) {
-  const FieldView &f = p.view[obj];
   V3 q = V3{0., 0., 0.};
-  const bool ok = project(p.cam, cut_edge_global_t<MAPPED>(f, i, j, k, f.thr, tail, head), q);
+  const bool ok = project(cam, cut_edge_global_t<MAPPED>(f, i, j, k, f.thr, tail, head), q);
   return ProjectedVertex{q.x, q.y, q.z, ok ? 1. : 0.};
 }
 __device__ __forceinline__ ProjectedVertex exact_vertex(const FrameParams &p, const unsigned int obj, const long long i, const long long j,
                                                         const long long k, const unsigned int tail, const unsigned int head) {
-  return exact_vertex_t<true>(p, obj, i, j, k, tail, head);
+  return exact_vertex_t<true>(p.cam, p.view[obj], i, j, k, tail, head);
 }
 
+/* the view a list entry refers to: this rank's own array, or (screen-partitioned frames) the array of the rank that listed it */
+template <bool PEER>
+__device__ __forceinline__ const FieldView &entry_view(const FrameParams &p, const unsigned long long entry) {
+  if (PEER) return p.pviews[C3D_PEER_VIEW(C3D_ENTRY_SRC(entry), C3D_ENTRY_OBJ(entry))];
+  return p.view[C3D_ENTRY_OBJ(entry)];
+}
+
+/* winner key of triangle s of cube (i, j, k) of view f (c3d_internal.h): global cube indices */
+__device__ __forceinline__ unsigned long long winner_key(const FieldView &f, const unsigned int obj, const long long i, const long long j,
+                                                         const long long k, const unsigned int s) {
+  return ((unsigned long long)(obj + 1u) << C3D_KEY_OBJ_SHIFT) | ((unsigned long long)(k + f.off[2]) << 36)
+       | ((unsigned long long)(j + f.off[1]) << 20) | ((unsigned long long)(i + f.off[0]) << 4) | s;
+}

@@ -46,6 +46,8 @@ struct FieldView {
   const double *g[3];      /* device coordinates of exactly those points */
   const float *gf[3];      /* the same rounded to fp32 (conservative visibility pre-tests only) */
   const PosMap *map;       /* device pointer; nullptr: identity converter, positions are (g[0][i], g[1][j], g[2][k]) */
+  long long off[3];        /* global index of the array's first point: winner keys carry GLOBAL cube indices, so that the
+                              drawing order that decides depth ties (render.c:125-132) is the one-rank order on any decomposition */
   double thr;              /* iso value; classification is thr < value (strict) */
   float thr_ge;            /* fp32 fields: smallest float f with (double)f > thr, so thr < v <=> v >= thr_ge */
   unsigned char color[3];
@@ -95,6 +97,11 @@ struct __align__(16) Pixel { unsigned long long depth, key; };
 #define C3D_ENTRY_OBJ(e) ((unsigned int)((e) >> 56) & 15u)
 #define C3D_ENTRY_IRREGULAR_BIT (1ull << 60)
 #define C3D_ENTRY_IRREGULAR(e) (0ull != ((e) & C3D_ENTRY_IRREGULAR_BIT))
+/* screen-partitioned multi-rank frames: bits 61-63 name the rank whose array the cube indices refer to */
+#define C3D_ENTRY_SRC_SHIFT 61
+#define C3D_ENTRY_SRC(e) ((unsigned int)((e) >> C3D_ENTRY_SRC_SHIFT) & 7u)
+#define C3D_MAX_RANKS 8               /* ranks of a screen-partitioned frame (3 bits of the entry) */
+#define C3D_PEER_VIEW(src, obj) (((src) << 4) | (obj))
 
 #define C3D_MAX_OBJECTS 16
 #define C3D_DEPTH_BUCKETS 2048        /* view-depth slabs of the front-to-back ordering (multiple of 1024) */
@@ -113,7 +120,41 @@ struct CullCam {
   float W, H;
   int w, h;
   int enabled;
+  int valid;                           /* the constants are finite and the screen fits: cube_owners() may use them even when culling is off */
 };
+
+/*
+ * Screen partition of a multi-rank frame ("sort-first"): the screen is cut into square tiles dealt out to the ranks in a
+ * fixed pattern; a rank rasterises EVERY cube (its own and the other ranks', read through peer memory) that can touch
+ * its tiles, nearest first, so the occlusion tests see the whole scene exactly as on one GPU and the raster work divides by
+ * the number of ranks.  Shading goes back to the rank that owns the winning cube's array (it needs the neighbouring cubes).
+ */
+struct Partition {
+  int nranks, me;                      /* nranks == 0: not partitioned */
+  int tile_shift;                      /* log2 of the tile edge in pixels */
+  int tiles_x, tiles_y;
+  unsigned int recip;                  /* ceil(2^32 / nranks): v % nranks for small v without a division */
+  int py, pz;                          /* process grid (x is never split) */
+  unsigned short yoff[C3D_MAX_RANKS + 1], zoff[C3D_MAX_RANKS + 1];   /* global index of the first point of block c; [p] = N */
+  unsigned char home[C3D_MAX_RANKS];   /* communicator rank of block (cy, cz): home[cy * pz + cz] */
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned int tile_owner(const Partition &q, const unsigned int tx, const unsigned int ty) {
+  const unsigned int v = tx + 3u * ty;
+  return v - __umulhi(v, q.recip) * (unsigned int)q.nranks;
+}
+__device__ __forceinline__ bool pixel_owned(const Partition &q, const int pi, const int pj) {
+  return tile_owner(q, (unsigned int)pi >> q.tile_shift, (unsigned int)pj >> q.tile_shift) == (unsigned int)q.me;
+}
+/* the rank whose INTERIOR holds point (gj, gk): it lists (and can shade) the cube whose low corner that is */
+__device__ __forceinline__ unsigned int cube_home(const Partition &q, const unsigned int gj, const unsigned int gk) {
+  unsigned int cy = 0u, cz = 0u;
+  for (int c = 1; c < q.py; c++) cy += (gj >= (unsigned int)q.yoff[c]) ? 1u : 0u;
+  for (int c = 1; c < q.pz; c++) cz += (gk >= (unsigned int)q.zoff[c]) ? 1u : 0u;
+  return (unsigned int)q.home[cy * (unsigned int)q.pz + cz];
+}
+#endif
 
 /* everything the raster / shading kernels need, passed by value (constant bank) */
 struct FrameParams {
@@ -124,12 +165,18 @@ struct FrameParams {
   const float *pxf, *pyf;    /* the same rounded to fp32 (conservative coverage pre-test) */
   unsigned int ncontours;
   FieldView view[C3D_MAX_OBJECTS];
+  /* screen-partitioned frames only */
+  Partition part;
+  const FieldView *pviews;   /* device table: view C3D_PEER_VIEW(src, obj) = object `obj` as rank `src` holds it (data through peer memory) */
 };
+
+/* a pixel won by a contour triangle, on its way to the rank that shades it */
+struct __align__(16) WorkItem { unsigned int pix, pad; unsigned long long key; };
 
 /* device scratch of the deferred shading (c3d_shade.cu), sized by the screen */
 #define C3D_SHADE_PIX_BYTES 56
 struct ShadeScratch {
-  unsigned int *work;            /* pixels won by a contour triangle, compacted: npix words */
+  WorkItem *work;                /* pixels won by a contour triangle, compacted: npix items */
   unsigned int *counters;        /* [0] listed pixels, [1] distinct vertices */
   void *pix;                     /* per listed pixel: weights, cube, vertex slots: npix x C3D_SHADE_PIX_BYTES */
   unsigned long long *table;     /* open-addressing set of the vertices (global cube edges) the listed pixels reference */
@@ -163,14 +210,26 @@ int c3d_k_raster(const FrameParams *p, const unsigned long long *list, const uns
                  Pixel *canvas, unsigned long long *culled, const unsigned long long *hiz_tiles, unsigned int part_begin,
                  unsigned int part_end, int sm_count, cudaStream_t s);
 int c3d_k_hiz_build(const Pixel *canvas, long long w, long long h, unsigned long long *tiles, int sm_count, cudaStream_t s);
+/* nout / nover may be NULL */
 int c3d_k_overflow_flag(const unsigned long long *nrec, unsigned long long rec_cap, const unsigned long long *nlist,
-                        unsigned long long list_cap, unsigned long long *flag, cudaStream_t s);
+                        unsigned long long list_cap, const unsigned long long *nout, unsigned long long out_cap,
+                        const unsigned long long *nover, unsigned long long *flag, cudaStream_t s);
 int c3d_k_lines(const Cam *c, const LineDev *lines_dev, const LineDev *lines_host, size_t nlines, unsigned long long first_obj,
                 Pixel *canvas, cudaStream_t s);
 int c3d_k_depth_extract(const Pixel *canvas, unsigned long long *depth, size_t npix, cudaStream_t s);
 int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
                 unsigned int *rgba, size_t npix, const ShadeScratch *scratch, unsigned long long *overflowed,
                 int sm_count, cudaStream_t s);
+int c3d_k_shade_begin(const ShadeScratch *scratch, cudaStream_t s);
+int c3d_k_shade_finish(const FrameParams *p, unsigned int *rgba, const ShadeScratch *scratch, unsigned long long *overflowed, int sm_count, cudaStream_t s);
+int c3d_k_shade_select_part(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, unsigned int *rgba_out,
+                            WorkItem *seg, unsigned int seg_cap, unsigned int *nseg, unsigned long long *overflowed, int sm_count, cudaStream_t s);
+/* screen-partitioned frames (c3d_sweep.cu, c3d_kernels.cu) */
+int c3d_k_expand_part(const FrameParams *fp, float near_depth, float far_depth, const void *records, const unsigned long long *nrecords,
+                      unsigned long long rec_capacity, unsigned long long *outbox, unsigned long long *count, unsigned long long capacity,
+                      unsigned int *histogram, unsigned long long *cursors, unsigned long long *seg_start,
+                      unsigned long long *per_object, unsigned int nobjects, int sm_count, cudaStream_t s);
+int c3d_k_clear_part(Pixel *canvas, const Partition *part, long long w, long long h, int sm_count, cudaStream_t s);
 int c3d_k_to_float(const double *in, float *out, size_t n, cudaStream_t s);
 int c3d_k_pack(const unsigned int *rgba, const unsigned char bg[3], long long w, long long h, unsigned char *out, cudaStream_t s);
 int c3d_k_canvas_split(const Pixel *canvas, double *depth, unsigned long long *key, size_t npix, cudaStream_t s);

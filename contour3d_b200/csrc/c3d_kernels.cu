@@ -38,6 +38,25 @@ extern "C" int c3d_k_clear(Pixel *canvas, size_t npix, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
+/* screen-partitioned frames: only this rank's tiles are ever read, so only they are cleared */
+__global__ void __launch_bounds__(256) k_clear_part(Pixel *__restrict__ canvas, const Partition part, const unsigned int w, const unsigned int h) {
+  const ulonglong2 empty = make_ulonglong2(ord_of(-DBL_MAX), 0ull);
+  const unsigned int tile = 1u << part.tile_shift, ntiles = (unsigned int)(part.tiles_x * part.tiles_y);
+  for (unsigned int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const unsigned int tx = t % (unsigned int)part.tiles_x, ty = t / (unsigned int)part.tiles_x;
+    if (tile_owner(part, tx, ty) != (unsigned int)part.me) continue;
+    for (unsigned int q = threadIdx.x; q < tile * tile; q += blockDim.x) {
+      const unsigned int pi = tx * tile + (q & (tile - 1u)), pj = ty * tile + (q >> part.tile_shift);
+      if (pi < w && pj < h) reinterpret_cast<ulonglong2 *>(canvas)[(size_t)pj * w + pi] = empty;
+    }
+  }
+}
+
+extern "C" int c3d_k_clear_part(Pixel *canvas, const Partition *part, long long w, long long h, int sm_count, cudaStream_t s) {
+  k_clear_part<<<sm_count * 4, 256, 0, s>>>(canvas, *part, (unsigned int)w, (unsigned int)h);
+  return (int)cudaGetLastError();
+}
+
 /* pixel-centre coordinates of every column and row (render.c:94-98), once per screen size; the float copies
    feed the conservative fp32 coverage pre-test of the raster */
 __global__ void k_pixel_tables(double *__restrict__ px, double *__restrict__ py, float *__restrict__ pxf, float *__restrict__ pyf,
@@ -289,10 +308,11 @@ extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int
    (triangle_hidden), or C3D_NO_BOX when the pre-test did not get that far */
 #define C3D_NO_BOX 0xffffffffffffffffull
 
-template <bool MAPPED>
+template <bool MAPPED, bool PEER>
 __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsigned long long entry, const unsigned int s,
                                                 const unsigned long long box, Pixel *__restrict__ canvas) {
   const unsigned int obj = C3D_ENTRY_OBJ(entry), code = C3D_ENTRY_CODE(entry);
+  const FieldView &f = entry_view<PEER>(p, entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
   Tri2D t;
@@ -300,13 +320,12 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
      within reach of the instruction cache while its warps sit in different phases */
 #pragma unroll
   for (int m = 0; m < 3; m++) {
-    const ProjectedVertex v = exact_vertex_t<MAPPED>(p, obj, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+    const ProjectedVertex v = exact_vertex_t<MAPPED>(p.cam, f, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
     if (0. == v.w) return;                          /* render.c:62-72 */
     t.q[m] = V3{v.x, v.y, v.z};
   }
   setup_projected(p.cam, t);
-  const unsigned long long mykey = ((unsigned long long)(obj + 1u) << C3D_KEY_OBJ_SHIFT)
-                                 | ((unsigned long long)k << 36) | ((unsigned long long)j << 20) | ((unsigned long long)i << 4) | s;
+  const unsigned long long mykey = winner_key(f, obj, i, j, k, s);
   /*
    * Coverage in two steps.  Most pixels of the +-1 pixel box are far outside the triangle, so each is first
    * tested with the three edge functions in fp32 and dropped when one of them is below -tol, tol being a
@@ -357,6 +376,7 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
         const int b = __ffs((int)maybe) - 1;
         maybe &= maybe - 1u;
         const long long pi = i0 + (b & 7), pj = j0 + (b >> 3);
+        if (PEER && !pixel_owned(p.part, (int)pi, (int)pj)) continue;     /* another rank draws that tile */
         double w[3];
         if (pixel_weights(t, __ldg(p.px + pi), __ldg(p.py + pj), w)) {
           submit_fragment(canvas + pj * p.cam.w + pi, ord_of(pixel_depth(t, w)), mykey);
@@ -367,8 +387,10 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsi
 }
 
 /* every pixel of [ceil(x0), floor(x1)] x [ceil(y0), floor(y1)] (clipped to the screen) holds a depth above `limit`;
-   an empty range is hidden only when `empty_is_hidden` (no pixel centre can be covered); more than 64 pixels: not decided */
-__device__ __forceinline__ bool region_hidden(const Pixel *__restrict__ canvas, const CullCam &q, const float x0, const float x1,
+   an empty range is hidden only when `empty_is_hidden` (no pixel centre can be covered); more than 64 pixels: not decided.
+   PEER (screen-partitioned frame): only this rank's pixels count, the others are not drawn here at all. */
+template <bool PEER>
+__device__ __forceinline__ bool region_hidden(const Pixel *__restrict__ canvas, const CullCam &q, const Partition &part, const float x0, const float x1,
                                               const float y0, const float y1, const bool empty_is_hidden, const unsigned long long limit) {
   const int imin = max(0, (int)ceilf(x0)), imax = min(q.w - 1, (int)floorf(x1));
   const int jmin = max(0, (int)ceilf(y0)), jmax = min(q.h - 1, (int)floorf(y1));
@@ -377,6 +399,7 @@ __device__ __forceinline__ bool region_hidden(const Pixel *__restrict__ canvas, 
   for (int pj = jmin; pj <= jmax; pj++) {
     const unsigned long long *row = reinterpret_cast<const unsigned long long *>(canvas + (long long)pj * q.w);
     for (int pi = imin; pi <= imax; pi++) {
+      if (PEER && !pixel_owned(part, pi, pj)) continue;
       if (__ldcg(row + 2 * pi) <= limit) return false;
     }
   }
@@ -417,7 +440,7 @@ __device__ __forceinline__ bool hiz_hidden(const HiZ &z, const CullCam &q, const
  * fp32 error (0.25 pixel, 1e-4 relative depth); anything doubtful is kept.
  * With a depth complexity of ~20 most cubes of a turbulent field are hidden.
  */
-template <bool MAPPED>
+template <bool MAPPED, bool PEER>
 __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned long long entry, const Pixel *__restrict__ canvas, const HiZ &hiz) {
   /* A triangle whose vertices have collapsed onto one cube corner is drawn by the reference as a blob: the
      clamped area (render.c:103-106) makes all three weights +-0, every pixel of the +-1 pixel box passes the
@@ -426,7 +449,7 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
      cubes of every 4 x 8 patch where that cannot be excluded (C3D_ENTRY_IRREGULAR) and those are never culled. */
   if (C3D_ENTRY_IRREGULAR(entry)) return false;
   const CullCam &q = p.cull;
-  const FieldView &f = p.view[C3D_ENTRY_OBJ(entry)];
+  const FieldView &f = entry_view<PEER>(p, entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
   float xlo = 3.e38f, xhi = -3.e38f, ylo = 3.e38f, yhi = -3.e38f, znear = -3.e38f, tlo = 3.e38f, thi = -3.e38f;
   if (MAPPED && nullptr != f.map) {
@@ -481,8 +504,8 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
      render.c:81-89 is just the search range), and every triangle lies inside the hull of the corners:
      the pixels to look at are those whose centre (i + 0.5) / W - 0.5 falls within the bounds, +- 0.05 pixel */
   const float X0 = (0.5f + xlo) * q.W - 0.55f, X1 = (0.5f + xhi) * q.W - 0.45f, Y0 = (0.5f + ylo) * q.H - 0.55f, Y1 = (0.5f + yhi) * q.H - 0.45f;
-  if (nullptr != hiz.tile && hiz_hidden(hiz, q, X0, X1, Y0, Y1, limit)) return true;
-  return region_hidden(canvas, q, X0, X1, Y0, Y1, true, limit);
+  if (!PEER && nullptr != hiz.tile && hiz_hidden(hiz, q, X0, X1, Y0, Y1, limit)) return true;
+  return region_hidden<PEER>(canvas, q, p.part, X0, X1, Y0, Y1, true, limit);
 }
 
 /*
@@ -500,13 +523,13 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
  * stays below 0.01 pixel on screens up to 2^20 pixels wide; 0.05 pixel is added on top.  Anything that
  * does not fit these assumptions (ferr > 0.02, vertices near the screen plane, NaN) keeps the triangle.
  */
-template <bool MAPPED>
+template <bool MAPPED, bool PEER>
 __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsigned long long entry, const unsigned int s,
                                                 const Pixel *__restrict__ canvas, unsigned long long &box) {
   box = C3D_NO_BOX;
   const CullCam &q = p.cull;
   const unsigned int code = C3D_ENTRY_CODE(entry);
-  const FieldView &f = p.view[C3D_ENTRY_OBJ(entry)];
+  const FieldView &f = entry_view<PEER>(p, entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
   const long long base = k * f.sz + j * f.sy + i;
@@ -571,15 +594,16 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsi
     box = (unsigned long long)imin | ((unsigned long long)imax << 16) | ((unsigned long long)jmin << 32) | ((unsigned long long)jmax << 48);
   }
   const double zcap = (double)znear + (1.e-4 * fabs((double)znear) + 1.e-6 + 2. * (double)zslack);
-  return region_hidden(canvas, q, xlo, xhi, ylo, yhi, true, ord_of(zcap));
+  return region_hidden<PEER>(canvas, q, p.part, xlo, xhi, ylo, yhi, true, ord_of(zcap));
 }
 
-/* list entry + triangle index in its four spare bits */
+/* list entry + triangle index in its top four bits (the irregular flag has been used by then; the source rank of a
+   screen-partitioned frame, which lives in three of those bits, travels in a side array of the queue) */
 #define C3D_TRI_PACK(entry, s) (((entry) & 0x0fffffffffffffffull) | ((unsigned long long)(s) << 60))
 #define C3D_TRI_ENTRY(q) ((q) & 0x0fffffffffffffffull)
 #define C3D_TRI_INDEX(q) ((unsigned int)((q) >> 60))
 
-template <int MINB, bool MAPPED>
+template <int MINB, bool MAPPED, bool PEER>
 __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ FrameParams p, const unsigned long long *__restrict__ list,
                                                      const unsigned long long *__restrict__ count, const unsigned long long capacity,
                                                      Pixel *__restrict__ canvas, unsigned long long *__restrict__ culled,
@@ -588,6 +612,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
   __shared__ unsigned int s_first[4][32];
   __shared__ unsigned long long s_queue[4][64];       /* triangles that passed the pre-test, waiting for a full warp */
   __shared__ unsigned long long s_qbox[4][64];        /* ... and the pixel boxes the pre-test left them */
+  __shared__ unsigned char s_qsrc[4][PEER ? 64 : 1];  /* ... and the rank their cube indices refer to */
   unsigned long long n = *count;
   if (n > capacity) n = capacity;
   const unsigned int lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -603,7 +628,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
     if (base + lane < n) {
       entry = __ldg(list + base + lane);
       ntri = __ldg(p.tab.count + C3D_ENTRY_CODE(entry));
-      if (p.cull.enabled && cube_hidden<MAPPED>(p, entry, canvas, hiz)) ntri = 0u;
+      if (p.cull.enabled && cube_hidden<MAPPED, PEER>(p, entry, canvas, hiz)) ntri = 0u;
     }
     const unsigned int alive = __ballot_sync(C3D_FULL_MASK, ntri > 0u);
     hidden_total += __popc(__ballot_sync(C3D_FULL_MASK, base + lane < n)) - __popc(alive);
@@ -631,11 +656,13 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
       const unsigned int src = (before + __popc(starts & (0xffffffffu >> (31u - lane))) - 1u) & 31u;
       bool keep = false;
       unsigned long long mine = 0ull, mybox = C3D_NO_BOX;
+      unsigned int mysrc = 0u;
       if (t0 + lane < total) {
         const unsigned long long e = s_entry[wid][src];
         const unsigned int s = t0 + lane - s_first[wid][src];
         mine = C3D_TRI_PACK(e, s);
-        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden<MAPPED>(p, e, s, canvas, mybox));
+        mysrc = C3D_ENTRY_SRC(e);
+        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden<MAPPED, PEER>(p, e, s, canvas, mybox));
       }
       const unsigned int kept = __ballot_sync(C3D_FULL_MASK, keep);
       hidden_tris += __popc(__ballot_sync(C3D_FULL_MASK, t0 + lane < total)) - __popc(kept);
@@ -643,26 +670,30 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
         const unsigned int at = queued + __popc(kept & ((1u << lane) - 1u));
         s_queue[wid][at] = mine;
         s_qbox[wid][at] = mybox;
+        if (PEER) s_qsrc[wid][at] = (unsigned char)mysrc;
       }
       queued += __popc(kept);
       __syncwarp();
       if (queued >= 32u) {
         /* a full warp of triangles that need the exact treatment */
         const unsigned long long q = s_queue[wid][lane], qb = s_qbox[wid][lane];
+        const unsigned long long qs = PEER ? (unsigned long long)s_qsrc[wid][lane] << C3D_ENTRY_SRC_SHIFT : 0ull;
         const unsigned long long rest = (lane + 32u < queued) ? s_queue[wid][lane + 32u] : 0ull;
         const unsigned long long restb = (lane + 32u < queued) ? s_qbox[wid][lane + 32u] : 0ull;
+        const unsigned char rests = (PEER && lane + 32u < queued) ? s_qsrc[wid][lane + 32u] : (unsigned char)0;
         __syncwarp();
-        if (lane + 32u < queued) { s_queue[wid][lane] = rest; s_qbox[wid][lane] = restb; }
+        if (lane + 32u < queued) { s_queue[wid][lane] = rest; s_qbox[wid][lane] = restb; if (PEER) s_qsrc[wid][lane] = rests; }
         queued -= 32u;
         __syncwarp();
-        raster_triangle<MAPPED>(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), qb, canvas);
+        raster_triangle<MAPPED, PEER>(p, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), qb, canvas);
       }
     }
   }
   __syncwarp();
   if (lane < queued) {
     const unsigned long long q = s_queue[wid][lane];
-    raster_triangle<MAPPED>(p, C3D_TRI_ENTRY(q), C3D_TRI_INDEX(q), s_qbox[wid][lane], canvas);
+    const unsigned long long qs = PEER ? (unsigned long long)s_qsrc[wid][lane] << C3D_ENTRY_SRC_SHIFT : 0ull;
+    raster_triangle<MAPPED, PEER>(p, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), s_qbox[wid][lane], canvas);
   }
   if (0u == lane && nullptr != culled) {
     if (hidden_total > 0u) atomicAdd(culled, (unsigned long long)hidden_total);
@@ -686,10 +717,13 @@ extern "C" int c3d_k_raster(const FrameParams *p, const unsigned long long *list
   /* the converter-table branches are compiled out unless an object of this frame has a tabulated converter */
   bool mapped = false;
   for (unsigned int n = 0; n < p->ncontours; n++) mapped = mapped || (nullptr != p->view[n].map);
+  const bool peer = p->part.nranks > 1;      /* screen-partitioned frame: entries name their source rank, identity converters only */
+  if (peer && mapped) return (int)cudaErrorInvalidValue;
 #define C3D_RASTER_LAUNCH(MINB, PER_SM) \
   do { \
-    if (mapped) k_raster<MINB, true><<<sm_count * PER_SM, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end); \
-    else k_raster<MINB, false><<<sm_count * PER_SM, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end); \
+    if (peer) k_raster<MINB, false, true><<<sm_count * PER_SM, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end); \
+    else if (mapped) k_raster<MINB, true, false><<<sm_count * PER_SM, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end); \
+    else k_raster<MINB, false, false><<<sm_count * PER_SM, 128, 0, s>>>(*p, list, count, capacity, canvas, culled, hiz, part_begin, part_end); \
   } while (0)
   if (occ >= 8) C3D_RASTER_LAUNCH(8, 16);
   else if (occ >= 6) C3D_RASTER_LAUNCH(6, 12);
@@ -729,16 +763,21 @@ extern "C" int c3d_k_hiz_build(const Pixel *canvas, long long w, long long h, un
   return (int)cudaGetLastError();
 }
 
-/* flag[0] = 1 when a work buffer of this frame overflowed (agreed across ranks by ncclMax before anybody redoes the frame) */
+/* flag[0] = 1 when a work buffer of this frame overflowed (agreed across ranks by a maximum before anybody redoes the frame) */
 __global__ void k_overflow_flag(const unsigned long long *__restrict__ nrec, const unsigned long long rec_cap,
                                 const unsigned long long *__restrict__ nlist, const unsigned long long list_cap,
-                                unsigned long long *__restrict__ flag) {
-  *flag = (*nrec > rec_cap || *nlist > list_cap) ? 1ull : 0ull;
+                                const unsigned long long *__restrict__ nout, const unsigned long long out_cap,
+                                const unsigned long long *__restrict__ nover, unsigned long long *__restrict__ flag) {
+  bool over = *nrec > rec_cap || *nlist > list_cap;
+  if (nullptr != nout) over = over || *nout > out_cap;
+  if (nullptr != nover) over = over || 0ull != *nover;
+  *flag = over ? 1ull : 0ull;
 }
 
 extern "C" int c3d_k_overflow_flag(const unsigned long long *nrec, unsigned long long rec_cap, const unsigned long long *nlist,
-                                   unsigned long long list_cap, unsigned long long *flag, cudaStream_t s) {
-  k_overflow_flag<<<1, 1, 0, s>>>(nrec, rec_cap, nlist, list_cap, flag);
+                                   unsigned long long list_cap, const unsigned long long *nout, unsigned long long out_cap,
+                                   const unsigned long long *nover, unsigned long long *flag, cudaStream_t s) {
+  k_overflow_flag<<<1, 1, 0, s>>>(nrec, rec_cap, nlist, list_cap, nout, out_cap, nover, flag);
   return (int)cudaGetLastError();
 }
 

@@ -22,6 +22,7 @@
 #include <dlfcn.h>
 #include "contour3d_b200.h"
 #include "c3d_internal.h"
+#include "c3d_peer.h"
 
 #define C3D_STR__(x) #x
 #define C3D_STR_(x) C3D_STR__(x)
@@ -92,6 +93,12 @@ static int nccl_load(void) {
   return 0;
 }
 
+/* what a rank tells the others about its block of a field (exchanged once, when the field is created) */
+struct FieldGeom {
+  int coords[3];                      /* position in the process grid */
+  unsigned int mysizes[3], offsets[3], ext[3], ext_off[3], lo[3];
+};
+
 struct c3d_field {
   c3d_decomp_t decomp;
   size_t gl[3], mysizes[3], offsets[3];
@@ -99,18 +106,44 @@ struct c3d_field {
   int elem_bytes;
   void *data;
   bool halo_valid;
+  bool borrowed;                      /* data is the caller's device array (c3d_field_wrap): never written, never freed */
+  bool shared;                        /* every rank has every other rank's array mapped (peer[]) and knows its shape (geom[]) */
+  void *peer[C3D_MAX_RANKS];
+  FieldGeom geom[C3D_MAX_RANKS];
 };
 
-enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_CULLED_TRIS = 3, CNT_SHADE_SPILL = 4, CNT_OVERFLOW = 5, CNT_OBJ = 6, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS, CNT_TOTAL = CNT_SNAP + C3D_MAX_OBJECTS + 1 };
-#define C3D_HIZ_CUTS_MULTI "6,20,40"
+enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_CULLED_TRIS = 3, CNT_SHADE_SPILL = 4, CNT_OVERFLOW = 5, CNT_OBJ = 6, CNT_SNAP = CNT_OBJ + C3D_MAX_OBJECTS,
+       CNT_OUT = CNT_SNAP + C3D_MAX_OBJECTS + 1,      /* screen-partitioned frames: entries this rank addressed to the ranks (outbox cursor) */
+       CNT_SEG_OVER,                                  /* ... pixels / work items that found no room (sized for the worst case: stays 0) */
+       CNT_PEER,                                      /* ... host copy only: a flag barrier timed out */
+       CNT_TOTAL };
+#define C3D_HIZ_CUTS_MULTI ""
 #define C3D_HIZ_CUTS_SINGLE ""
 enum { EV_START, EV_HALO, EV_CLEAR, EV_SWEEP, EV_EXPAND, EV_RASTER, EV_LINES, EV_RESOLVE, EV_REDUCE0, EV_SHADE, EV_REDUCE1, EV_PACK, EV_DOWNLOAD, EV_COUNT };
+
+/*
+ * Device memory of a screen-partitioned frame that OTHER ranks read or write: one allocation per rank, mapped by all.
+ * The layout up to the outbox depends only on (ranks, screen, seg_cap), so every rank can address every other rank's;
+ * the outbox comes last because its capacity is the owner's business (readers go by seg_start and the histogram).
+ */
+struct Exchange {
+  char *base;
+  void *peer[C3D_MAX_RANKS];
+  size_t bytes, npix, width, height, seg_cap, out_cap;
+  int nranks;
+  bool stale;                          /* must be re-created (and re-mapped by everybody) before the next frame */
+  size_t off_flags, off_seg_start, off_nseg, off_hist, off_rgba, off_seg, off_out;
+};
 
 struct c3d_context {
   int device, rank, size, sm_count;
   cudaStream_t stream;
   ncclComm_t comm;
   bool has_comm;
+  c3d_peer peer;                                   /* device-to-device exchange between the ranks of this node */
+  Exchange xa;
+  unsigned long long *merge_base, *part_cursors;   /* C3D_DEPTH_BUCKETS x ranks each: merged-list offsets / outbox cursors */
+  int tile_shift;                                  /* log2 of the screen-tile edge of partitioned frames */
   void *table_mem;
   DevTables tab;
   /* canvases */
@@ -159,33 +192,23 @@ extern "C" const char *c3d_version(void) { return "contour3d_b200 0.1 (sm_100a, 
 extern "C" int c3d_nccl_unique_id(void *id128) {
   if (NULL == id128) return c3d_error("c3d_nccl_unique_id: NULL output");
   static_assert(sizeof(ncclUniqueId) == C3D_NCCL_ID_BYTES, "ncclUniqueId size");
-  if (0 != nccl_load()) return 1;
+  if (0 != nccl_load()) {
+    /* no NCCL on this host: the id still names the ranks' shared-memory board (c3d_peer.cu); any 128 random bytes will do */
+    FILE *fp = fopen("/dev/urandom", "rb");
+    const size_t got = NULL != fp ? fread(id128, 1, C3D_NCCL_ID_BYTES, fp) : 0;
+    if (NULL != fp) fclose(fp);
+    return C3D_NCCL_ID_BYTES == got ? 0 : c3d_error("could not create a unique id");
+  }
   ncclUniqueId id;
   NCCL_OK(g_nccl.GetUniqueId(&id));
   memcpy(id128, &id, sizeof(id));
   return 0;
 }
 
-extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank, int comm_size, const void *nccl_id128) {
-  if (NULL == out) return c3d_error("c3d_context_create: NULL output");
-  *out = NULL;
-  if (comm_size < 1 || comm_rank < 0 || comm_rank >= comm_size) return c3d_error("c3d_context_create: bad rank %d of %d", comm_rank, comm_size);
-  int ndev = 0;
-  const cudaError_t probe = cudaGetDeviceCount(&ndev);
-  if (cudaSuccess != probe || ndev < 1) {
-    return c3d_error("no usable CUDA device (%s); this library has no CPU path", cudaSuccess != probe ? cudaGetErrorString(probe) : "device count is 0");
-  }
-  if (device < 0) device = comm_rank % ndev;
-  if (device >= ndev) return c3d_error("device %d requested but only %d present", device, ndev);
-  CUDA_OK(cudaSetDevice(device));
+static int context_init(c3d_context *ctx, const int comm_rank, const int comm_size, const void *nccl_id128) {
   cudaDeviceProp prop;
-  CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) return c3d_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-  c3d_context *ctx = (c3d_context *)calloc(1, sizeof(c3d_context));
-  if (NULL == ctx) return c3d_error("out of host memory");
-  ctx->device = device;
-  ctx->rank = comm_rank;
-  ctx->size = comm_size;
+  CUDA_OK(cudaGetDeviceProperties(&prop, ctx->device));
+  if (prop.major < 10) return c3d_error("device %d is sm_%d%d; this library is built for sm_100a only", ctx->device, prop.major, prop.minor);
   ctx->sm_count = prop.multiProcessorCount;
   CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (int e = 0; e < EV_COUNT; e++) CUDA_OK(cudaEventCreate(&ctx->ev[e]));
@@ -195,9 +218,10 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   c3d_tables_t *host_tab = (c3d_tables_t *)malloc(sizeof(c3d_tables_t));
   if (NULL == host_tab) return c3d_error("out of host memory");
   c3d_tables_build(host_tab);
-  CUDA_OK(cudaMalloc(&ctx->table_mem, sizeof(c3d_tables_t)));
-  CUDA_OK(cudaMemcpy(ctx->table_mem, host_tab, sizeof(c3d_tables_t), cudaMemcpyHostToDevice));
+  cudaError_t err = cudaMalloc(&ctx->table_mem, sizeof(c3d_tables_t));
+  if (cudaSuccess == err) err = cudaMemcpy(ctx->table_mem, host_tab, sizeof(c3d_tables_t), cudaMemcpyHostToDevice);
   free(host_tab);
+  if (cudaSuccess != err) return c3d_error("case tables: %s", cudaGetErrorString(err));
   const char *tb = (const char *)ctx->table_mem;
   ctx->tab.count = (const uint8_t *)(tb + offsetof(c3d_tables_t, count));
   ctx->tab.code24 = (const uint32_t *)(tb + offsetof(c3d_tables_t, code24));
@@ -213,8 +237,8 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   CUDA_OK(cudaMalloc(&ctx->bucket_cursors, C3D_DEPTH_BUCKETS * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->views_dev, C3D_MAX_OBJECTS * sizeof(FieldView)));
   /* Hi-Z refresh points of the raster (see frame_once): "a,b,..." in 1/64ths of the nearest-first list, "" or "0" = none.
-     Several ranks: what the others have drawn in front is only known through this table, so it is on by default;
-     every rank must use the same cuts (each refresh is a collective). */
+     Off by default (measured: the frame is bounded by the front rank, which has nothing to cull and only waits at the extra
+     collectives); every rank must use the same cuts (each refresh is a collective). */
   {
     const char *env = getenv("CONTOUR3D_HIZ_CUTS");
     const char *spec = NULL != env ? env : (comm_size > 1 ? C3D_HIZ_CUTS_MULTI : C3D_HIZ_CUTS_SINGLE);
@@ -227,23 +251,74 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
       spec = (',' == *end) ? end + 1 : end;
     }
   }
+  {
+    const char *env = getenv("CONTOUR3D_TILE_SHIFT");
+    ctx->tile_shift = (NULL != env && atoi(env) >= 3 && atoi(env) <= 10) ? atoi(env) : 6;
+  }
   if (comm_size > 1) {
-    if (NULL == nccl_id128) return c3d_error("c3d_context_create: %d ranks need an NCCL unique id", comm_size);
-    if (0 != nccl_load()) return 1;
-    ncclUniqueId id;
-    memcpy(&id, nccl_id128, sizeof(id));
-    NCCL_OK(g_nccl.CommInitRank(&ctx->comm, comm_size, id, comm_rank));
-    ctx->has_comm = true;
+    if (NULL == nccl_id128) return c3d_error("c3d_context_create: %d ranks need the shared 128-byte id (c3d_nccl_unique_id)", comm_size);
+    /* 1. device-to-device exchange between the ranks of this node (CUDA IPC): the data path of multi-rank frames */
+    if (0 != c3d_peer_init(&ctx->peer, comm_rank, comm_size, nccl_id128, ctx->device)) return 1;
+    if (ctx->peer.active) {
+      CUDA_OK(cudaMalloc(&ctx->merge_base, (size_t)C3D_DEPTH_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
+      CUDA_OK(cudaMalloc(&ctx->part_cursors, (size_t)C3D_DEPTH_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
+    }
+    /* 2. NCCL communicator: frames with coordinate converters and nodes without peer access reduce whole images through it.
+          Ranks that share a GPU (test boxes) cannot form one: they have the peer path only. */
+    if (!ctx->peer.shared_device) {
+      if (0 != nccl_load()) return 1;
+      ncclUniqueId id;
+      memcpy(&id, nccl_id128, sizeof(id));
+      NCCL_OK(g_nccl.CommInitRank(&ctx->comm, comm_size, id, comm_rank));
+      ctx->has_comm = true;
+    } else if (!ctx->peer.active) {
+      return c3d_error("ranks share a GPU and cannot map each other's memory: no way to exchange data");
+    }
+  }
+  return 0;
+}
+
+extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank, int comm_size, const void *nccl_id128) {
+  if (NULL == out) return c3d_error("c3d_context_create: NULL output");
+  *out = NULL;
+  if (comm_size < 1 || comm_rank < 0 || comm_rank >= comm_size) return c3d_error("c3d_context_create: bad rank %d of %d", comm_rank, comm_size);
+  int ndev = 0;
+  const cudaError_t probe = cudaGetDeviceCount(&ndev);
+  if (cudaSuccess != probe || ndev < 1) {
+    return c3d_error("no usable CUDA device (%s); this library has no CPU path", cudaSuccess != probe ? cudaGetErrorString(probe) : "device count is 0");
+  }
+  if (device < 0) device = comm_rank % ndev;
+  if (device >= ndev) return c3d_error("device %d requested but only %d present", device, ndev);
+  CUDA_OK(cudaSetDevice(device));
+  c3d_context *ctx = (c3d_context *)calloc(1, sizeof(c3d_context));
+  if (NULL == ctx) return c3d_error("out of host memory");
+  ctx->device = device;
+  ctx->rank = comm_rank;
+  ctx->size = comm_size;
+  if (0 != context_init(ctx, comm_rank, comm_size, nccl_id128)) {
+    c3d_context_destroy(ctx);        /* releases whatever had been created */
+    return 1;
   }
   *out = ctx;
   return 0;
 }
 
+static void release_exchange(c3d_context *ctx) {
+  if (NULL != ctx->xa.base) {
+    c3d_peer_unshare(&ctx->peer, ctx->xa.peer);
+    cudaFree(ctx->xa.base);
+  }
+  memset(&ctx->xa, 0, sizeof(ctx->xa));
+}
+
 extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   if (NULL == ctx) return 0;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
+  release_exchange(ctx);
+  cudaFree(ctx->merge_base); cudaFree(ctx->part_cursors);
+  c3d_peer_destroy(&ctx->peer);
   cudaFree(ctx->table_mem);
   cudaFree(ctx->shade.work); cudaFree(ctx->shade.counters); cudaFree(ctx->shade.pix); cudaFree(ctx->shade.table); cudaFree(ctx->shade.vlist); cudaFree(ctx->shade.vn);
   cudaFree(ctx->canvas); cudaFree(ctx->depth_local); cudaFree(ctx->depth_global); cudaFree(ctx->hiz); cudaFree(ctx->pixel_xy); cudaFree(ctx->rgba); cudaFree(ctx->ppm_dev);
@@ -252,12 +327,19 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   if (ctx->counts_host) cudaFreeHost(ctx->counts_host);
   cudaFree(ctx->views_dev); cudaFree(ctx->lines_dev); cudaFree(ctx->grids_dev); cudaFree(ctx->halo_buf); cudaFree(ctx->arena_dev);
   if (ctx->arena_host) cudaFreeHost(ctx->arena_host);
-  for (int e = 0; e < EV_COUNT; e++) cudaEventDestroy(ctx->ev[e]);
-  for (int e = 0; e <= C3D_MAX_OBJECTS; e++) cudaEventDestroy(ctx->ev_sweep[e]);
-  for (int e = 0; e < 2 * C3D_MAX_OBJECTS; e++) cudaEventDestroy(ctx->ev_upload[e]);
-  cudaStreamDestroy(ctx->stream);
+  for (int e = 0; e < EV_COUNT; e++) if (ctx->ev[e]) cudaEventDestroy(ctx->ev[e]);
+  for (int e = 0; e <= C3D_MAX_OBJECTS; e++) if (ctx->ev_sweep[e]) cudaEventDestroy(ctx->ev_sweep[e]);
+  for (int e = 0; e < 2 * C3D_MAX_OBJECTS; e++) if (ctx->ev_upload[e]) cudaEventDestroy(ctx->ev_upload[e]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
   free(ctx);
   return 0;
+}
+
+/* 0: one rank; 1: whole-image reduction through NCCL; 2: screen-partitioned over peer memory */
+extern "C" int c3d_context_exchange_mode(const c3d_context_t *ctx) {
+  if (NULL == ctx || ctx->size < 2) return 0;
+  return ctx->peer.active ? 2 : 1;
 }
 
 extern "C" int c3d_context_device(const c3d_context_t *ctx) { return ctx ? ctx->device : -1; }
@@ -336,8 +418,62 @@ extern "C" int c3d_field_create(c3d_context_t *ctx, const c3d_decomp_t *decomp, 
   }
   CUDA_OK(cudaSetDevice(ctx->device));
   const cudaError_t err = cudaMalloc(&f->data, total * (size_t)elem_bytes);
-  if (cudaSuccess != err) { free(f); return c3d_error("failed to allocate %zu bytes of device memory for a field: %s", total * (size_t)elem_bytes, cudaGetErrorString(err)); }
+  if (cudaSuccess != err) {
+    cudaGetLastError();
+    f->data = NULL;
+    c3d_error("failed to allocate %zu bytes of device memory for a field: %s", total * (size_t)elem_bytes, cudaGetErrorString(err));
+  }
+  if (ctx->peer.active) {
+    /* collective: every rank maps every other rank's array and learns its shape (a rank that could not allocate says so,
+       and then all of them fail together instead of one waiting for the others for ever) */
+    const int failed = c3d_peer_share(&ctx->peer, f->data, f->peer);
+    FieldGeom mine;
+    for (int d = 0; d < 3; d++) {
+      mine.coords[d] = decomp->myrank[d];
+      mine.mysizes[d] = (unsigned int)f->mysizes[d]; mine.offsets[d] = (unsigned int)f->offsets[d];
+      mine.ext[d] = (unsigned int)f->ext[d]; mine.ext_off[d] = (unsigned int)f->ext_off[d]; mine.lo[d] = (unsigned int)f->lo[d];
+    }
+    if (0 != failed || 0 != c3d_peer_allgather(&ctx->peer, &mine, sizeof(mine), f->geom)) {
+      if (NULL != f->data) { c3d_peer_unshare(&ctx->peer, f->peer); cudaFree(f->data); }
+      free(f);
+      return c3d_error("the ranks could not map each other's copy of a field");
+    }
+    f->shared = true;
+  } else if (NULL == f->data) {
+    free(f);
+    return 1;
+  }
   f->halo_valid = (1 == ctx->size);
+  *out = f;
+  return 0;
+}
+
+/* One rank, or a rank without neighbours: the array needs no halo room, so a DEVICE array of the caller can be swept where it
+   lies.  Returns 0 and a field that borrows `device_array` (never written, never freed), or 2 when that does not apply
+   (host pointer, another device, halo room needed) -- the caller then creates a field and uploads as usual. */
+extern "C" int c3d_field_wrap(c3d_context_t *ctx, const c3d_decomp_t *decomp, const size_t glsizes[3], int elem_bytes,
+                              const void *device_array, c3d_field_t **out) {
+  if (NULL == ctx || NULL == decomp || NULL == glsizes || NULL == device_array || NULL == out) return c3d_error("c3d_field_wrap: NULL argument");
+  *out = NULL;
+  if (4 != elem_bytes && 8 != elem_bytes) return c3d_error("element size must be 4 or 8 bytes, received %d", elem_bytes);
+  if (1 != ctx->size) return 2;
+  for (int d = 0; d < 3; d++) {
+    if (1 != decomp->nprocs[d]) return 2;
+  }
+  cudaPointerAttributes attr;
+  if (cudaSuccess != cudaPointerGetAttributes(&attr, device_array)) { cudaGetLastError(); return 2; }
+  if (cudaMemoryTypeDevice != attr.type || attr.device != ctx->device) return 2;
+  c3d_field *f = (c3d_field *)calloc(1, sizeof(c3d_field));
+  if (NULL == f) return c3d_error("out of host memory");
+  f->decomp = *decomp;
+  f->elem_bytes = elem_bytes;
+  for (int d = 0; d < 3; d++) {
+    f->gl[d] = f->mysizes[d] = f->ext[d] = glsizes[d];
+    f->offsets[d] = f->ext_off[d] = f->lo[d] = 0;
+  }
+  f->data = const_cast<void *>(device_array);
+  f->borrowed = true;
+  f->halo_valid = true;
   *out = f;
   return 0;
 }
@@ -345,7 +481,8 @@ extern "C" int c3d_field_create(c3d_context_t *ctx, const c3d_decomp_t *decomp, 
 extern "C" int c3d_field_destroy(c3d_context_t *ctx, c3d_field_t *field) {
   if (NULL == field) return 0;
   if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  cudaFree(field->data);
+  if (ctx && field->shared) c3d_peer_unshare(&ctx->peer, field->peer);
+  if (!field->borrowed) cudaFree(field->data);
   free(field);
   return 0;
 }
@@ -356,6 +493,7 @@ static inline char *interior_ptr(const c3d_field *f) {
 
 extern "C" int c3d_field_upload(c3d_context_t *ctx, c3d_field_t *f, const void *local) {
   if (NULL == ctx || NULL == f || NULL == local) return c3d_error("c3d_field_upload: NULL argument");
+  if (f->borrowed) return c3d_error("c3d_field_upload: the field borrows the caller's array (c3d_field_wrap)");
   CUDA_OK(cudaSetDevice(ctx->device));
   const size_t eb = (size_t)f->elem_bytes;
   const bool timed = ctx->nuploads < C3D_MAX_OBJECTS;
@@ -425,10 +563,59 @@ static int ensure_bytes(void **ptr, size_t *cap, const size_t need) {
  *   y: 2 rows x nx per interior plane, strided -> pack kernel + ncclSend/Recv
  *   z: 2 full extended planes, contiguous      -> ncclSend/Recv in place
  */
+/*
+ * The same exchange over peer memory: every rank PULLS its halo out of the neighbours' arrays (rows of the neighbour's
+ * interior for y, then -- after all y halos are in place -- two whole planes for z, which carry the fresh y halos into
+ * the corners).  `synced` = a flag barrier already stands between the neighbours' last writes and this call.
+ */
+static int field_exchange_peer(c3d_context *ctx, c3d_field *f, const bool synced, uint32_t *launches) {
+  cudaStream_t s = ctx->stream;
+  if (!synced) { LAUNCH_OK(c3d_peer_barrier(&ctx->peer, s)); *launches += 1; }
+  const long long nx = (long long)f->ext[0], sy = (long long)f->ext[0], sz = (long long)(f->ext[0] * f->ext[1]);
+  const bool ysplit = f->decomp.neighbours[1][0] >= 0 || f->decomp.neighbours[1][1] >= 0 || f->decomp.nprocs[1] > 1;
+  const bool zsplit = f->decomp.nprocs[2] > 1;
+  for (int side = 0; side < 2; side++) {
+    const int nb = f->decomp.neighbours[1][side];
+    if (nb < 0) continue;
+    const FieldGeom &g = f->geom[nb];
+    /* the two rows next to the shared face, planes of the common interior (same z block) */
+    const long long their_j0 = 0 == side ? (long long)g.lo[1] + g.mysizes[1] - 2 : (long long)g.lo[1];
+    const long long my_j0 = 0 == side ? 0 : (long long)(f->lo[1] + f->mysizes[1]);
+    LAUNCH_OK(c3d_k_halo_pull_y(f->data, f->peer[nb], f->elem_bytes, nx, sy, sz, (long long)g.ext[0], (long long)g.ext[0] * g.ext[1],
+                                (long long)f->lo[2], (long long)g.lo[2], (long long)f->mysizes[2], my_j0, their_j0, s));
+    *launches += 1;
+  }
+  if (zsplit) {
+    if (ysplit) { LAUNCH_OK(c3d_peer_barrier(&ctx->peer, s)); *launches += 1; }       /* everybody's y halos are in place */
+    for (int side = 0; side < 2; side++) {
+      const int nb = f->decomp.neighbours[2][side];
+      if (nb < 0) continue;
+      const FieldGeom &g = f->geom[nb];
+      const size_t their_plane = (size_t)g.ext[0] * g.ext[1], my_plane = (size_t)sz;
+      if (their_plane != my_plane) return c3d_error("z neighbour %d holds planes of another shape", nb);
+      const size_t their_k0 = 0 == side ? (size_t)g.lo[2] + g.mysizes[2] - 2 : (size_t)g.lo[2];
+      const size_t my_k0 = 0 == side ? 0 : f->lo[2] + f->mysizes[2];
+      LAUNCH_OK(c3d_k_halo_pull_z((char *)f->data + my_k0 * my_plane * (size_t)f->elem_bytes,
+                                  (const char *)f->peer[nb] + their_k0 * their_plane * (size_t)f->elem_bytes, f->elem_bytes, 2 * my_plane, s));
+      *launches += 1;
+    }
+  }
+  f->halo_valid = true;
+  return 0;
+}
+
 extern "C" int c3d_field_exchange(c3d_context_t *ctx, c3d_field_t *f) {
   if (NULL == ctx || NULL == f) return c3d_error("c3d_field_exchange: NULL argument");
   if (1 == ctx->size) { f->halo_valid = true; return 0; }
   CUDA_OK(cudaSetDevice(ctx->device));
+  if (f->shared) {
+    /* a barrier on both sides: the neighbours' arrays are complete before, and stay untouched until everybody has read */
+    uint32_t launches = 0;
+    if (0 != field_exchange_peer(ctx, f, false, &launches)) return 1;
+    LAUNCH_OK(c3d_peer_barrier(&ctx->peer, ctx->stream));
+    return 0;
+  }
+  if (!ctx->has_comm) return c3d_error("no communicator: the halo cannot be exchanged");
   const size_t eb = (size_t)f->elem_bytes;
   const long long nx = (long long)f->ext[0], sy = (long long)f->ext[0], sz = (long long)(f->ext[0] * f->ext[1]);
   const ncclDataType_t dt = 4 == f->elem_bytes ? ncclFloat : ncclDouble;
@@ -534,6 +721,7 @@ static int make_view(c3d_context *ctx, const c3d_field *f, const double *const g
   }
   LAUNCH_OK(c3d_k_to_float(grid_slot, (float *)(grid_slot + total), total, ctx->stream));
   v->map = NULL;
+  for (int d = 0; d < 3; d++) v->off[d] = (long long)f->ext_off[d];
   v->thr = threshold;
   v->thr_ge = smallest_float_above(threshold);
   v->color[0] = color[0]; v->color[1] = color[1]; v->color[2] = color[2];
@@ -552,23 +740,28 @@ static size_t table_length(const c3d_field *f, const c3d_positions_t *pos, const
 /*
  * Everything the kernels read besides the arrays, in ONE device arena filled with as few copies as possible
  * (a dozen small pageable copies cost more host time than the clear of a 4K canvas):
- *   [PosMap x nc][LineDev x nl] [doubles: grid coordinates of every object | converter tables | converted line points]
+ *   [PosMap x nc][LineDev x nl][FieldView x ranks x 16 (partitioned frames)]
+ *   [doubles: grid coordinates of every object | converter tables | converted line points]
  *   [floats: the same grid coordinates and tables rounded, for the visibility pre-tests]
- * The maps, lines and grid coordinates are staged in pinned memory and travel in one copy; tables and line points
- * (arbitrarily large, caller-owned) are copied from where they lie.
+ * The maps, lines, peer views and grid coordinates are staged in pinned memory and travel in one copy; tables and line
+ * points (arbitrarily large, caller-owned) are copied from where they lie.
+ * part: a screen-partitioned frame -- the GLOBAL coordinates are uploaded (every rank indexes them with the offsets of
+ * whichever rank's array a cube comes from) and *pviews receives the table of those arrays as seen through peer memory.
  */
 static int stage_frame(c3d_context *ctx, const size_t nc, const c3d_contour_t *contours, const size_t nl, const c3d_line_t *lines,
-                       std::vector<LineDev> &hl, FieldView *views, const LineDev **lines_dev) {
+                       std::vector<LineDev> &hl, FieldView *views, const LineDev **lines_dev, const bool part, const FieldView **pviews) {
   cudaStream_t s = ctx->stream;
   const size_t maps_bytes = round_up(nc * sizeof(PosMap), 256), lines_bytes = round_up(nl * sizeof(LineDev), 256);
+  const size_t pviews_bytes = part ? round_up((size_t)C3D_MAX_RANKS * 16 * sizeof(FieldView), 256) : 0;
   size_t grid_doubles = 0, table_doubles = 0, point_doubles = 0;
   for (size_t n = 0; n < nc; n++) {
     const c3d_field *f = contours[n].field;
     for (int d = 0; d < 3; d++) {
       if ((long long)f->ext[d] - 1 > C3D_MAX_AXIS) return c3d_error("extended array too large in direction %d (%zu points)", d, f->ext[d]);
+      if ((long long)f->gl[d] - 1 > C3D_MAX_AXIS) return c3d_error("array too large in direction %d (%zu points; winner keys hold 16-bit cube indices)", d, f->gl[d]);
       if (NULL == contours[n].grids[d]) return c3d_error("grid coordinates of direction %d are missing", d);
     }
-    grid_doubles += f->ext[0] + f->ext[1] + f->ext[2];
+    grid_doubles += part ? f->gl[0] + f->gl[1] + f->gl[2] : f->ext[0] + f->ext[1] + f->ext[2];
     if (NULL != contours[n].positions) {
       for (int c = 0; c < 3; c++) {
         if (NULL == contours[n].positions->table[c]) return c3d_error("contour object %zu: converter table %d is missing", n, c);
@@ -579,7 +772,7 @@ static int stage_frame(c3d_context *ctx, const size_t nc, const c3d_contour_t *c
   for (size_t n = 0; n < nl; n++) {
     if (NULL != lines[n].points) point_doubles += 3 * lines[n].nitems;
   }
-  const size_t doubles_at = maps_bytes + lines_bytes;
+  const size_t doubles_at = maps_bytes + lines_bytes + pviews_bytes;
   const size_t floats_at = round_up(doubles_at + (grid_doubles + table_doubles + point_doubles) * sizeof(double), 256);
   const size_t total = floats_at + (grid_doubles + table_doubles) * sizeof(float) + 256;
   const size_t staged = doubles_at + grid_doubles * sizeof(double);
@@ -593,6 +786,8 @@ static int stage_frame(c3d_context *ctx, const size_t nc, const c3d_contour_t *c
   }
   PosMap *maps_host = (PosMap *)ctx->arena_host;
   PosMap *maps_dev = (PosMap *)ctx->arena_dev;
+  FieldView *pviews_host = (FieldView *)(ctx->arena_host + maps_bytes + lines_bytes);
+  if (part) memset(pviews_host, 0, pviews_bytes);
   double *dbl_host = (double *)(ctx->arena_host + doubles_at);
   double *dbl_dev = (double *)(ctx->arena_dev + doubles_at);
   float *flt_dev = (float *)(ctx->arena_dev + floats_at);
@@ -606,10 +801,23 @@ static int stage_frame(c3d_context *ctx, const size_t nc, const c3d_contour_t *c
     v->sy = (long long)f->ext[0];
     v->sz = (long long)(f->ext[0] * f->ext[1]);
     for (int d = 0; d < 3; d++) {
-      memcpy(dbl_host + at, contours[n].grids[d] + f->ext_off[d], f->ext[d] * sizeof(double));
-      v->g[d] = dbl_dev + at;
-      v->gf[d] = flt_dev + at;
-      at += f->ext[d];
+      if (part) {
+        memcpy(dbl_host + at, contours[n].grids[d], f->gl[d] * sizeof(double));
+        v->g[d] = dbl_dev + at + f->ext_off[d];
+        v->gf[d] = flt_dev + at + f->ext_off[d];
+        for (int r = 0; r < ctx->size; r++) {
+          FieldView *pv = &pviews_host[C3D_PEER_VIEW(r, n)];
+          pv->g[d] = dbl_dev + at + f->geom[r].ext_off[d];
+          pv->gf[d] = flt_dev + at + f->geom[r].ext_off[d];
+        }
+        at += f->gl[d];
+      } else {
+        memcpy(dbl_host + at, contours[n].grids[d] + f->ext_off[d], f->ext[d] * sizeof(double));
+        v->g[d] = dbl_dev + at;
+        v->gf[d] = flt_dev + at;
+        at += f->ext[d];
+      }
+      v->off[d] = (long long)f->ext_off[d];
     }
     v->map = NULL;
     if (NULL != contours[n].positions) {
@@ -628,6 +836,21 @@ static int stage_frame(c3d_context *ctx, const size_t nc, const c3d_contour_t *c
     v->thr = contours[n].threshold;
     v->thr_ge = smallest_float_above(contours[n].threshold);
     v->color[0] = contours[n].color[0]; v->color[1] = contours[n].color[1]; v->color[2] = contours[n].color[2];
+    if (part) {
+      /* the same object as each rank holds it: that rank's block of the array, through peer memory */
+      for (int r = 0; r < ctx->size; r++) {
+        FieldView *pv = &pviews_host[C3D_PEER_VIEW(r, n)];
+        const FieldGeom &g = f->geom[r];
+        pv->data = f->peer[r];
+        pv->elem_bytes = f->elem_bytes;
+        for (int d = 0; d < 3; d++) { pv->n[d] = (long long)g.ext[d]; pv->off[d] = (long long)g.ext_off[d]; }
+        pv->sy = (long long)g.ext[0];
+        pv->sz = (long long)g.ext[0] * (long long)g.ext[1];
+        pv->map = NULL;
+        pv->thr = v->thr; pv->thr_ge = v->thr_ge;
+        pv->color[0] = v->color[0]; pv->color[1] = v->color[1]; pv->color[2] = v->color[2];
+      }
+    }
   }
   /* lines: deltas = (1 / (npoints - 1)) * (tail - head), line.c:138-140 */
   LineDev *lines_host = (LineDev *)(ctx->arena_host + maps_bytes);
@@ -655,6 +878,7 @@ static int stage_frame(c3d_context *ctx, const size_t nc, const c3d_contour_t *c
     lines_host[n] = hl[n];
   }
   *lines_dev = (const LineDev *)(ctx->arena_dev + maps_bytes);
+  *pviews = part ? (const FieldView *)(ctx->arena_dev + maps_bytes + lines_bytes) : NULL;
   if (staged > 0) CUDA_OK(cudaMemcpyAsync(ctx->arena_dev, ctx->arena_host, staged, cudaMemcpyHostToDevice, s));
   LAUNCH_OK(c3d_k_to_float(dbl_dev, flt_dev, grid_doubles + table_doubles, s));
   return 0;
@@ -687,7 +911,7 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
     CUDA_OK(cudaMalloc(&ctx->rgba, npix * 4));
     /* one word per pixel is an upper bound for any screen shape (a tile row / column may be partial) */
     CUDA_OK(cudaMalloc(&ctx->hiz, (npix / 8 + w + h + 64) * sizeof(unsigned long long)));
-    CUDA_OK(cudaMalloc(&ctx->shade.work, npix * 4));
+    CUDA_OK(cudaMalloc(&ctx->shade.work, npix * sizeof(WorkItem)));
     CUDA_OK(cudaMalloc(&ctx->shade.pix, npix * C3D_SHADE_PIX_BYTES));
     {
       /* four to eight slots per pixel: at the benchmark's resolution triangles are smaller than a pixel and 3.7 M winning
@@ -783,7 +1007,69 @@ static void make_cull(const Cam *c, CullCam *q) {
   const char *env = getenv("CONTOUR3D_NO_CULL");
   const bool off = NULL != env && '\0' != *env && '0' != *env;
   /* needs finite, non-degenerate constants and a screen that fits the int / float arithmetic of the test */
-  q->enabled = !off && fabs(c->d - c->nc) > 1.e-9 && isfinite(q->ax) && isfinite(q->ay) && c->w < 65535 && c->h < 65535;   /* pixel boxes travel as 16-bit fields (C3D_NO_BOX, c3d_kernels.cu) */
+  q->valid = fabs(c->d - c->nc) > 1.e-9 && isfinite(q->ax) && isfinite(q->ay) && c->w < 65535 && c->h < 65535;   /* pixel boxes travel as 16-bit fields (C3D_NO_BOX, c3d_kernels.cu) */
+  q->enabled = !off && q->valid;
+}
+
+/* ---- screen-partitioned frames: the memory the ranks share ---- */
+
+/* tiles of a w x h screen owned by rank r (the pattern of tile_owner(), c3d_internal.h) */
+static size_t own_tiles(const int nranks, const int r, const int tiles_x, const int tiles_y) {
+  size_t n = 0;
+  for (int ty = 0; ty < tiles_y; ty++) {
+    for (int tx = 0; tx < tiles_x; tx++) n += ((tx + 3 * ty) % nranks == r) ? 1 : 0;
+  }
+  return n;
+}
+
+/* collective: (re)creates this rank's exchange arena and maps everybody's */
+static int ensure_exchange(c3d_context *ctx, const size_t w, const size_t h, const size_t out_cap) {
+  Exchange &x = ctx->xa;
+  if (NULL != x.base && !x.stale && x.width == w && x.height == h && x.nranks == ctx->size) return 0;
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  const size_t keep_out = (NULL != x.base && x.out_cap > out_cap) ? x.out_cap : out_cap;
+  release_exchange(ctx);
+  const int n = ctx->size;
+  const int tiles_x = (int)((w + ((size_t)1 << ctx->tile_shift) - 1) >> ctx->tile_shift), tiles_y = (int)((h + ((size_t)1 << ctx->tile_shift) - 1) >> ctx->tile_shift);
+  size_t most = 0;
+  for (int r = 0; r < n; r++) most = std::max(most, own_tiles(n, r, tiles_x, tiles_y));
+  x.nranks = n;
+  x.width = w; x.height = h; x.npix = w * h;
+  x.seg_cap = most << (2 * ctx->tile_shift);          /* every pixel of my tiles may be won by cubes of ONE rank */
+  x.out_cap = keep_out;
+  size_t at = 0;
+  x.off_flags = at; at += 256;
+  x.off_seg_start = at; at += 256;
+  x.off_nseg = at; at += 256;
+  x.off_hist = at; at += round_up((size_t)n * C3D_DEPTH_BUCKETS * sizeof(unsigned int), 256);
+  x.off_rgba = at; at += round_up(x.npix * 4, 256);
+  x.off_seg = at; at += round_up((size_t)n * x.seg_cap * sizeof(WorkItem), 256);
+  x.off_out = at; at += x.out_cap * 8;
+  x.bytes = at;
+  void *base = NULL;
+  const cudaError_t err = cudaMalloc(&base, x.bytes);
+  if (cudaSuccess != err) { cudaGetLastError(); base = NULL; c3d_error("failed to allocate %zu bytes for the ranks' exchange buffers: %s", x.bytes, cudaGetErrorString(err)); }
+  if (NULL != base) cudaMemset(base, 0, x.off_hist);
+  if (0 != c3d_peer_share(&ctx->peer, base, x.peer)) {
+    if (NULL != base) cudaFree(base);
+    memset(&x, 0, sizeof(x));
+    return c3d_error("the ranks could not map each other's exchange buffers");
+  }
+  x.base = (char *)base;
+  x.stale = false;
+  return 0;
+}
+
+static bool frame_can_partition(const c3d_context *ctx, const size_t nc, const c3d_contour_t *contours) {
+  if (ctx->size < 2 || !ctx->peer.active || ctx->peer.broken) return false;
+  for (size_t n = 0; n < nc; n++) {
+    const c3d_field *f = contours[n].field;
+    if (!f->shared || NULL != contours[n].positions) return false;
+    if (0 != memcmp(f->gl, contours[0].field->gl, sizeof(f->gl)) || 0 != memcmp(&f->decomp, &contours[0].field->decomp, sizeof(f->decomp))) return false;
+    /* the tiled sweep (records) is the only producer of the partitioned lists: needs 16-byte rows, the same on every rank */
+    if (0 != (f->ext[0] * (size_t)f->elem_bytes) % 16) return false;
+  }
+  return true;
 }
 
 static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t nc, const c3d_contour_t *contours,
@@ -794,13 +1080,26 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   Cam cam;
   make_cam(scene, &cam);
   uint32_t launches = 0;
+  /* Several ranks: either the screen is partitioned (every rank draws its tiles from everybody's cubes, read through peer
+     memory; decided from properties all ranks share, so they agree without asking) or, with coordinate converters or without
+     peer access, every rank draws its own cubes and whole images are reduced through NCCL. */
+  const bool part = frame_can_partition(ctx, nc, contours);
+  if (ctx->size > 1 && !part && !ctx->has_comm) {
+    return c3d_error("this frame needs the NCCL path (coordinate converter, unaligned rows or objects of different shapes), but the ranks share a GPU");
+  }
+  c3d_peer *peer = &ctx->peer;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_START], s));
   /* halos */
+  if (part) { LAUNCH_OK(c3d_peer_barrier(peer, s)); launches += 1; }    /* every rank's arrays are complete; last frame's buffers are free */
   for (size_t n = 0; n < nc; n++) {
     c3d_field *f = (c3d_field *)contours[n].field;
     if (!f->halo_valid) {
-      if (0 != c3d_field_exchange(ctx, f)) return 1;
-      launches += 4;
+      if (part) {
+        if (0 != field_exchange_peer(ctx, f, true, &launches)) return 1;
+      } else {
+        if (0 != c3d_field_exchange(ctx, f)) return 1;
+        launches += 4;
+      }
     }
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_HALO], s));
@@ -818,7 +1117,33 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   FieldView *views = fp.view;
   std::vector<LineDev> hl(nl);
   const LineDev *lines_dev = NULL;
-  if (0 != stage_frame(ctx, nc, contours, nl, lines, hl, views, &lines_dev)) return 1;
+  if (0 != stage_frame(ctx, nc, contours, nl, lines, hl, views, &lines_dev, part, &fp.pviews)) return 1;
+  if (part) {
+    Partition &q = fp.part;
+    q.nranks = ctx->size;
+    q.me = ctx->rank;
+    q.tile_shift = ctx->tile_shift;
+    q.tiles_x = (int)((scene->width + ((size_t)1 << q.tile_shift) - 1) >> q.tile_shift);
+    q.tiles_y = (int)((scene->height + ((size_t)1 << q.tile_shift) - 1) >> q.tile_shift);
+    q.recip = 0xffffffffu / (unsigned int)q.nranks + 1u;
+    q.py = q.pz = 1;
+    if (nc > 0) {
+      /* which rank holds which block: told by the ranks themselves when the field was created (any Cartesian numbering) */
+      const c3d_field *f = contours[0].field;
+      q.py = f->decomp.nprocs[1];
+      q.pz = f->decomp.nprocs[2];
+      if (q.py * q.pz != ctx->size) return c3d_error("process grid %d x %d does not match %d ranks", q.py, q.pz, ctx->size);
+      for (int r = 0; r < ctx->size; r++) {
+        const FieldGeom &g = f->geom[r];
+        if (g.coords[1] < 0 || g.coords[1] >= q.py || g.coords[2] < 0 || g.coords[2] >= q.pz) return c3d_error("rank %d reports a position outside the process grid", r);
+        q.yoff[g.coords[1]] = (unsigned short)g.offsets[1];
+        q.zoff[g.coords[2]] = (unsigned short)g.offsets[2];
+        q.home[g.coords[1] * q.pz + g.coords[2]] = (unsigned char)r;
+      }
+      q.yoff[q.py] = (unsigned short)f->gl[1];
+      q.zoff[q.pz] = (unsigned short)f->gl[2];
+    }
+  }
   /* work buffers of the frame: patch records from the tiled sweeps, then one list entry per cut cube */
   if (nc > 0 && 0 == ctx->list_cap) {
     size_t want = 0;
@@ -840,8 +1165,17 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     CUDA_OK(cudaMalloc(&ctx->records, want * 32));
     ctx->rec_cap = want;
   }
+  if (part && 0 != ensure_exchange(ctx, scene->width, scene->height, std::max<size_t>(ctx->list_cap, 64))) return 1;
+  Exchange &xa = ctx->xa;
+  unsigned int *rgba_out = ctx->rgba;                /* where finished colours go: the writer's image */
+  if (part) rgba_out = (unsigned int *)((char *)xa.peer[0] + xa.off_rgba);
   CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, CNT_TOTAL * sizeof(unsigned long long), s));
-  LAUNCH_OK(c3d_k_clear(ctx->canvas, npix, s));
+  if (part) {
+    CUDA_OK(cudaMemsetAsync(xa.base + xa.off_nseg, 0, 256, s));
+    LAUNCH_OK(c3d_k_clear_part(ctx->canvas, &fp.part, cam.w, cam.h, ctx->sm_count, s));
+  } else {
+    LAUNCH_OK(c3d_k_clear(ctx->canvas, npix, s));
+  }
   launches += 1;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_CLEAR], s));
   /* 1. classification sweeps: contour objects that share an array share ONE pass over it (up to
@@ -885,6 +1219,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
         sweep_nthr[nsweeps] = (uint32_t)cnt;
         used_records = true;
       } else {
+        if (part) return c3d_error("internal: a partitioned frame met an array the tiled sweep cannot take");
         done[n] = true;
         CUDA_OK(cudaEventRecord(ctx->ev_sweep[nsweeps], s));
         LAUNCH_OK(c3d_k_sweep(&views[n], &r, (unsigned int)n, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->sm_count, s));
@@ -899,8 +1234,9 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   }
   CUDA_OK(cudaEventRecord(ctx->ev_sweep[nsweeps], s));
   CUDA_OK(cudaEventRecord(ctx->ev[EV_SWEEP], s));
-  if (used_records) {
-    /* range of the view depth n.(p - cam) over the corners of every array: the slabs of the front-to-back order */
+  if (used_records || part) {
+    /* range of the view depth n.(p - cam) over the corners of every array: the slabs of the front-to-back order.
+       Partitioned frames take the corners of the GLOBAL domain, so that a bucket means the same depth on every rank. */
     double near_depth = -DBL_MAX, far_depth = DBL_MAX;
     for (size_t n = 0; n < nc; n++) {
       const c3d_field *f = contours[n].field;
@@ -928,18 +1264,43 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
       for (int c = 0; c < 8; c++) {
         double depth = 0.;
         for (int d = 0; d < 3; d++) {
-          const size_t at = f->ext_off[d] + (((c >> d) & 1) ? f->ext[d] - 1 : 0);
+          const size_t first = part ? 0 : f->ext_off[d], count = part ? f->gl[d] : f->ext[d];
+          const size_t at = first + (((c >> d) & 1) ? count - 1 : 0);
           depth += cam.normal[d] * (contours[n].grids[d][at] - cam.cam[d]);
         }
         near_depth = std::max(near_depth, depth);
         far_depth = std::min(far_depth, depth);
       }
     }
-    const int sorted = fp.cull.enabled && near_depth > far_depth;
-    LAUNCH_OK(c3d_k_expand(&fp, sorted, (float)near_depth, (float)far_depth, ctx->records, ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->list,
-                           ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->bucket_hist, ctx->bucket_cursors,
-                           ctx->counts_dev + CNT_OBJ, (unsigned int)nc, ctx->sm_count, s));
-    launches += sorted ? 3 : 1;
+    if (part) {
+      /* 2a. every cut cube goes to the outbox of each rank whose screen tiles it can touch, nearest first */
+      if (!(near_depth > far_depth)) { near_depth = 1.; far_depth = 0.; }      /* degenerate / NaN coordinates: one bucket */
+      LAUNCH_OK(c3d_k_expand_part(&fp, (float)near_depth, (float)far_depth, ctx->records, ctx->counts_dev + CNT_REC, ctx->rec_cap,
+                                  (unsigned long long *)(xa.base + xa.off_out), ctx->counts_dev + CNT_OUT, xa.out_cap,
+                                  (unsigned int *)(xa.base + xa.off_hist), ctx->part_cursors, (unsigned long long *)(xa.base + xa.off_seg_start),
+                                  ctx->counts_dev + CNT_OBJ, (unsigned int)nc, ctx->sm_count, s));
+      launches += 3;
+    } else {
+      const int sorted = fp.cull.enabled && near_depth > far_depth;
+      LAUNCH_OK(c3d_k_expand(&fp, sorted, (float)near_depth, (float)far_depth, ctx->records, ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->list,
+                             ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->bucket_hist, ctx->bucket_cursors,
+                             ctx->counts_dev + CNT_OBJ, (unsigned int)nc, ctx->sm_count, s));
+      launches += sorted ? 3 : 1;
+    }
+  }
+  if (part) {
+    /* 2b. all outboxes are complete -> every rank pulls what is addressed to it into ONE nearest-first list */
+    LAUNCH_OK(c3d_peer_barrier(peer, s));
+    MergeSources ms;
+    memset(&ms, 0, sizeof(ms));
+    for (int r = 0; r < ctx->size; r++) {
+      const char *pb = (const char *)xa.peer[r];
+      ms.hist[r] = (const unsigned int *)(pb + xa.off_hist);
+      ms.seg_start[r] = (const unsigned long long *)(pb + xa.off_seg_start);
+      ms.outbox[r] = (const unsigned long long *)(pb + xa.off_out);
+    }
+    LAUNCH_OK(c3d_k_merge_lists(&ms, ctx->size, ctx->rank, ctx->merge_base, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, s));
+    launches += 3;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_EXPAND], s));
   /* 2. tessellate + rasterise every active cube, contours in one launch (src/contour3d/main.c:105-117) */
@@ -948,15 +1309,15 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
         rank has already hidden -- without this a slab behind its neighbours rasterises everything it owns.  The table is
         only ever a lower bound of the final depths, so the image cannot change (cube_hidden, c3d_kernels.cu). */
   if (nc > 0) {
-    const int ncuts = fp.cull.enabled ? ctx->nraster_cuts : 0;
+    const int ncuts = (fp.cull.enabled && !part) ? ctx->nraster_cuts : 0;
     const size_t ntiles = ((scene->width + C3D_HIZ_TILE - 1) / C3D_HIZ_TILE) * ((scene->height + C3D_HIZ_TILE - 1) / C3D_HIZ_TILE);
-    for (int part = 0; part <= ncuts; part++) {
-      const unsigned int begin = 0 == part ? 0u : (unsigned int)ctx->raster_cuts[part - 1];
-      const unsigned int end = part == ncuts ? C3D_RASTER_PARTS : (unsigned int)ctx->raster_cuts[part];
+    for (int cut = 0; cut <= ncuts; cut++) {
+      const unsigned int begin = 0 == cut ? 0u : (unsigned int)ctx->raster_cuts[cut - 1];
+      const unsigned int end = cut == ncuts ? C3D_RASTER_PARTS : (unsigned int)ctx->raster_cuts[cut];
       LAUNCH_OK(c3d_k_raster(&fp, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->canvas, ctx->counts_dev + CNT_CULLED,
-                             part > 0 ? ctx->hiz : NULL, begin, end, ctx->sm_count, s));
+                             cut > 0 ? ctx->hiz : NULL, begin, end, ctx->sm_count, s));
       launches += 1;
-      if (part < ncuts) {
+      if (cut < ncuts) {
         LAUNCH_OK(c3d_k_hiz_build(ctx->canvas, cam.w, cam.h, ctx->hiz, ctx->sm_count, s));
         launches += 1;
         if (ctx->size > 1) NCCL_OK(g_nccl.AllReduce(ctx->hiz, ctx->hiz, ntiles, ncclUint64, ncclMax, ctx->comm, s));
@@ -968,42 +1329,87 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   LAUNCH_OK(c3d_k_lines(&cam, lines_dev, hl.data(), nl, nc, ctx->canvas, s));
   if (nl > 0) launches += 1;
   CUDA_OK(cudaEventRecord(ctx->ev[EV_LINES], s));
-  CUDA_OK(cudaEventRecord(ctx->ev[EV_RESOLVE], s));
-  /* 4. nearest depth across ranks (replaces the depth half of MPI_Reduce, output.c:10-30,82) */
-  const unsigned long long *depth_global = NULL;
-  if (ctx->size > 1) {
-    LAUNCH_OK(c3d_k_depth_extract(ctx->canvas, ctx->depth_local, npix, s));
+  if (part) {
+    /* 4'. my tiles are final: background and lines go to the writer's image, pixels won by a contour triangle to the rank
+           that holds the winning cube's array (replaces MPI_Reduce, output.c:10-30,82: nothing image-sized is reduced) */
+    LAUNCH_OK(c3d_k_shade_begin(&ctx->shade, s));
+    LAUNCH_OK(c3d_k_shade_select_part(&fp, lines_dev, ctx->canvas, rgba_out, (WorkItem *)(xa.base + xa.off_seg), (unsigned int)xa.seg_cap,
+                                      (unsigned int *)(xa.base + xa.off_nseg), ctx->counts_dev + CNT_SEG_OVER, ctx->sm_count, s));
     launches += 1;
-    NCCL_OK(g_nccl.AllReduce(ctx->depth_local, ctx->depth_global, npix, ncclUint64, ncclMax, ctx->comm, s));
-    depth_global = ctx->depth_global;
-  }
-  CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
-  /* 5. shade only what survived */
-  LAUNCH_OK(c3d_k_shade(&fp, lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, &ctx->shade,
-                        ctx->counts_dev + CNT_SHADE_SPILL, ctx->sm_count, s));
-  launches += 4;
-  CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
-  /* 6. colours to the writer (the colour half of the reference's reduce) */
-  if (ctx->size > 1) {
-    NCCL_OK(g_nccl.Reduce(ctx->rgba, ctx->rgba, npix, ncclUint32, ncclMax, 0, ctx->comm, s));
-  }
-  CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE1], s));
-  if (0 == ctx->rank) {
-    LAUNCH_OK(c3d_k_pack(ctx->rgba, scene->bg, cam.w, cam.h, ctx->ppm_dev, s));
-    launches += 1;
+    CUDA_OK(cudaEventRecord(ctx->ev[EV_RESOLVE], s));
+    LAUNCH_OK(c3d_peer_barrier(peer, s));
+    WorkSources ws;
+    memset(&ws, 0, sizeof(ws));
+    for (int r = 0; r < ctx->size; r++) {
+      const char *pb = (const char *)xa.peer[r];
+      ws.seg[r] = (const WorkItem *)(pb + xa.off_seg) + (size_t)ctx->rank * xa.seg_cap;
+      ws.count[r] = (const unsigned int *)(pb + xa.off_nseg) + ctx->rank;
+    }
+    LAUNCH_OK(c3d_k_work_pull(&ws, ctx->size, ctx->shade.work, ctx->shade.counters, (unsigned int)std::min<size_t>(npix, 0xffffffffu),
+                              ctx->counts_dev + CNT_SEG_OVER, s));
+    launches += 2;
+    CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
+    /* 5'. shade what this rank's cubes have won, anywhere on the screen, straight into the writer's image */
+    LAUNCH_OK(c3d_k_shade_finish(&fp, rgba_out, &ctx->shade, ctx->counts_dev + CNT_SHADE_SPILL, ctx->sm_count, s));
+    launches += 3;
+    CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
+    /* 6'. the image is complete when everybody is done; a buffer that overflowed anywhere makes everybody redo the frame */
+    LAUNCH_OK(c3d_k_overflow_flag(ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->counts_dev + CNT_OUT, xa.out_cap,
+                                  ctx->counts_dev + CNT_SEG_OVER, (unsigned long long *)(xa.base + xa.off_flags), s));
+    LAUNCH_OK(c3d_peer_barrier(peer, s));
+    FlagSources fs;
+    memset(&fs, 0, sizeof(fs));
+    for (int r = 0; r < ctx->size; r++) fs.flag[r] = (const unsigned long long *)((const char *)xa.peer[r] + xa.off_flags);
+    LAUNCH_OK(c3d_k_flags_max(&fs, ctx->size, ctx->counts_dev + CNT_OVERFLOW, s));
+    launches += 3;
+    CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE1], s));
+    if (0 == ctx->rank) {
+      LAUNCH_OK(c3d_k_pack((const unsigned int *)(xa.base + xa.off_rgba), scene->bg, cam.w, cam.h, ctx->ppm_dev, s));
+      launches += 1;
+    }
+  } else {
+    CUDA_OK(cudaEventRecord(ctx->ev[EV_RESOLVE], s));
+    /* 4. nearest depth across ranks (replaces the depth half of MPI_Reduce, output.c:10-30,82) */
+    const unsigned long long *depth_global = NULL;
+    if (ctx->size > 1) {
+      LAUNCH_OK(c3d_k_depth_extract(ctx->canvas, ctx->depth_local, npix, s));
+      launches += 1;
+      NCCL_OK(g_nccl.AllReduce(ctx->depth_local, ctx->depth_global, npix, ncclUint64, ncclMax, ctx->comm, s));
+      depth_global = ctx->depth_global;
+    }
+    CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
+    /* 5. shade only what survived */
+    LAUNCH_OK(c3d_k_shade(&fp, lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, &ctx->shade,
+                          ctx->counts_dev + CNT_SHADE_SPILL, ctx->sm_count, s));
+    launches += 4;
+    CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
+    /* 6. colours to the writer (the colour half of the reference's reduce) */
+    if (ctx->size > 1) {
+      NCCL_OK(g_nccl.Reduce(ctx->rgba, ctx->rgba, npix, ncclUint32, ncclMax, 0, ctx->comm, s));
+    }
+    CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE1], s));
+    if (0 == ctx->rank) {
+      LAUNCH_OK(c3d_k_pack(ctx->rgba, scene->bg, cam.w, cam.h, ctx->ppm_dev, s));
+      launches += 1;
+    }
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_PACK], s));
   const bool want_host = (0 == ctx->rank) && (NULL != host_rgb || NULL != fname);
   if (want_host) CUDA_OK(cudaMemcpyAsync(ctx->ppm_host, ctx->ppm_dev, 3 * npix, cudaMemcpyDeviceToHost, s));
-  if (ctx->size > 1) {
+  if (ctx->size > 1 && !part) {
     /* the frame is redone when a work buffer overflowed: all ranks must agree, the frame is full of collectives */
-    LAUNCH_OK(c3d_k_overflow_flag(ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->counts_dev + CNT_OVERFLOW, s));
+    LAUNCH_OK(c3d_k_overflow_flag(ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->counts_dev + CNT_LIST, ctx->list_cap, NULL, 0, NULL, ctx->counts_dev + CNT_OVERFLOW, s));
     NCCL_OK(g_nccl.AllReduce(ctx->counts_dev + CNT_OVERFLOW, ctx->counts_dev + CNT_OVERFLOW, 1, ncclUint64, ncclMax, ctx->comm, s));
     launches += 1;
   }
   CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  if (part) CUDA_OK(cudaMemcpyAsync(ctx->counts_host + CNT_PEER, peer->status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaEventRecord(ctx->ev[EV_DOWNLOAD], s));
   CUDA_OK(cudaStreamSynchronize(s));
+  if (part && 0ull != ctx->counts_host[CNT_PEER]) {
+    peer->broken = true;
+    return c3d_error("rank %d waited in vain for another rank at a device barrier: the ranks are out of step", ctx->rank);
+  }
   /* capacity policy: a buffer that overflowed is grown and the frame is redone */
   {
     const size_t need_rec = (size_t)ctx->counts_host[CNT_REC], need_list = (size_t)ctx->counts_host[CNT_LIST];
@@ -1027,8 +1433,17 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
       if (cudaSuccess != err) return c3d_error("failed to grow the active-cube list to %zu entries: %s", want, cudaGetErrorString(err));
       ctx->list_cap = want;
     }
+    if (part && (size_t)ctx->counts_host[CNT_OUT] > xa.out_cap) {
+      *overflow = true;
+      xa.out_cap = (size_t)ctx->counts_host[CNT_OUT] + (size_t)ctx->counts_host[CNT_OUT] / 4 + 1024;    /* taken up when the arena is re-created */
+    }
+    if (part && 0ull != ctx->counts_host[CNT_SEG_OVER]) return c3d_error("internal: a shading work segment overflowed");
     if (0ull != ctx->counts_host[CNT_OVERFLOW]) *overflow = true;      /* another rank's buffer: redo with it */
-    if (*overflow) return 0;
+    if (*overflow) {
+      /* everybody redoes the frame; the shared arena is re-created (and re-mapped by all) because one rank's outbox may have grown */
+      if (part) xa.stale = true;
+      return 0;
+    }
   }
   /* timings */
   c3d_timings_t *t = &ctx->last;
@@ -1054,6 +1469,8 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   t->ncontours = (uint32_t)nc;
   t->launches = launches;
   t->nsweeps = nsweeps;
+  t->exchange_mode = (uint32_t)(ctx->size < 2 ? 0 : (part ? 2 : 1));
+  t->list_entries = ctx->counts_host[CNT_LIST];
   t->culled_cubes = ctx->counts_host[CNT_CULLED];
   t->culled_triangles = ctx->counts_host[CNT_CULLED_TRIS];
   t->shade_spills = ctx->counts_host[CNT_SHADE_SPILL];
@@ -1167,6 +1584,8 @@ static int stage_view(c3d_context *ctx, const c3d_field *f, const double *const 
     v->data = f->data; v->elem_bytes = f->elem_bytes;
     for (int d = 0; d < 3; d++) { v->n[d] = (long long)f->ext[d]; v->g[d] = ctx->grids_dev; v->gf[d] = (const float *)ctx->grids_dev; }
     v->sy = (long long)f->ext[0]; v->sz = (long long)(f->ext[0] * f->ext[1]);
+    v->map = NULL;
+    for (int d = 0; d < 3; d++) v->off[d] = (long long)f->ext_off[d];
     v->thr = thr; v->thr_ge = smallest_float_above(thr);
     return 0;
   }

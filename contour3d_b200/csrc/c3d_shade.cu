@@ -35,7 +35,7 @@
 
 __global__ void __launch_bounds__(256) k_shade_select(const __grid_constant__ FrameParams p, const LineDev *__restrict__ lines,
                                                       const Pixel *__restrict__ canvas, const unsigned long long *__restrict__ depth_global,
-                                                      unsigned int *__restrict__ rgba, const size_t npix, unsigned int *__restrict__ work,
+                                                      unsigned int *__restrict__ rgba, const size_t npix, WorkItem *__restrict__ work,
                                                       unsigned int *__restrict__ nwork) {
   /* a warp takes a tile of 8 x 4 pixels, so that the work list is ordered by screen tiles: the 32 pixels a warp of
      k_shade_setup handles then share cubes, vertices and cache lines (rows of 3840 pixels do not) */
@@ -48,9 +48,11 @@ __global__ void __launch_bounds__(256) k_shade_select(const __grid_constant__ Fr
     const unsigned int pi = (tile % tiles_x) * 8u + (lane & 7u), pj = (tile / tiles_x) * 4u + (lane >> 3);
     const size_t pix = (size_t)pj * w + pi;
     bool mine = false;
+    unsigned long long mykey = 0ull;
     if (pi < w && pj < h && pix < npix) {
       const ulonglong2 px = *reinterpret_cast<const ulonglong2 *>(canvas + pix);
       unsigned int out = 0u;     /* 0 = nothing from this rank: background, or another rank is nearer */
+      mykey = px.y;
       if (0ull != px.y && (nullptr == depth_global || px.x == depth_global[pix])) {
         const unsigned int obj = (unsigned int)(px.y >> C3D_KEY_OBJ_SHIFT) - 1u;
         if (obj >= p.ncontours) {
@@ -67,7 +69,68 @@ __global__ void __launch_bounds__(256) k_shade_select(const __grid_constant__ Fr
       unsigned int at = 0u;
       if (0u == lane) at = atomicAdd(nwork, (unsigned int)__popc(who));
       at = __shfl_sync(C3D_FULL_MASK, at, 0);
-      if (mine) work[at + __popc(who & ((1u << lane) - 1u))] = (unsigned int)pix;
+      if (mine) work[at + __popc(who & ((1u << lane) - 1u))] = WorkItem{(unsigned int)pix, 0u, mykey};
+    }
+  }
+}
+
+/*
+ * Screen-partitioned frames: this rank resolves only its own tiles.  Background and line pixels are final and go
+ * straight into the writer's image (rank 0's, through peer memory); a pixel won by a contour triangle is queued for
+ * the rank that holds the winning cube's array -- it alone can form the vertex normals (normal.c:78-158 needs the
+ * neighbouring cubes) -- in the segment that rank will pull: seg[r * seg_cap ...], nseg[r].
+ */
+__global__ void __launch_bounds__(256) k_shade_select_part(const __grid_constant__ FrameParams p, const LineDev *__restrict__ lines,
+                                                           const Pixel *__restrict__ canvas, unsigned int *__restrict__ rgba_out,
+                                                           WorkItem *__restrict__ seg, const unsigned int seg_cap, unsigned int *__restrict__ nseg,
+                                                           unsigned long long *__restrict__ overflowed) {
+  const Partition &part = p.part;
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int w = (unsigned int)p.cam.w, h = (unsigned int)p.cam.h;
+  const unsigned int tile = 1u << part.tile_shift;
+  const unsigned int sub_x = tile >> 3, sub_y = tile >> 2, per_tile = sub_x * sub_y;       /* 8 x 4 pixel warps per tile */
+  const unsigned int ntiles = (unsigned int)(part.tiles_x * part.tiles_y);
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  /* own tiles are every nranks-th of a row, shifted from row to row: walk all (tile, sub-tile) pairs and skip foreign tiles */
+  for (unsigned long long unit = warp; unit < (unsigned long long)ntiles * per_tile; unit += nwarps) {
+    const unsigned int t = (unsigned int)(unit / per_tile), sub = (unsigned int)(unit % per_tile);
+    const unsigned int tx = t % (unsigned int)part.tiles_x, ty = t / (unsigned int)part.tiles_x;
+    if (tile_owner(part, tx, ty) != (unsigned int)part.me) continue;
+    const unsigned int pi = tx * tile + (sub % sub_x) * 8u + (lane & 7u), pj = ty * tile + (sub / sub_x) * 4u + (lane >> 3);
+    const size_t pix = (size_t)pj * w + pi;
+    unsigned int home = 0xffffffffu;
+    unsigned long long mykey = 0ull;
+    if (pi < w && pj < h) {
+      const ulonglong2 px = *reinterpret_cast<const ulonglong2 *>(canvas + pix);
+      unsigned int out = 0u;
+      mykey = px.y;
+      if (0ull != px.y) {
+        const unsigned int obj = (unsigned int)(px.y >> C3D_KEY_OBJ_SHIFT) - 1u;
+        if (obj >= p.ncontours) {
+          const LineDev &ln = lines[obj - p.ncontours];
+          out = 0xFF000000u | ((unsigned int)ln.color[2] << 16) | ((unsigned int)ln.color[1] << 8) | ln.color[0];
+        } else {
+          const unsigned long long prim = px.y & C3D_KEY_PRIM_MASK;
+          home = cube_home(part, (unsigned int)((prim >> 20) & 65535ull), (unsigned int)((prim >> 36) & 65535ull));
+        }
+      }
+      if (0xffffffffu == home) rgba_out[pix] = out;
+    }
+    /* one append per rank that has pixels in this warp */
+    unsigned int pending = __ballot_sync(C3D_FULL_MASK, 0xffffffffu != home);
+    while (pending) {
+      const unsigned int leader = (unsigned int)__ffs((int)pending) - 1u;
+      const unsigned int r = __shfl_sync(C3D_FULL_MASK, home, (int)leader);
+      const unsigned int who = __ballot_sync(C3D_FULL_MASK, home == r);
+      unsigned int at = 0u;
+      if (lane == leader) at = atomicAdd(nseg + r, (unsigned int)__popc(who));
+      at = __shfl_sync(C3D_FULL_MASK, at, (int)leader);
+      if (home == r) {
+        const unsigned int slot = at + __popc(who & ((1u << lane) - 1u));
+        if (slot < seg_cap) seg[(size_t)r * seg_cap + slot] = WorkItem{(unsigned int)pix, 0u, mykey};
+        else atomicAdd(overflowed, 1ull);
+      }
+      pending &= ~who;
     }
   }
 }
@@ -199,8 +262,8 @@ __device__ __forceinline__ unsigned long long vertex_key(const unsigned int obj,
        | ((unsigned long long)cj << 16) | (unsigned long long)ci;
 }
 
-__global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ FrameParams p, const Pixel *__restrict__ canvas,
-                                                     const unsigned int *__restrict__ work, unsigned int *__restrict__ counters,
+__global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ FrameParams p,
+                                                     const WorkItem *__restrict__ work, unsigned int *__restrict__ counters,
                                                      ShadePix *__restrict__ out, unsigned long long *__restrict__ table, const unsigned int mask,
                                                      unsigned int *__restrict__ vlist, unsigned long long *__restrict__ overflowed) {
   const unsigned int lane = threadIdx.x & 31u;
@@ -218,13 +281,16 @@ __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ Fra
     me.pix = 0u; me.i = me.j = me.k = 0; me.obj = 0; me.edges[0] = me.edges[1] = me.edges[2] = 0;
     unsigned long long vkey[3] = {0ull, 0ull, 0ull};
     if (valid) {
-      const unsigned int pix = __ldg(work + idx);
-      const unsigned long long key = canvas[pix].key;
+      const uint4 item = __ldg(reinterpret_cast<const uint4 *>(work) + idx);
+      const unsigned int pix = item.x;
+      const unsigned long long key = (unsigned long long)item.z | ((unsigned long long)item.w << 32);
       const unsigned int obj = (unsigned int)(key >> C3D_KEY_OBJ_SHIFT) - 1u;
       const unsigned long long prim = key & C3D_KEY_PRIM_MASK;
       const unsigned int s = (unsigned int)(prim & 15ull);
-      const long long i = (long long)((prim >> 4) & 65535ull), j = (long long)((prim >> 20) & 65535ull), k = (long long)((prim >> 36) & 65535ull);
       const FieldView &f = p.view[obj];
+      /* the key names the cube by its GLOBAL indices; this rank's array starts at f.off */
+      const long long i = (long long)((prim >> 4) & 65535ull) - f.off[0], j = (long long)((prim >> 20) & 65535ull) - f.off[1],
+                      k = (long long)((prim >> 36) & 65535ull) - f.off[2];
       const unsigned int code = cube_code(f, i, j, k);
       const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
       const unsigned int edges = __ldg(p.tab.edges + code * C3D_MAX_TRIS + s);
@@ -474,17 +540,36 @@ template <typename K> static int resident_blocks(K kernel, const int threads, co
   return per_sm * sm_count;
 }
 
-extern "C" int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
-                           unsigned int *rgba, size_t npix, const ShadeScratch *sc, unsigned long long *overflowed,
-                           int sm_count, cudaStream_t s) {
+/* clears the counters and the vertex table of a frame's shading */
+extern "C" int c3d_k_shade_begin(const ShadeScratch *sc, cudaStream_t s) {
   cudaError_t err = cudaMemsetAsync(sc->counters, 0, 2 * sizeof(unsigned int), s);
   if (cudaSuccess != err) return (int)err;
   err = cudaMemsetAsync(sc->table, 0, ((size_t)sc->table_mask + 1u) * sizeof(unsigned long long), s);
-  if (cudaSuccess != err) return (int)err;
-  k_shade_select<<<sm_count * 8, 256, 0, s>>>(*p, lines_dev, canvas, depth_global, rgba, npix, sc->work, sc->counters);
-  k_shade_setup<<<resident_blocks(k_shade_setup, 128, sm_count), 128, 0, s>>>(*p, canvas, sc->work, sc->counters, static_cast<ShadePix *>(sc->pix),
+  return (int)err;
+}
+
+/* shades the sc->counters[0] work items of sc->work into rgba (which may be another rank's image, through peer memory) */
+extern "C" int c3d_k_shade_finish(const FrameParams *p, unsigned int *rgba, const ShadeScratch *sc, unsigned long long *overflowed,
+                                  int sm_count, cudaStream_t s) {
+  k_shade_setup<<<resident_blocks(k_shade_setup, 128, sm_count), 128, 0, s>>>(*p, sc->work, sc->counters, static_cast<ShadePix *>(sc->pix),
                                                                               sc->table, sc->table_mask, sc->vlist, overflowed);
   k_shade_normals<<<resident_blocks(k_shade_normals, SH_THREADS, sm_count), SH_THREADS, 0, s>>>(*p, sc->table, sc->vlist, sc->counters, sc->vn, sc->vn_cap, overflowed);
   k_shade_blend<<<resident_blocks(k_shade_blend, 128, sm_count), 128, 0, s>>>(*p, static_cast<const ShadePix *>(sc->pix), sc->counters, sc->table, sc->vn, rgba);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, const unsigned long long *depth_global,
+                           unsigned int *rgba, size_t npix, const ShadeScratch *sc, unsigned long long *overflowed,
+                           int sm_count, cudaStream_t s) {
+  const int rc = c3d_k_shade_begin(sc, s);
+  if (0 != rc) return rc;
+  k_shade_select<<<sm_count * 8, 256, 0, s>>>(*p, lines_dev, canvas, depth_global, rgba, npix, sc->work, sc->counters);
+  return c3d_k_shade_finish(p, rgba, sc, overflowed, sm_count, s);
+}
+
+extern "C" int c3d_k_shade_select_part(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, unsigned int *rgba_out,
+                                       WorkItem *seg, unsigned int seg_cap, unsigned int *nseg, unsigned long long *overflowed,
+                                       int sm_count, cudaStream_t s) {
+  k_shade_select_part<<<sm_count * 8, 256, 0, s>>>(*p, lines_dev, canvas, rgba_out, seg, seg_cap, nseg, overflowed);
   return (int)cudaGetLastError();
 }

@@ -488,8 +488,10 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(const unsigned int *__rest
  * Can a triangle of this 4 x 8 patch of cubes have collapsed to a point?  Vertices reach a cube corner only
  * when an interpolation factor (thr - v0) / (v1 - v0) = a0 / (a0 + a1), a = |v - thr|, is within rounding of
  * 0 or 1 (or |v1 - v0| < 1e-8, triangulate.c:62-71).  If min a > 1e-6 max a over the points of the patch that
- * its cut cubes use, every factor of every such cube lies in (5e-7, 1 - 5e-7): no collapse.  Anything else (including
- * NaN / infinite data) marks the patch, and the raster then skips its visibility shortcuts there.
+ * its cut cubes use, every factor of every such cube lies in (5e-7, 1 - 5e-7): no collapse.  The reference's other branch is
+ * absolute -- |v1 - v0| < 1e-8 puts the vertex on the tail corner whatever the ratio (triangulate.c:62-71; a field of tiny
+ * magnitude) -- so min a > 1e-8 is asked as well: every straddling pair then has |v1 - v0| = a0 + a1 >= 2e-8.  Anything else
+ * (including NaN / infinite data) marks the patch, and the raster then skips its visibility shortcuts there.
  */
 __device__ __forceinline__ bool patch_irregular(const FieldView &f, const unsigned int x, const unsigned int j, const unsigned int k,
                                                 const unsigned int active) {
@@ -534,7 +536,7 @@ __device__ __forceinline__ bool patch_irregular(const FieldView &f, const unsign
           sum += (a0 + a1) + (a2 + a3) + a4;             /* NaN / inf detector (fminf / fmaxf would drop a NaN) */
         }
       }
-      return !(sum <= FLT_MAX) || !(amin > 1.1e-6f * amax + thr_err);
+      return !(sum <= FLT_MAX) || !(amin > 1.1e-6f * amax + thr_err) || !(amin > 1.01e-8f + thr_err);
     }
     for (int dz = 0; dz < 2; dz++) {
       for (int r = 0; r < 9; r++) {
@@ -553,7 +555,7 @@ __device__ __forceinline__ bool patch_irregular(const FieldView &f, const unsign
         }
       }
     }
-    return !(sum <= FLT_MAX) || !(amin > 1.1e-6f * amax + thr_err);
+    return !(sum <= FLT_MAX) || !(amin > 1.1e-6f * amax + thr_err) || !(amin > 1.01e-8f + thr_err);
   }
   double amin = DBL_MAX, amax = 0.;
   bool bad = false;
@@ -570,7 +572,7 @@ __device__ __forceinline__ bool patch_irregular(const FieldView &f, const unsign
       }
     }
   }
-  return bad || !(amin > 1.e-6 * amax);
+  return bad || !(amin > 1.e-6 * amax) || !(amin > 1.e-8);
 }
 
 template <bool SORTED>
@@ -610,7 +612,8 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ FramePar
       if (0u == lane) at = atomicAdd(count, (unsigned long long)total);
       at = __shfl_sync(SW_FULL, at, 0) + (incl - mine);
     }
-    const unsigned long long flag = (SORTED && 0u != mine && patch_irregular(p.view[obj], x, j, k, active)) ? C3D_ENTRY_IRREGULAR_BIT : 0ull;
+    /* wanted whenever the raster may skip cubes, sorted list or not */
+    const unsigned long long flag = (p.cull.enabled && 0u != mine && patch_irregular(p.view[obj], x, j, k, active)) ? C3D_ENTRY_IRREGULAR_BIT : 0ull;
     /* rows 0..8 of the four bit planes */
     const unsigned long long pl = a.x | ((unsigned long long)(b.y & 15u) << 32), ql = a.y | ((unsigned long long)((b.y >> 4) & 15u) << 32);
     const unsigned long long pu = a.z | ((unsigned long long)((b.y >> 8) & 15u) << 32), qu = a.w | ((unsigned long long)((b.y >> 12) & 15u) << 32);
@@ -628,6 +631,191 @@ __global__ void __launch_bounds__(256) k_expand(const __grid_constant__ FramePar
                               | ((unsigned int)((pu >> (bit + 4)) & 1ull) << 6) | ((unsigned int)((qu >> (bit + 4)) & 1ull) << 7);
       if (at < capacity) list[at] = C3D_ENTRY(obj, x + (unsigned int)(bit & 3), j + (unsigned int)(bit >> 2), k, code) | flag;
       at++;
+    }
+  }
+}
+
+/* ------------------------------------------------- screen-partitioned expand */
+
+/*
+ * Which ranks' screen tiles can cube (i, j, k) of view f touch?  Bit r of the result = rank r must draw it.
+ * The pixels a cube can reach are the reference's search boxes of its triangles: trunc((0.5 + sx) W -+ 1) clamped to
+ * the screen (render.c:81-89), and every vertex lies inside the hull of the eight corners, so the box of the
+ * corners, widened by one pixel plus a quarter for the fp32 arithmetic, holds them all.  Cubes the fp32 projection
+ * cannot bound (a corner at or behind the screen plane, non-finite data, a huge footprint) go to every rank: each rank
+ * only ever draws its own pixels, so a superset costs time, never correctness.
+ */
+__device__ __forceinline__ unsigned int cube_owners(const FrameParams &p, const FieldView &f, const long long i, const long long j, const long long k) {
+  const Partition &part = p.part;
+  const unsigned int everyone = (1u << part.nranks) - 1u;
+  const CullCam &q = p.cull;
+  if (!q.valid || nullptr != f.map) return everyone;
+  float an[2], al[2], am[2], bn[2], bl[2], bm[2], cn[2], cl[2], cm[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const float rx = __ldg(f.gf[0] + i + e) - q.cam[0];
+    const float ry = __ldg(f.gf[1] + j + e) - q.cam[1];
+    const float rz = __ldg(f.gf[2] + k + e) - q.cam[2];
+    an[e] = q.n[0] * rx; al[e] = q.lxs[0] * rx; am[e] = q.lys[0] * rx;
+    bn[e] = q.n[1] * ry; bl[e] = q.lxs[1] * ry; bm[e] = q.lys[1] * ry;
+    cn[e] = q.n[2] * rz; cl[e] = q.lxs[2] * rz; cm[e] = q.lys[2] * rz;
+  }
+  float xlo = 3.e38f, xhi = -3.e38f, ylo = 3.e38f, yhi = -3.e38f, tlo = 3.e38f, thi = -3.e38f;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int a = c & 1, b = (c >> 1) & 1, d = c >> 2;
+    const float nr = an[a] + bn[b] + cn[d];
+    const float t = __fdividef(q.c, nr);
+    const float sx = q.ax + t * (al[a] + bl[b] + cl[d]);
+    const float sy = q.ay + t * (am[a] + bm[b] + cm[d]);
+    xlo = fminf(xlo, sx); xhi = fmaxf(xhi, sx);
+    ylo = fminf(ylo, sy); yhi = fmaxf(yhi, sy);
+    tlo = fminf(tlo, t); thi = fmaxf(thi, t);
+  }
+  if (!(tlo > 1.e-4f && thi < 0.9999f)) return everyone;
+  if (!(xlo > -1.e6f && xhi < 1.e6f && ylo > -1.e6f && yhi < 1.e6f)) return everyone;
+  const float wmax = (float)(q.w - 1), hmax = (float)(q.h - 1);
+  const int imin = (int)fminf(fmaxf(floorf((0.5f + xlo) * q.W - 1.25f), 0.f), wmax), imax = (int)fminf(fmaxf(floorf((0.5f + xhi) * q.W + 1.25f), 0.f), wmax);
+  const int jmin = (int)fminf(fmaxf(floorf((0.5f + ylo) * q.H - 1.25f), 0.f), hmax), jmax = (int)fminf(fmaxf(floorf((0.5f + yhi) * q.H + 1.25f), 0.f), hmax);
+  const int tx0 = imin >> part.tile_shift, tx1 = imax >> part.tile_shift, ty0 = jmin >> part.tile_shift, ty1 = jmax >> part.tile_shift;
+  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 16) return everyone;
+  unsigned int mask = 0u;
+  for (int ty = ty0; ty <= ty1; ty++) {
+    for (int tx = tx0; tx <= tx1; tx++) mask |= 1u << tile_owner(part, (unsigned int)tx, (unsigned int)ty);
+  }
+  return mask;
+}
+
+/* cubes per (destination rank, depth bucket); histogram[r * C3D_DEPTH_BUCKETS + b] */
+__global__ void __launch_bounds__(256) k_part_count(const __grid_constant__ FrameParams p, const DepthOrder o,
+                                                    const SweepRecord *__restrict__ records, const unsigned long long *__restrict__ nrecords,
+                                                    const unsigned long long rec_capacity, unsigned int *__restrict__ histogram) {
+  extern __shared__ unsigned int local[];
+  const unsigned int nbins = (unsigned int)p.part.nranks * C3D_DEPTH_BUCKETS;
+  for (unsigned int b = threadIdx.x; b < nbins; b += blockDim.x) local[b] = 0u;
+  __syncthreads();
+  unsigned long long n = *nrecords;
+  if (n > rec_capacity) n = rec_capacity;
+  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(records) + 2ull * q + 1ull);
+    unsigned int active = b.x;
+    const unsigned int x = b.z & 65535u, j = b.z >> 16, k = b.w & 65535u, obj = b.w >> 16;
+    const unsigned int bucket = depth_bucket(p, o, obj, x, j, k);
+    const FieldView &f = p.view[obj];
+    while (active) {
+      const int bit = __ffs((int)active) - 1;
+      active &= active - 1u;
+      unsigned int owners = cube_owners(p, f, (long long)x + (bit & 3), (long long)j + (bit >> 2), (long long)k);
+      while (owners) {
+        const int r = __ffs((int)owners) - 1;
+        owners &= owners - 1u;
+        atomicAdd(local + (unsigned int)r * C3D_DEPTH_BUCKETS + bucket, 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (unsigned int b = threadIdx.x; b < nbins; b += blockDim.x) {
+    if (0u != local[b]) atomicAdd(histogram + b, local[b]);
+  }
+}
+
+/* one block: histogram -> cursors into the outbox, destination-major; seg_start[r] = where rank r's cubes begin;
+   *count = all of them (the host compares it with the outbox capacity) */
+__global__ void __launch_bounds__(1024) k_part_scan(const unsigned int *__restrict__ histogram, const int nranks, unsigned long long *__restrict__ cursors,
+                                                    unsigned long long *__restrict__ seg_start, unsigned long long *__restrict__ count) {
+  __shared__ unsigned long long part[1024];
+  const unsigned int per = (unsigned int)(C3D_DEPTH_BUCKETS / 1024) * (unsigned int)nranks;
+  const unsigned int first = threadIdx.x * per;
+  unsigned long long mine = 0ull;
+  for (unsigned int q = 0; q < per; q++) mine += histogram[first + q];
+  part[threadIdx.x] = mine;
+  __syncthreads();
+  for (unsigned int d = 1; d < 1024; d <<= 1) {
+    const unsigned long long add = threadIdx.x >= d ? part[threadIdx.x - d] : 0ull;
+    __syncthreads();
+    part[threadIdx.x] += add;
+    __syncthreads();
+  }
+  unsigned long long at = part[threadIdx.x] - mine;
+  for (unsigned int q = 0; q < per; q++) {
+    const unsigned int bin = first + q;
+    cursors[bin] = at;
+    if (0u == bin % C3D_DEPTH_BUCKETS) seg_start[bin / C3D_DEPTH_BUCKETS] = at;
+    at += histogram[bin];
+  }
+  if (1023u == threadIdx.x) *count = part[1023];
+}
+
+/* records -> one outbox entry per (cut cube, rank that must draw it), sorted by (rank, depth bucket); entries are tagged
+   with this rank (bits 61-63): their cube indices refer to ITS array */
+__global__ void __launch_bounds__(256) k_part_expand(const __grid_constant__ FrameParams p, const DepthOrder o,
+                                                     const SweepRecord *__restrict__ records, const unsigned long long *__restrict__ nrecords,
+                                                     const unsigned long long rec_capacity, unsigned long long *__restrict__ outbox,
+                                                     const unsigned long long capacity, unsigned long long *__restrict__ cursors,
+                                                     unsigned long long *__restrict__ per_object, const unsigned int nobjects) {
+  unsigned long long n = *nrecords;
+  if (n > rec_capacity) n = rec_capacity;
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long tag = (unsigned long long)p.part.me << C3D_ENTRY_SRC_SHIFT;
+  for (unsigned long long q0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); q0 < n; q0 += stride) {
+    const unsigned long long q = q0 + lane;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u);
+    if (q < n) {
+      a = __ldg(reinterpret_cast<const uint4 *>(records) + 2ull * q);
+      b = __ldg(reinterpret_cast<const uint4 *>(records) + 2ull * q + 1ull);
+    }
+    const unsigned int active = b.x;
+    const unsigned int mine = __popc(active);
+    const unsigned int x = b.z & 65535u, j = b.z >> 16, k = b.w & 65535u, obj = b.w >> 16;
+    for (unsigned int ob = 0; ob < nobjects; ob++) {
+      const unsigned int sum = __reduce_add_sync(SW_FULL, obj == ob ? mine : 0u);
+      if (0u == lane && 0u != sum) atomicAdd(per_object + ob, (unsigned long long)sum);
+    }
+    if (0u == mine) continue;
+    const FieldView &f = p.view[obj];
+    const unsigned int bucket = depth_bucket(p, o, obj, x, j, k);
+    const unsigned long long flag = (p.cull.enabled && patch_irregular(f, x, j, k, active)) ? C3D_ENTRY_IRREGULAR_BIT : 0ull;
+    const unsigned long long pl = a.x | ((unsigned long long)(b.y & 15u) << 32), ql = a.y | ((unsigned long long)((b.y >> 4) & 15u) << 32);
+    const unsigned long long pu = a.z | ((unsigned long long)((b.y >> 8) & 15u) << 32), qu = a.w | ((unsigned long long)((b.y >> 12) & 15u) << 32);
+    /* who must draw each of my cubes; then one cursor bump per (record, rank) */
+    unsigned char owners[32];
+    unsigned int present = 0u;
+    {
+      unsigned int todo = active;
+      while (todo) {
+        const int bit = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        const unsigned int m = cube_owners(p, f, (long long)x + (bit & 3), (long long)j + (bit >> 2), (long long)k);
+        owners[bit] = (unsigned char)m;
+        present |= m;
+      }
+    }
+    while (present) {
+      const int r = __ffs((int)present) - 1;
+      present &= present - 1u;
+      unsigned int cnt = 0u;
+      {
+        unsigned int todo = active;
+        while (todo) {
+          const int bit = __ffs((int)todo) - 1;
+          todo &= todo - 1u;
+          cnt += (owners[bit] >> r) & 1u;
+        }
+      }
+      unsigned long long at = atomicAdd(cursors + (unsigned int)r * C3D_DEPTH_BUCKETS + bucket, (unsigned long long)cnt);
+      unsigned int todo = active;
+      while (todo) {
+        const int bit = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        if (0u == ((owners[bit] >> r) & 1u)) continue;
+        const unsigned int code = (unsigned int)((pl >> bit) & 1ull) | ((unsigned int)((ql >> bit) & 1ull) << 1)
+                                | ((unsigned int)((pl >> (bit + 4)) & 1ull) << 2) | ((unsigned int)((ql >> (bit + 4)) & 1ull) << 3)
+                                | ((unsigned int)((pu >> bit) & 1ull) << 4) | ((unsigned int)((qu >> bit) & 1ull) << 5)
+                                | ((unsigned int)((pu >> (bit + 4)) & 1ull) << 6) | ((unsigned int)((qu >> (bit + 4)) & 1ull) << 7);
+        if (at < capacity) outbox[at] = C3D_ENTRY(obj, x + (unsigned int)(bit & 3), j + (unsigned int)(bit >> 2), k, code) | flag | tag;
+        at++;
+      }
     }
   }
 }
@@ -796,5 +984,26 @@ extern "C" int c3d_k_expand(const FrameParams *fp, int sorted, float near_depth,
   } else {
     k_expand<false><<<sm_count * 8, 256, 0, s>>>(*fp, o, rec, nrecords, rec_capacity, list, count, capacity, cursors, per_object, nobjects);
   }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int c3d_k_expand_part(const FrameParams *fp, float near_depth, float far_depth, const void *records, const unsigned long long *nrecords,
+                                 unsigned long long rec_capacity, unsigned long long *outbox, unsigned long long *count, unsigned long long capacity,
+                                 unsigned int *histogram, unsigned long long *cursors, unsigned long long *seg_start,
+                                 unsigned long long *per_object, unsigned int nobjects, int sm_count, cudaStream_t s) {
+  const SweepRecord *rec = static_cast<const SweepRecord *>(records);
+  const int nranks = fp->part.nranks;
+  if (nranks < 2 || nranks > C3D_MAX_RANKS) return (int)cudaErrorInvalidValue;
+  DepthOrder o;
+  o.near_depth = near_depth;
+  o.scale = (near_depth > far_depth) ? (float)C3D_DEPTH_BUCKETS / (near_depth - far_depth) : 0.f;
+  const size_t bins = (size_t)nranks * C3D_DEPTH_BUCKETS;
+  cudaError_t err = cudaMemsetAsync(histogram, 0, bins * sizeof(unsigned int), s);
+  if (cudaSuccess != err) return (int)err;
+  err = cudaFuncSetAttribute(k_part_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bins * sizeof(unsigned int)));
+  if (cudaSuccess != err) return (int)err;
+  k_part_count<<<sm_count * 2, 256, bins * sizeof(unsigned int), s>>>(*fp, o, rec, nrecords, rec_capacity, histogram);
+  k_part_scan<<<1, 1024, 0, s>>>(histogram, nranks, cursors, seg_start, count);
+  k_part_expand<<<sm_count * 8, 256, 0, s>>>(*fp, o, rec, nrecords, rec_capacity, outbox, capacity, cursors, per_object, nobjects);
   return (int)cudaGetLastError();
 }

@@ -103,6 +103,9 @@ typedef struct {
   uint32_t nsweeps;
   uint32_t ncontours;
   uint32_t launches;             /* kernels launched by this library in the frame */
+  uint32_t exchange_mode;        /* 0 one rank; 1 every rank draws its own cubes, whole images reduced through NCCL;
+                                    2 screen-partitioned: cube lists, shading work and colours move through peer memory */
+  uint64_t list_entries;         /* cubes this rank's raster walked (mode 2: from all ranks, for its screen tiles) */
 } c3d_timings_t;
 
 /* ---- life cycle ---- */
@@ -118,6 +121,9 @@ int c3d_context_device(const c3d_context_t *ctx);
 /* cudaStream_t the pipeline runs on, as an integer (for event timing from outside) */
 uintptr_t c3d_context_stream(const c3d_context_t *ctx);
 int c3d_context_synchronize(c3d_context_t *ctx);
+/* how the ranks of this context exchange data: 0 one rank; 1 NCCL (halo send/recv, whole-image reductions); 2 peer memory
+   over NVLink (CUDA IPC): halo planes, cube lists, shading work and colours are read / written in place, screen-partitioned */
+int c3d_context_exchange_mode(const c3d_context_t *ctx);
 
 /* block decomposition of SimpleDecomp (sdecomp/kernel.c:89,111-116) for a
    process grid dims = {1, Py, Pz}, ranks row-major with z fastest (MPI_Cart_create) */
@@ -135,6 +141,11 @@ int c3d_field_upload(c3d_context_t *ctx, c3d_field_t *field, const void *local);
 /* extended shape / global offsets of the first extended point / device pointer + strides of the INTERIOR */
 int c3d_field_geometry(const c3d_field_t *field, size_t ext_sizes[3], size_t ext_offsets[3], size_t mysizes[3], size_t offsets[3]);
 int c3d_field_interior(const c3d_field_t *field, void **device_ptr, size_t strides_elems[2]);
+/* One rank (no halo room needed): sweep a DEVICE array of the caller where it lies instead of copying it.  Returns 0 and a
+   field that borrows device_array (read only; c3d_field_destroy leaves it alone), 2 when that does not apply (host pointer,
+   other device, several ranks) -- then create + upload as usual.  reference: the copy of contour/extend.c:199-208 */
+int c3d_field_wrap(c3d_context_t *ctx, const c3d_decomp_t *decomp, const size_t glsizes[3], int elem_bytes,
+                   const void *device_array, c3d_field_t **field);
 /* tell the library the interior was written through c3d_field_interior (halo must be re-exchanged) */
 int c3d_field_mark_dirty(c3d_field_t *field);
 /* halo exchange: replaces communicate_in_{x,y,z}, contour/extend.c:10-147 (ncclSend/ncclRecv) */

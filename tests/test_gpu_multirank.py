@@ -1,6 +1,9 @@
-"""GPU, N > 1: halo exchange and cross-rank image reduction over NCCL, one process per GPU.
+"""GPU, N > 1: halo exchange, screen-partitioned frames over peer memory and whole-image reduction over NCCL.
 
-Skipped on single-GPU boxes (the world_size-2 gloo test covers the host logic there)."""
+One process per rank.  With fewer GPUs than ranks several ranks share a GPU: CUDA IPC maps device memory between
+processes on one device just as between devices, so the peer-memory path -- the default data path of multi-rank
+frames -- is exercised on a single-GPU box too.  Only the NCCL path (coordinate converters, CONTOUR3D_P2P=0) needs
+one GPU per rank and is skipped otherwise."""
 import os
 import subprocess
 import sys
@@ -18,19 +21,42 @@ def _gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("world,dims", [(2, "1x1x2"), (2, "1x2x1"), (4, "1x2x2"), (4, "1x1x4"), (8, "1x4x2")])
-def test_multi_gpu_image_equals_single_rank_oracle(world, dims, monkeypatch):
-    if _gpus() < world:
-        pytest.skip(f"needs {world} GPUs")
-    if dims == "1x1x2":
-        # also the grow-and-redo path: the ranks overflow their tiny work buffers by different amounts and must agree to run again
-        monkeypatch.setenv("CONTOUR3D_LIST_CAP", "2000")
-    port = 29500 + (os.getpid() + world * 7 + len(dims)) % 400
+def _run_check(world, dims, env_extra):
+    port = 29500 + (os.getpid() + world * 7 + len(dims) + 13 * len(env_extra)) % 400
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py"), dims]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    env = dict(os.environ)
+    env.update(env_extra)
+    env.setdefault("CONTOUR3D_PEER_TIMEOUT", "120")
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "ok" in proc.stdout
+    return proc.stdout
+
+
+@pytest.mark.parametrize("world,dims", [(2, "1x1x2"), (2, "1x2x1"), (4, "1x2x2"), (4, "1x1x4"), (8, "1x4x2"), (8, "1x1x8"), (3, "1x1x3")])
+def test_multi_rank_image_equals_single_rank_oracle(world, dims):
+    """screen-partitioned frames over peer memory (exchange mode 2); ranks share GPUs when the box has fewer"""
+    if _gpus() < 1:
+        pytest.skip("needs a GPU")
+    extra = {"C3D_EXPECT_MODE": "2"}
+    if dims == "1x1x2":
+        # also the grow-and-redo path: the ranks overflow their tiny work buffers by different amounts and must agree to run again
+        extra["CONTOUR3D_LIST_CAP"] = "2000"
+    if dims == "1x2x2":
+        extra["CONTOUR3D_TILE_SHIFT"] = "4"       # 16-pixel tiles: many cubes straddle tiles of different ranks
+    _run_check(world, dims, extra)
+
+
+@pytest.mark.parametrize("world,dims", [(2, "1x1x2"), (2, "1x2x1"), (4, "1x2x2"), (8, "1x4x2")])
+def test_multi_gpu_nccl_path_image_equals_single_rank_oracle(world, dims):
+    """CONTOUR3D_P2P=0: every rank draws its own cubes, halos and whole images travel through NCCL (exchange mode 1)"""
+    if _gpus() < world:
+        pytest.skip(f"the NCCL path needs one GPU per rank ({world})")
+    extra = {"CONTOUR3D_P2P": "0", "C3D_EXPECT_MODE": "1"}
+    if dims == "1x1x2":
+        extra["CONTOUR3D_LIST_CAP"] = "2000"
+    _run_check(world, dims, extra)
 
 
 @pytest.mark.parametrize("kind,dims", [(0, (1, 1, 2)), (1, (1, 2, 1)), (3, (1, 1, 2))])
@@ -44,8 +70,8 @@ def test_dropin_program_two_ranks_matches_the_reference(tmp_path, kind, dims):
     from contour3d_b200 import api, casefile, scenes
     from oracle import reference
 
-    if _gpus() < 2:
-        pytest.skip("needs 2 GPUs")
+    if _gpus() < 1 or (kind != 0 and _gpus() < 2):
+        pytest.skip("coordinate converters take the NCCL path: one GPU per rank")
     if not reference.available():
         pytest.skip("oracle/_ref not built")
     n = 40
