@@ -6,6 +6,7 @@ Outputs (git-ignored, but they travel to the GPU box with the snapshot):
   contour3d_b200/libcontour3d_b200.so     kernels + runtime + contour3d_execute
   contour3d_b200/libc3d_sdecomp_compat.so SimpleDecomp stand-in + minimpi (hosts without MPI)
   contour3d_b200/c3d_case                 case-file demo program on the public API
+  contour3d_b200/libc3d_synth_host.so     host twin of the device field generator (bench.py's reference arm; no CUDA)
 """
 from __future__ import annotations
 
@@ -24,6 +25,7 @@ OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libcontour3d_b200.so")
 COMPAT = os.path.join(PKG, "libc3d_sdecomp_compat.so")
 CASE = os.path.join(PKG, "c3d_case")
+SYNTH = os.path.join(PKG, "libc3d_synth_host.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -63,7 +65,7 @@ def have_real_mpi() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, h) for h in ("c3d_internal.h", "c3d_tables.h", "c3d_device.cuh", "c3d_peer.h")]
+    headers = [os.path.join(CSRC, h) for h in ("c3d_internal.h", "c3d_tables.h", "c3d_device.cuh", "c3d_peer.h", "c3d_synth.h")]
     headers += [os.path.join(INCLUDE, h) for h in ("contour3d_b200.h", "contour3d.h", "sdecomp.h")]
     headers += [os.path.join(MINIMPI, "mpi.h")]
     inc = ["-I", INCLUDE, "-I", CSRC]
@@ -96,6 +98,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if force or _newer(COMPAT, srcs + headers):
             _run(["gcc", "-std=gnu11", "-O2", "-Wall", "-Wextra", "-fPIC", "-shared", "-D_GNU_SOURCE"] + inc + mpi_inc
                  + ["-o", COMPAT] + srcs + ["-lpthread", "-lrt"])
+    synth_src = os.path.join(CSRC, "c3d_synth_host.c")
+    if force or _newer(SYNTH, [synth_src, os.path.join(CSRC, "c3d_synth.h")]):
+        # same single-precision arithmetic as the kernel: no contraction into fused multiply-adds
+        _run(["gcc", "-std=c99", "-O3", "-ffp-contract=off", "-Wall", "-Wextra", "-fPIC", "-shared", "-I", CSRC, "-o", SYNTH, synth_src, "-lpthread", "-lm"])
     src = os.path.join(CSRC, "c3d_case_main.c")
     if force or _newer(CASE, [src, LIB] + ([COMPAT] if not have_real_mpi() else [])):
         link = ["-L", PKG, "-lcontour3d_b200", "-Wl,-rpath,$ORIGIN"]

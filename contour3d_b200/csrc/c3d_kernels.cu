@@ -20,6 +20,7 @@
 #include <float.h>
 #include <stdlib.h>
 #include "c3d_device.cuh"
+#include "c3d_synth.h"
 
 /* ------------------------------------------------------------------ clear */
 
@@ -1034,8 +1035,35 @@ __device__ float value_noise(const float x, const float y, const float z, const 
   return acc;
 }
 
+/* sum_o gain^o (2 valuenoise(2^(o+2) (p + 0.5), seed + o) - 1) / sum_o gain^o, in [-1, 1]; the host twin is c3d_synth_host.c */
+__device__ float fractal_noise(const float x, const float y, const float z, const unsigned int seed, const int octaves, const float gain) {
+  float amp = 1.f, sum = 0.f, norm = 0.f, freq = 4.f;
+  for (int o = 0; o < octaves; o++) {
+    sum += amp * (2.f * value_noise((x + 0.5f) * freq, (y + 0.5f) * freq, (z + 0.5f) * freq, seed + (unsigned int)o) - 1.f);
+    norm += amp;
+    amp *= gain;
+    freq *= 2.f;
+  }
+  return sum / norm;
+}
+
+/* |curl F| of F = (noise(seed), noise(seed + 101), noise(seed + 202)), central differences of half a cell, scaled and shifted */
+__device__ float curl_magnitude(const float x, const float y, const float z, const float h, const unsigned int seed, const int octaves,
+                                const float gain, const float scale) {
+  const float inv = 1.f / (2.f * h);
+  const float dFz_dy = (fractal_noise(x, y + h, z, seed + 202u, octaves, gain) - fractal_noise(x, y - h, z, seed + 202u, octaves, gain)) * inv;
+  const float dFy_dz = (fractal_noise(x, y, z + h, seed + 101u, octaves, gain) - fractal_noise(x, y, z - h, seed + 101u, octaves, gain)) * inv;
+  const float dFx_dz = (fractal_noise(x, y, z + h, seed, octaves, gain) - fractal_noise(x, y, z - h, seed, octaves, gain)) * inv;
+  const float dFz_dx = (fractal_noise(x + h, y, z, seed + 202u, octaves, gain) - fractal_noise(x - h, y, z, seed + 202u, octaves, gain)) * inv;
+  const float dFy_dx = (fractal_noise(x + h, y, z, seed + 101u, octaves, gain) - fractal_noise(x - h, y, z, seed + 101u, octaves, gain)) * inv;
+  const float dFx_dy = (fractal_noise(x, y + h, z, seed, octaves, gain) - fractal_noise(x, y - h, z, seed, octaves, gain)) * inv;
+  const float cx = dFz_dy - dFy_dz, cy = dFx_dz - dFz_dx, cz = dFy_dx - dFx_dy;
+  return scale * sqrtf(cx * cx + cy * cy + cz * cz) - 1.f;
+}
+
 /* kind 0: gyroid sin X cos Y + sin Y cos Z + sin Z cos X, X = 2 pi 4 x;
-   kind 1: sum_o gain^o * valuenoise(2^(o+2) p, seed + o), mapped to [-1, 1].
+   kind 1: sum_o gain^o * valuenoise(2^(o+2) p, seed + o), mapped to [-1, 1];
+   kind 2: "vorticity magnitude": scaled |curl| of a three-component noise field (config 4 of BASELINE.json).
    Coordinates are the cell centres x_n = -0.5 + (n + 0.5) / N of the GLOBAL grid. */
 template <typename T>
 __global__ void k_synth(T *__restrict__ data, const long long nx, const long long ny, const long long nz, const long long sy,
@@ -1052,15 +1080,10 @@ __global__ void k_synth(T *__restrict__ data, const long long nx, const long lon
     if (0 == kind) {
       const float s = 6.2831853071795864769f * 4.f;
       v = sinf(s * x) * cosf(s * y) + sinf(s * y) * cosf(s * z) + sinf(s * z) * cosf(s * x);
+    } else if (1 == kind) {
+      v = fractal_noise(x, y, z, seed, octaves, gain);
     } else {
-      float amp = 1.f, sum = 0.f, norm = 0.f, freq = 4.f;
-      for (int o = 0; o < octaves; o++) {
-        sum += amp * (2.f * value_noise((x + 0.5f) * freq, (y + 0.5f) * freq, (z + 0.5f) * freq, seed + (unsigned int)o) - 1.f);
-        norm += amp;
-        amp *= gain;
-        freq *= 2.f;
-      }
-      v = sum / norm;
+      v = curl_magnitude(x, y, z, 0.5f / (float)gx, seed, octaves, gain, C3D_CURL_SCALE);
     }
     data[k * sz + j * sy + i] = (T)v;
   }

@@ -670,7 +670,7 @@ extern "C" int c3d_field_download_ext(c3d_context_t *ctx, const c3d_field_t *f, 
 
 extern "C" int c3d_field_synthesize(c3d_context_t *ctx, c3d_field_t *f, int kind, uint32_t seed, int octaves, double gain) {
   if (NULL == ctx || NULL == f) return c3d_error("c3d_field_synthesize: NULL argument");
-  if (kind < 0 || kind > 1) return c3d_error("unknown synthetic field kind %d", kind);
+  if (kind < 0 || kind > 2) return c3d_error("unknown synthetic field kind %d", kind);
   CUDA_OK(cudaSetDevice(ctx->device));
   /* the generator is a function of the GLOBAL index, so it can fill the halo too: no exchange needed */
   const long long n[3] = {(long long)f->ext[0], (long long)f->ext[1], (long long)f->ext[2]};

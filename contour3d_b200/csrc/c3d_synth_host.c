@@ -15,15 +15,11 @@
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include "c3d_synth.h"
 
 static inline uint32_t lowbias32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
-}
-
-static inline float lattice_value(const int x, const int y, const int z, const uint32_t seed) {
-  const uint32_t h = lowbias32((uint32_t)x * 0x9E3779B1u ^ lowbias32((uint32_t)y * 0x85EBCA77u ^ lowbias32((uint32_t)z * 0xC2B2AE3Du ^ seed)));
-  return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
 static float value_noise(const float x, const float y, const float z, const uint32_t seed) {
@@ -31,11 +27,16 @@ static float value_noise(const float x, const float y, const float z, const uint
   const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
   float tx = x - fx, ty = y - fy, tz = z - fz;
   tx = tx * tx * (3.f - 2.f * tx); ty = ty * ty * (3.f - 2.f * ty); tz = tz * tz * (3.f - 2.f * tz);
+  /* the nested hash of lattice_value() with its inner levels shared between corners (integer arithmetic: same values) */
+  uint32_t hz[2], hyz[4];
+  for (int dz = 0; dz < 2; dz++) hz[dz] = lowbias32((uint32_t)(iz + dz) * 0xC2B2AE3Du ^ seed);
+  for (int c = 0; c < 4; c++) hyz[c] = lowbias32((uint32_t)(iy + (c & 1)) * 0x85EBCA77u ^ hz[c >> 1]);
   float acc = 0.f;
   for (int c = 0; c < 8; c++) {
     const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
     const float w = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
-    acc += w * lattice_value(ix + dx, iy + dy, iz + dz, seed);
+    const uint32_t h = lowbias32((uint32_t)(ix + dx) * 0x9E3779B1u ^ hyz[dy + 2 * dz]);
+    acc += w * ((float)(h >> 8) * (1.0f / 16777216.0f));
   }
   return acc;
 }

@@ -114,3 +114,32 @@ def sines(n, seed=7, dtype=np.float64):
                       * np.sin(2 * np.pi * kz * gz + pz)[:, None, None])
     f = (f - f.min()) / (f.max() - f.min()) * 2.0 - 1.0
     return f.astype(dtype), [gx, gy, gz]
+
+
+def synth_host(gl, kind=1, seed=1234, octaves=5, gain=0.5, window=None, offset=(0, 0, 0), nthreads=None):
+    """The device generator's values (c3d_field_synthesize kinds 1 and 2) computed on the HOST, bit for bit, by
+    libc3d_synth_host.so (plain C, no CUDA): the window `window` = (nx, ny, nz) at global `offset` of the gl = (nx, ny, nz)
+    field, returned as a float32 array (nz, ny, nx).  Used where the CUDA library must not be involved (the CPU
+    reference arm of bench.py)."""
+    import ctypes as C
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libc3d_synth_host.so")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -m contour3d_b200.build`")
+    lib = C.CDLL(path)
+    lib.c3d_synth_host.restype = C.c_int
+    lib.c3d_synth_host.argtypes = [C.c_void_p, C.POINTER(C.c_longlong * 3), C.POINTER(C.c_longlong * 3), C.POINTER(C.c_longlong * 3),
+                                   C.c_int, C.c_uint32, C.c_int, C.c_double, C.c_int]
+    window = tuple(int(v) for v in (window if window is not None else gl))
+    out = np.empty((window[2], window[1], window[0]), dtype=np.float32)
+    if nthreads is None:
+        try:
+            nthreads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            nthreads = os.cpu_count() or 1
+    rc = lib.c3d_synth_host(out.ctypes.data, C.byref((C.c_longlong * 3)(*window)), C.byref((C.c_longlong * 3)(*[int(v) for v in offset])),
+                            C.byref((C.c_longlong * 3)(*[int(v) for v in gl])), int(kind), int(seed), int(octaves), float(gain), int(nthreads))
+    if rc != 0:
+        raise ValueError("c3d_synth_host: bad argument")
+    return out

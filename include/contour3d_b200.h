@@ -153,7 +153,8 @@ int c3d_field_exchange(c3d_context_t *ctx, c3d_field_t *field);
 /* copy the extended array to the host (tests) */
 int c3d_field_download_ext(c3d_context_t *ctx, const c3d_field_t *field, void *host);
 
-/* synthetic benchmark fields, generated on the device (kind: 0 gyroid, 1 multi-octave value noise) */
+/* synthetic benchmark fields, generated on the device (kind: 0 gyroid, 1 multi-octave value noise, 2 curl magnitude of a
+   three-component noise field); kinds 1 and 2 have a bit-identical host twin (c3d_synth_host.c) for the CPU reference arm */
 int c3d_field_synthesize(c3d_context_t *ctx, c3d_field_t *field, int kind, uint32_t seed, int octaves, double gain);
 
 /* ---- whole frame: replaces contour3d_execute's body, src/contour3d/main.c:68-146 ---- */
