@@ -228,6 +228,8 @@ def lib():
         L.c3d_field_geometry.argtypes = [vp, C.POINTER(sz * 3), C.POINTER(sz * 3), C.POINTER(sz * 3), C.POINTER(sz * 3)]
         L.c3d_field_interior.argtypes = [vp, C.POINTER(vp), C.POINTER(sz * 2)]
         L.c3d_field_mark_dirty.argtypes = [vp]
+        L.c3d_context_exchange_mode.argtypes = [vp]
+        L.c3d_field_wrap.argtypes = [vp, C.POINTER(Decomp), C.POINTER(sz * 3), i32, vp, C.POINTER(vp)]
         L.c3d_field_exchange.argtypes = [vp, vp]
         L.c3d_field_download_ext.argtypes = [vp, vp, vp]
         L.c3d_field_synthesize.argtypes = [vp, vp, i32, C.c_uint32, i32, dbl]
@@ -312,6 +314,11 @@ class Field:
 
     def exchange(self):
         _check(lib().c3d_field_exchange(self.ctx.handle, self.handle), "c3d_field_exchange")
+        return self
+
+    def mark_dirty(self):
+        """the interior changed (or is to be treated so): the next frame exchanges the halos again"""
+        _check(lib().c3d_field_mark_dirty(self.handle), "c3d_field_mark_dirty")
         return self
 
     def download_ext(self) -> np.ndarray:

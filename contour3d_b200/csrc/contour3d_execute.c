@@ -225,16 +225,20 @@ int contour3d_execute (
   scene.width = screen_sizes[0];
   scene.height = screen_sizes[1];
   scene.bg[0] = bg_color->r; scene.bg[1] = bg_color->g; scene.bg[2] = bg_color->b;
+  /* Everything up to the frame can fail on ONE rank only (a converter table over the memory bound for that rank's block, an
+     allocation, a halo that does not fit): such a rank must not leave the others alone in the frame's collectives.
+     `failed` is agreed on (maximum over the ranks, MPI_Allreduce on the Cartesian communicator) before the frame starts. */
+  int failed = 1;
   /* contour objects -> device fields (one per distinct array) */
   for (size_t n = 0; n < num_contours; n++) {
     const contour3d_contour_obj_t *obj = contour3d_contour_objs + n;
     if (SDECOMP_X1PENCIL != obj->pencil && SDECOMP_X2PENCIL != obj->pencil) {
       log_error("contour object %zu: only x pencils (x-fastest arrays) are supported, received pencil %d", n, (int)obj->pencil);
-      goto done;
+      goto agree;
     }
     if (NULL == obj->array || NULL == obj->grids[0] || NULL == obj->grids[1] || NULL == obj->grids[2]) {
       log_error("contour object %zu: array or grids missing", n);
-      goto done;
+      goto agree;
     }
     /* what contour/extend.c:160-181, 216-221 asks SimpleDecomp */
     c3d_decomp_t decomp;
@@ -243,7 +247,7 @@ int contour3d_execute (
           || 0 != sdecomp.get_myrank(sdecomp_info, obj->pencil, dir, &decomp.myrank[dir])
           || 0 != sdecomp.get_neighbours(sdecomp_info, obj->pencil, dir, decomp.neighbours[dir])) {
         log_error("sdecomp getters failed");
-        goto done;
+        goto agree;
       }
       /* no wrap-around: boundary ranks clip instead (extend.c:222-252) */
       if (0 == decomp.myrank[dir]) decomp.neighbours[dir][0] = -1;
@@ -261,13 +265,22 @@ int contour3d_execute (
     if (same < n) {
       contours[n].field = contours[same].field;
     } else {
-      if (0 != acquire_field(&decomp, obj->glsizes, &fields[n], &cached[n])) {
+      /* a device array that needs no halo room (one rank) is swept where it lies; everything else is copied into an
+         array with halo room (the padding copy of contour/extend.c:199-208) */
+      const int wrapped = c3d_field_wrap(g_ctx, &decomp, obj->glsizes, (int)sizeof(double), obj->array, &fields[n]);
+      if (1 == wrapped) {
         log_error("failed to extend domain");
-        goto done;
+        goto agree;
       }
-      if (0 != c3d_field_upload(g_ctx, fields[n], obj->array)) {
-        log_error("failed to extend domain");
-        goto done;
+      if (0 != wrapped) {
+        if (0 != acquire_field(&decomp, obj->glsizes, &fields[n], &cached[n])) {
+          log_error("failed to extend domain");
+          goto agree;
+        }
+        if (0 != c3d_field_upload(g_ctx, fields[n], obj->array)) {
+          log_error("failed to extend domain");
+          goto agree;
+        }
       }
       contours[n].field = fields[n];
     }
@@ -288,11 +301,11 @@ int contour3d_execute (
       } else {
         size_t ext[3], ext_off[3], mysizes[3], offsets[3];
         int identity = 1;
-        if (0 != c3d_field_geometry(contours[n].field, ext, ext_off, mysizes, offsets)) goto done;
+        if (0 != c3d_field_geometry(contours[n].field, ext, ext_off, mysizes, offsets)) goto agree;
         boxes[n].fn = obj->converter;
         if (0 != c3d_positions_probe(call_converter, &boxes[n], obj->grids, ext_off, ext, converter_max_bytes(), &positions[n], &identity)) {
           log_error("contour object %zu: the coordinate converter could not be tabulated", n);
-          goto done;
+          goto agree;
         }
         if (!identity) {
           has_positions[n] = 1;
@@ -306,11 +319,11 @@ int contour3d_execute (
   if (num_lines > 0) {
     lines = calloc(num_lines, sizeof(c3d_line_t));
     line_points = calloc(num_lines, sizeof(double *));
-    if (NULL == lines || NULL == line_points) { log_error("out of host memory"); goto done; }
+    if (NULL == lines || NULL == line_points) { log_error("out of host memory"); goto agree; }
   }
   for (size_t n = 0; n < num_lines; n++) {
     const contour3d_line_obj_t *obj = contour3d_line_objs + n;
-    if (0 != convert_line(obj, &line_points[n])) goto done;
+    if (0 != convert_line(obj, &line_points[n])) goto agree;
     lines[n].points = line_points[n];
     lines[n].edges[0][0] = obj->edges[0].x; lines[n].edges[0][1] = obj->edges[0].y; lines[n].edges[0][2] = obj->edges[0].z;
     lines[n].edges[1][0] = obj->edges[1].x; lines[n].edges[1][1] = obj->edges[1].y; lines[n].edges[1][2] = obj->edges[1].z;
@@ -318,6 +331,34 @@ int contour3d_execute (
     lines[n].width = obj->width;
     lines[n].color[0] = obj->color.r; lines[n].color[1] = obj->color.g; lines[n].color[2] = obj->color.b;
   }
+  failed = 0;
+agree:
+  if (g_size > 1) {
+    MPI_Comm comm = MPI_COMM_NULL;
+    /* which objects carry converter tables must be the same everywhere too: it selects how the ranks exchange data */
+    int word[1 + 2 * MAX_OBJECTS], agreed[1 + 2 * MAX_OBJECTS];
+    word[0] = failed;
+    for (size_t n = 0; n < MAX_OBJECTS; n++) {
+      const int counts = n < num_contours && !failed;
+      word[1 + n] = (counts && NULL != contours[n].positions) ? 1 : 0;                  /* "I have tables" ... */
+      word[1 + MAX_OBJECTS + n] = (counts && NULL == contours[n].positions) ? 1 : 0;    /* ... "I have none": both seen = mismatch, seen by all */
+    }
+    if (0 != sdecomp.get_comm_cart(sdecomp_info, &comm) || MPI_SUCCESS != MPI_Allreduce(word, agreed, 1 + 2 * MAX_OBJECTS, MPI_INT, MPI_MAX, comm)) {
+      log_error("the ranks could not agree on the state of the call");
+      goto done;
+    }
+    if (0 != agreed[0]) {
+      if (!failed) log_error("another rank could not prepare the frame");
+      goto done;
+    }
+    for (size_t n = 0; n < num_contours; n++) {
+      if (agreed[1 + n] && agreed[1 + MAX_OBJECTS + n]) {
+        log_error("contour object %zu: the coordinate converter is the identity on some ranks' blocks and not on others'", n);
+        goto done;
+      }
+    }
+  }
+  if (failed) goto done;
   if (0 != c3d_frame_render(g_ctx, &scene, num_contours, contours, num_lines, lines, NULL, fname)) {
     log_error("frame rendering failed");
     goto done;

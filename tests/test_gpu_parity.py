@@ -443,3 +443,57 @@ def test_full_size_visibility_shortcuts_change_nothing():
         assert dropped > 0 and none == 0, name
         assert np.array_equal(ka, kb) and np.array_equal(da, db, equal_nan=True) and np.array_equal(ia, ib), name
         assert (ka != 0).mean() > 0.1, name
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_frame_tiny_magnitude_field_takes_the_absolute_branch(ctx, dtype):
+    """A field whose values lie within ~1e-8 of the iso-value everywhere near the surface: the reference's ABSOLUTE branch
+    |v1 - v0| < 1e-8 puts every vertex on the tail corner (triangulate.c:62-71), all triangles collapse and are drawn as
+    infinite-depth blobs.  The raster's visibility shortcuts must leave such cubes alone (patch_irregular's absolute test)."""
+    n = 24
+    f = (scenes.noise(n, seed=31).astype(np.float64) * 1e-9).astype(dtype)
+    g = scenes.uniform_grids(n, n, n)
+    scene = scenes.scene(320, 180)
+    thr = float(dtype(1e-10))
+    # a second, ordinary surface in front: its occlusion must not remove the blobs behind it
+    big = scenes.noise(n, seed=32).astype(dtype)
+    contours = [dict(field=1, threshold=float(dtype(-0.3)), color=(250, 160, 60)), dict(field=0, threshold=thr, color=(60, 160, 250))]
+    img, want, depth, odepth, _ = _render_both(ctx, scene, [f, big], g, contours, [])
+    _assert_image(img, want)
+    assert np.array_equal(depth, odepth)
+    assert np.isinf(odepth).any(), "the scene was meant to contain collapsed triangles"
+
+
+def test_dropin_device_array_is_swept_in_place(ctx, tmp_path):
+    """contour3d_execute with a DEVICE double array (a GPU-resident solver): one rank needs no halo room, so the array is
+    borrowed (c3d_field_wrap) instead of copied; the image is the host-array image"""
+    import torch
+
+    g = load_golden("frame_sines24.npz")
+    grids = [g["gx"], g["gy"], g["gz"]]
+    host = np.ascontiguousarray(g["field"], dtype=np.float64)
+    dev = torch.from_numpy(host).cuda()
+    before = dev.clone()
+    out_h, out_d = str(tmp_path / "host.ppm"), str(tmp_path / "dev.ppm")
+    assert 0 == api.execute(g["scene"], grids, [host], g["contours"], g["lines"], out_h)
+    assert 0 == api.execute(g["scene"], grids, [int(dev.data_ptr())], g["contours"], g["lines"], out_d)
+    assert open(out_h, "rb").read() == open(out_d, "rb").read()
+    _assert_image(api.read_ppm(out_d), g["image"])
+    assert torch.equal(dev, before), "the caller's array must not be written"
+
+
+@pytest.mark.parametrize("kind,seed,octaves,gain", [(1, 1234, 5, 0.5), (1, 7, 7, 2.0 ** (-5.0 / 6.0)), (2, 2, 5, 0.5)])
+def test_host_generator_is_the_device_generator(ctx, kind, seed, octaves, gain):
+    """bench.py's reference arm takes its field from libc3d_synth_host.so (plain C, no CUDA); the GPU arm from
+    c3d_field_synthesize.  Same bits, or the two arms would not render the same job."""
+    n = 40
+    f = ctx.field((n, n, n), dtype=np.float32).synthesize(kind=kind, seed=seed, octaves=octaves, gain=gain)
+    try:
+        dev = f.download_ext()
+    finally:
+        f.destroy()
+    host = scenes.synth_host((n, n, n), kind=kind, seed=seed, octaves=octaves, gain=gain)
+    assert np.array_equal(dev, host), f"{int((dev != host).sum())} of {dev.size} values differ (max {np.abs(dev - host).max()})"
+    # a window of a larger field is that field's window
+    win = scenes.synth_host((n, n, n), kind=kind, seed=seed, octaves=octaves, gain=gain, window=(8, 9, 10), offset=(5, 6, 7))
+    assert np.array_equal(win, host[7:17, 6:15, 5:13])

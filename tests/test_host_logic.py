@@ -229,3 +229,27 @@ def test_sdecomp_standin_agrees_with_simpledecomp(tmp_path, ranks, dims):
         out[name] = [open(f"{prefix}.{r}").read() for r in range(ranks)]
     assert out["standin"] == out["genuine"]
     assert "nprocs" in out["genuine"][0]
+
+
+def test_host_generator_matches_the_numpy_construction():
+    """libc3d_synth_host.so (the reference arm's field source) against the numpy statement of the same noise"""
+    a = scenes.synth_host((24, 24, 24), kind=1, seed=99, octaves=4, gain=0.5)
+    b = scenes.noise(24, seed=99, octaves=4, gain=0.5)
+    assert a.dtype == np.float32 and a.shape == (24, 24, 24)
+    assert np.array_equal(a, b)
+    v = scenes.synth_host((24, 24, 24), kind=2, seed=2)
+    assert np.isfinite(v).all() and v.min() >= -1.0 and v.std() > 0.05
+
+
+def test_bench_workloads_follow_baseline_configs():
+    import argparse
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    want = {2: (512, (1920, 1080), 1, 1), 3: (1024, (3840, 2160), 1, 3), 4: (1024, (3840, 2160), 2, 4), 5: (2048, (7680, 4320), 1, 4)}
+    for c, (size, image, nfields, ncontours) in want.items():
+        w = bench.workload(argparse.Namespace(config=c, size=0, image=None, isovalues=None))
+        assert (w["size"], w["image"], len(w["fields"]), len(w["contours"])) == (size, image, nfields, ncontours)
+        assert all(v == float(np.float32(v)) for _, v in w["contours"])
