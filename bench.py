@@ -323,6 +323,7 @@ def ours(args):
 
     # ---- device-resident arm ----
     stage_sum, launches = {}, 0
+    detail_sum = [0.0] * 11
     sweep_ms, sweep_bytes = [], []
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:          # nvidia-smi needs ~0.2 s to start: it runs through the warm-up too
@@ -339,6 +340,7 @@ def ours(args):
             sweep_bytes += t["sweep_bytes"]
             for k in ("halo", "clear", "sweep", "expand", "raster", "lines", "resolve", "reduce", "shade", "pack", "download", "total"):
                 stage_sum[k] = stage_sum.get(k, 0.0) + t[k]
+            detail_sum = [a + b for a, b in zip(detail_sum, t["detail"])]
         end.record(stream)
         barrier()
         clocks.mark_end()
@@ -361,6 +363,8 @@ def ours(args):
         mine["cut_cubes_listed"] = int(sum(active[:nct]))
         mine["cubes_walked_by_raster"] = int(t["list_entries"])
         mine["culled_cubes"] = int(t["culled_cubes"])
+        names = ("barrier0", "halo_pull", "stage_clear_sweep", "to_outboxes", "barrier1", "merge_lists", "raster_lines_select", "barrier2", "work_pull", "shading", "barrier3")
+        mine["detail"] = {k: round(v / args.steps, 4) for k, v in zip(names, detail_sum)}
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
         per_rank = gathered

@@ -134,6 +134,7 @@ class Timings(C.Structure):
         ("launches", C.c_uint32),
         ("exchange_mode", C.c_uint32),
         ("list_entries", C.c_uint64),
+        ("detail", C.c_float * 16),
     ]
 
     def as_dict(self):
@@ -149,6 +150,7 @@ class Timings(C.Structure):
         d["launches"] = int(self.launches)
         d["exchange_mode"] = int(self.exchange_mode)
         d["list_entries"] = int(self.list_entries)
+        d["detail"] = [float(self.detail[i]) for i in range(11)]
         return d
 
 

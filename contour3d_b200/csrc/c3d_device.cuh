@@ -340,15 +340,36 @@ static __device__ __noinline__ ProjectedVertex exact_vertex_t(const Cam &cam, co
   const bool ok = project(cam, cut_edge_global_t<MAPPED>(f, i, j, k, f.thr, tail, head), q);
   return ProjectedVertex{q.x, q.y, q.z, ok ? 1. : 0.};
 }
+/* the same from the two corner values and positions already in registers: callers that need several vertices of a cube
+   issue all their loads first (one exposure to the memory latency instead of one per vertex -- a peer read over NVLink
+   takes microseconds) and then come here */
+static __device__ __noinline__ ProjectedVertex exact_vertex_from(const Cam &cam, const double thr, const double v0, const double v1,
+                                                                 const double x0, const double y0, const double z0,
+                                                                 const double x1, const double y1, const double z1) {
+  const V3 p0 = V3{x0, y0, z0};
+  const double dv = r_sub(v1, v0);
+  V3 c = p0;
+  if (!(fabs(dv) < 1.e-8)) {                       /* triangulate.c:62-71 */
+    const double factor = r_div(r_sub(thr, v0), dv);
+    c = v_add(p0, v_mul(factor, v_sub(V3{x1, y1, z1}, p0)));
+  }
+  V3 q = V3{0., 0., 0.};
+  const bool ok = project(cam, c, q);
+  return ProjectedVertex{q.x, q.y, q.z, ok ? 1. : 0.};
+}
 __device__ __forceinline__ ProjectedVertex exact_vertex(const FrameParams &p, const unsigned int obj, const long long i, const long long j,
                                                         const long long k, const unsigned int tail, const unsigned int head) {
   return exact_vertex_t<true>(p.cam, p.view[obj], i, j, k, tail, head);
 }
 
 /* the view a list entry refers to: this rank's own array, or (screen-partitioned frames) the array of the rank that listed it */
+/* staged: a shared-memory copy of the views in use, indexed src * ncontours + obj (nullptr: the device table p.pviews) */
 template <bool PEER>
-__device__ __forceinline__ const FieldView &entry_view(const FrameParams &p, const unsigned long long entry) {
-  if (PEER) return p.pviews[C3D_PEER_VIEW(C3D_ENTRY_SRC(entry), C3D_ENTRY_OBJ(entry))];
+__device__ __forceinline__ const FieldView &entry_view(const FrameParams &p, const FieldView *staged, const unsigned long long entry) {
+  if (PEER) {
+    if (nullptr != staged) return staged[C3D_ENTRY_SRC(entry) * p.ncontours + C3D_ENTRY_OBJ(entry)];
+    return p.pviews[C3D_PEER_VIEW(C3D_ENTRY_SRC(entry), C3D_ENTRY_OBJ(entry))];
+  }
   return p.view[C3D_ENTRY_OBJ(entry)];
 }
 

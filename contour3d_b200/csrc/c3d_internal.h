@@ -227,7 +227,7 @@ int c3d_k_shade_select_part(const FrameParams *p, const LineDev *lines_dev, cons
 /* screen-partitioned frames (c3d_sweep.cu, c3d_kernels.cu) */
 int c3d_k_expand_part(const FrameParams *fp, float near_depth, float far_depth, const void *records, const unsigned long long *nrecords,
                       unsigned long long rec_capacity, unsigned long long *outbox, unsigned long long *count, unsigned long long capacity,
-                      unsigned int *histogram, unsigned long long *cursors, unsigned long long *seg_start,
+                      unsigned int *histogram, unsigned long long *cursors, unsigned long long *seg_start, unsigned char *masks,
                       unsigned long long *per_object, unsigned int nobjects, int sm_count, cudaStream_t s);
 int c3d_k_clear_part(Pixel *canvas, const Partition *part, long long w, long long h, int sm_count, cudaStream_t s);
 int c3d_k_to_float(const double *in, float *out, size_t n, cudaStream_t s);

@@ -310,20 +310,43 @@ extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int
 #define C3D_NO_BOX 0xffffffffffffffffull
 
 template <bool MAPPED, bool PEER>
-__device__ __forceinline__ void raster_triangle(const FrameParams &p, const unsigned long long entry, const unsigned int s,
+__device__ __forceinline__ void raster_triangle(const FrameParams &p, const FieldView *staged, const unsigned long long entry, const unsigned int s,
                                                 const unsigned long long box, Pixel *__restrict__ canvas) {
   const unsigned int obj = C3D_ENTRY_OBJ(entry), code = C3D_ENTRY_CODE(entry);
-  const FieldView &f = entry_view<PEER>(p, entry);
+  const FieldView &f = entry_view<PEER>(p, staged, entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
   Tri2D t;
   /* one out-of-line copy of "cut the edge and project" serves the three vertices: the kernel's code must stay
      within reach of the instruction cache while its warps sit in different phases */
+  if (MAPPED && nullptr != f.map) {
 #pragma unroll
-  for (int m = 0; m < 3; m++) {
-    const ProjectedVertex v = exact_vertex_t<MAPPED>(p.cam, f, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
-    if (0. == v.w) return;                          /* render.c:62-72 */
-    t.q[m] = V3{v.x, v.y, v.z};
+    for (int m = 0; m < 3; m++) {
+      const ProjectedVertex v = exact_vertex_t<MAPPED>(p.cam, f, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+      if (0. == v.w) return;                          /* render.c:62-72 */
+      t.q[m] = V3{v.x, v.y, v.z};
+    }
+  } else {
+    /* all loads of the three vertices first: six corner values, six coordinates */
+    const long long base = k * f.sz + j * f.sy + i;
+    double val[6];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
+      val[2 * m] = ld_value(f, base + ((tail & 1u) + ((tail & 2u) ? f.sy : 0ll) + ((tail & 4u) ? f.sz : 0ll)));
+      val[2 * m + 1] = ld_value(f, base + ((head & 1u) + ((head & 2u) ? f.sy : 0ll) + ((head & 4u) ? f.sz : 0ll)));
+    }
+    const double gx0 = __ldg(f.g[0] + i), gx1 = __ldg(f.g[0] + i + 1), gy0 = __ldg(f.g[1] + j), gy1 = __ldg(f.g[1] + j + 1);
+    const double gz0 = __ldg(f.g[2] + k), gz1 = __ldg(f.g[2] + k + 1);
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
+      const ProjectedVertex v = exact_vertex_from(p.cam, f.thr, val[2 * m], val[2 * m + 1],
+                                                  (tail & 1u) ? gx1 : gx0, (tail & 2u) ? gy1 : gy0, (tail & 4u) ? gz1 : gz0,
+                                                  (head & 1u) ? gx1 : gx0, (head & 2u) ? gy1 : gy0, (head & 4u) ? gz1 : gz0);
+      if (0. == v.w) return;                          /* render.c:62-72 */
+      t.q[m] = V3{v.x, v.y, v.z};
+    }
   }
   setup_projected(p.cam, t);
   const unsigned long long mykey = winner_key(f, obj, i, j, k, s);
@@ -442,7 +465,7 @@ __device__ __forceinline__ bool hiz_hidden(const HiZ &z, const CullCam &q, const
  * With a depth complexity of ~20 most cubes of a turbulent field are hidden.
  */
 template <bool MAPPED, bool PEER>
-__device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned long long entry, const Pixel *__restrict__ canvas, const HiZ &hiz) {
+__device__ __forceinline__ bool cube_hidden(const FrameParams &p, const FieldView *staged, const unsigned long long entry, const Pixel *__restrict__ canvas, const HiZ &hiz) {
   /* A triangle whose vertices have collapsed onto one cube corner is drawn by the reference as a blob: the
      clamped area (render.c:103-106) makes all three weights +-0, every pixel of the +-1 pixel box passes the
      inside test and the depth is 1 / +-0 = +-inf -- it beats any finite depth.  Collapse needs an interpolation
@@ -450,7 +473,7 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
      cubes of every 4 x 8 patch where that cannot be excluded (C3D_ENTRY_IRREGULAR) and those are never culled. */
   if (C3D_ENTRY_IRREGULAR(entry)) return false;
   const CullCam &q = p.cull;
-  const FieldView &f = entry_view<PEER>(p, entry);
+  const FieldView &f = entry_view<PEER>(p, staged, entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
   float xlo = 3.e38f, xhi = -3.e38f, ylo = 3.e38f, yhi = -3.e38f, znear = -3.e38f, tlo = 3.e38f, thi = -3.e38f;
   if (MAPPED && nullptr != f.map) {
@@ -525,12 +548,12 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const unsigned
  * does not fit these assumptions (ferr > 0.02, vertices near the screen plane, NaN) keeps the triangle.
  */
 template <bool MAPPED, bool PEER>
-__device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsigned long long entry, const unsigned int s,
+__device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const FieldView *staged, const unsigned long long entry, const unsigned int s,
                                                 const Pixel *__restrict__ canvas, unsigned long long &box) {
   box = C3D_NO_BOX;
   const CullCam &q = p.cull;
   const unsigned int code = C3D_ENTRY_CODE(entry);
-  const FieldView &f = entry_view<PEER>(p, entry);
+  const FieldView &f = entry_view<PEER>(p, staged, entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
   const long long base = k * f.sz + j * f.sy + i;
@@ -546,11 +569,20 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const unsi
   /* fp32 with explicit fused multiply-adds (the translation unit is compiled with -fmad=false for the exact fp64 path;
      here fewer roundings only help) and ONE reciprocal per vertex: rcp is within 1 ulp and the product adds half an ulp,
      so the factor is off by < 2e-7 on top of the bound below -- covered by the extra 3e-7 in ferr */
+  /* the six corner values of the three vertices are requested before any is used: the loop below stays rolled (code size),
+     but meets the memory latency once, not three times -- in a partitioned frame these may be peer reads over NVLink */
+  float tv[3], hv[3];
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
+    tv[m] = (float)ld_value(f, base + ((tail & 1u) + ((tail & 2u) ? f.sy : 0ll) + ((tail & 4u) ? f.sz : 0ll)));
+    hv[m] = (float)ld_value(f, base + ((head & 1u) + ((head & 2u) ? f.sy : 0ll) + ((head & 4u) ? f.sz : 0ll)));
+  }
 #pragma unroll 1
   for (int m = 0; m < 3; m++) {
     const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
-    const float v0 = (float)ld_value(f, base + ((tail & 1u) + ((tail & 2u) ? f.sy : 0ll) + ((tail & 4u) ? f.sz : 0ll)));
-    const float v1 = (float)ld_value(f, base + ((head & 1u) + ((head & 2u) ? f.sy : 0ll) + ((head & 4u) ? f.sz : 0ll)));
+    const float v0 = 0 == m ? tv[0] : (1 == m ? tv[1] : tv[2]);
+    const float v1 = 0 == m ? hv[0] : (1 == m ? hv[1] : hv[2]);
     const float dv = v1 - v0;
     const float inv = __frcp_rn(dv);
     const float ferr = 2.00002e-7f * (fabsf(thr) + fabsf(v0) + fabsf(v1)) * fabsf(inv) + 3.e-7f;
@@ -614,6 +646,20 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
   __shared__ unsigned long long s_queue[4][64];       /* triangles that passed the pre-test, waiting for a full warp */
   __shared__ unsigned long long s_qbox[4][64];        /* ... and the pixel boxes the pre-test left them */
   __shared__ unsigned char s_qsrc[4][PEER ? 64 : 1];  /* ... and the rank their cube indices refer to */
+  /* the views of a partitioned frame live in device memory (ranks x objects of them); the few in use are staged here, so that
+     the per-cube tests read them like the single-rank kernel reads its constant bank */
+  constexpr unsigned int STAGED = PEER ? 32u : 1u;
+  __shared__ FieldView s_views[STAGED];
+  const FieldView *staged = nullptr;
+  if (PEER && (unsigned int)p.part.nranks * p.ncontours <= STAGED) {
+    const unsigned int words = (unsigned int)(sizeof(FieldView) / 4u);
+    for (unsigned int q = threadIdx.x; q < (unsigned int)p.part.nranks * p.ncontours * words; q += blockDim.x) {
+      const unsigned int v = q / words, w = q % words;
+      reinterpret_cast<unsigned int *>(s_views)[q] = reinterpret_cast<const unsigned int *>(p.pviews + C3D_PEER_VIEW(v / p.ncontours, v % p.ncontours))[w];
+    }
+    __syncthreads();
+    staged = s_views;
+  }
   unsigned long long n = *count;
   if (n > capacity) n = capacity;
   const unsigned int lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -629,7 +675,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
     if (base + lane < n) {
       entry = __ldg(list + base + lane);
       ntri = __ldg(p.tab.count + C3D_ENTRY_CODE(entry));
-      if (p.cull.enabled && cube_hidden<MAPPED, PEER>(p, entry, canvas, hiz)) ntri = 0u;
+      if (p.cull.enabled && cube_hidden<MAPPED, PEER>(p, staged, entry, canvas, hiz)) ntri = 0u;
     }
     const unsigned int alive = __ballot_sync(C3D_FULL_MASK, ntri > 0u);
     hidden_total += __popc(__ballot_sync(C3D_FULL_MASK, base + lane < n)) - __popc(alive);
@@ -663,7 +709,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
         const unsigned int s = t0 + lane - s_first[wid][src];
         mine = C3D_TRI_PACK(e, s);
         mysrc = C3D_ENTRY_SRC(e);
-        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden<MAPPED, PEER>(p, e, s, canvas, mybox));
+        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden<MAPPED, PEER>(p, staged, e, s, canvas, mybox));
       }
       const unsigned int kept = __ballot_sync(C3D_FULL_MASK, keep);
       hidden_tris += __popc(__ballot_sync(C3D_FULL_MASK, t0 + lane < total)) - __popc(kept);
@@ -686,7 +732,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
         if (lane + 32u < queued) { s_queue[wid][lane] = rest; s_qbox[wid][lane] = restb; if (PEER) s_qsrc[wid][lane] = rests; }
         queued -= 32u;
         __syncwarp();
-        raster_triangle<MAPPED, PEER>(p, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), qb, canvas);
+        raster_triangle<MAPPED, PEER>(p, staged, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), qb, canvas);
       }
     }
   }
@@ -694,7 +740,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
   if (lane < queued) {
     const unsigned long long q = s_queue[wid][lane];
     const unsigned long long qs = PEER ? (unsigned long long)s_qsrc[wid][lane] << C3D_ENTRY_SRC_SHIFT : 0ull;
-    raster_triangle<MAPPED, PEER>(p, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), s_qbox[wid][lane], canvas);
+    raster_triangle<MAPPED, PEER>(p, staged, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), s_qbox[wid][lane], canvas);
   }
   if (0u == lane && nullptr != culled) {
     if (hidden_total > 0u) atomicAdd(culled, (unsigned long long)hidden_total);

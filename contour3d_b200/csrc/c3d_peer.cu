@@ -371,6 +371,7 @@ __global__ void __launch_bounds__(1024) k_merge_scan(const MergeSources src, con
 }
 
 #define MERGE_THREADS 256
+#define MERGE_QUADS 4          /* 16-byte requests a thread keeps in flight: a peer read is a round trip over NVLink */
 __global__ void __launch_bounds__(MERGE_THREADS) k_merge_copy(const MergeSources src, const int n, const int me,
                                                               const unsigned long long *__restrict__ merge_base,
                                                               unsigned long long *__restrict__ list, const unsigned long long capacity) {
@@ -401,7 +402,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_copy(const MergeSources
   const unsigned int total = prefix[C3D_DEPTH_BUCKETS];
   const unsigned long long start = src.seg_start[s][me];
   const unsigned long long *outbox = src.outbox[s] + start;
-  for (unsigned int e = blockIdx.x * MERGE_THREADS + threadIdx.x; e < total; e += gridDim.x * MERGE_THREADS) {
+  /* entries travel in aligned pairs (16 bytes); the segment may start on an odd entry */
+  const unsigned int odd = (unsigned int)(start & 1ull);
+  const unsigned int npairs = (total + odd + 1u) / 2u;
+  const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(outbox - odd);
+  auto place = [&](const unsigned int e, const unsigned long long entry) {
     /* largest b with prefix[b] <= e */
     unsigned int lo = 0u, hi = C3D_DEPTH_BUCKETS;
     while (hi - lo > 1u) {
@@ -409,14 +414,31 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_copy(const MergeSources
       if (prefix[mid] <= e) lo = mid; else hi = mid;
     }
     const unsigned long long to = merge_base[lo * (unsigned int)n + (unsigned int)s] + (e - prefix[lo]);
-    if (to < capacity) list[to] = outbox[e];
+    if (to < capacity) list[to] = entry;
+  };
+  const unsigned int stride = gridDim.x * MERGE_THREADS;
+  for (unsigned int p0 = blockIdx.x * MERGE_THREADS + threadIdx.x; p0 < npairs; p0 += MERGE_QUADS * stride) {
+    ulonglong2 got[MERGE_QUADS];
+#pragma unroll
+    for (int q = 0; q < MERGE_QUADS; q++) {
+      const unsigned int p = p0 + (unsigned int)q * stride;
+      got[q] = p < npairs ? pairs[p] : make_ulonglong2(0ull, 0ull);
+    }
+#pragma unroll
+    for (int q = 0; q < MERGE_QUADS; q++) {
+      const unsigned int p = p0 + (unsigned int)q * stride;
+      if (p >= npairs) break;
+      const unsigned int first = 2u * p;                       /* index of got.x counted from the aligned start */
+      if (first >= odd && first - odd < total) place(first - odd, got[q].x);
+      if (first + 1u >= odd && first + 1u - odd < total) place(first + 1u - odd, got[q].y);
+    }
   }
 }
 
 int c3d_k_merge_lists(const MergeSources *src, int nranks, int me, unsigned long long *merge_base, unsigned long long *list,
                       unsigned long long *count, unsigned long long capacity, cudaStream_t s) {
   k_merge_scan<<<1, 1024, 0, s>>>(*src, nranks, me, merge_base, count);
-  k_merge_copy<<<dim3(96, (unsigned int)nranks), MERGE_THREADS, 0, s>>>(*src, nranks, me, merge_base, list, capacity);
+  k_merge_copy<<<dim3(148, (unsigned int)nranks), MERGE_THREADS, 0, s>>>(*src, nranks, me, merge_base, list, capacity);
   return (int)cudaGetLastError();
 }
 

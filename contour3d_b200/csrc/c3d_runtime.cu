@@ -119,6 +119,7 @@ enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_CULLED_TRIS = 3, CNT_SHADE
        CNT_TOTAL };
 #define C3D_HIZ_CUTS_MULTI ""
 #define C3D_HIZ_CUTS_SINGLE ""
+#define C3D_DETAIL_EVENTS 20
 enum { EV_START, EV_HALO, EV_CLEAR, EV_SWEEP, EV_EXPAND, EV_RASTER, EV_LINES, EV_RESOLVE, EV_REDUCE0, EV_SHADE, EV_REDUCE1, EV_PACK, EV_DOWNLOAD, EV_COUNT };
 
 /*
@@ -143,6 +144,8 @@ struct c3d_context {
   c3d_peer peer;                                   /* device-to-device exchange between the ranks of this node */
   Exchange xa;
   unsigned long long *merge_base, *part_cursors;   /* C3D_DEPTH_BUCKETS x ranks each: merged-list offsets / outbox cursors */
+  unsigned char *part_masks;                       /* 32 bytes per sweep record: which ranks draw each of its cubes */
+  size_t part_masks_cap;                           /* in records */
   int tile_shift;                                  /* log2 of the screen-tile edge of partitioned frames */
   void *table_mem;
   DevTables tab;
@@ -184,6 +187,8 @@ struct c3d_context {
   cudaEvent_t ev_upload[2 * C3D_MAX_OBJECTS];   /* start/stop pairs of the uploads since the last frame */
   int nuploads;
   cudaEvent_t ev_sweep[C3D_MAX_OBJECTS + 1];
+  cudaEvent_t ev_detail[C3D_DETAIL_EVENTS];      /* screen-partitioned frames: the steps between the stage events */
+  int ndetail;
   c3d_timings_t last;
 };
 
@@ -214,6 +219,7 @@ static int context_init(c3d_context *ctx, const int comm_rank, const int comm_si
   for (int e = 0; e < EV_COUNT; e++) CUDA_OK(cudaEventCreate(&ctx->ev[e]));
   for (int e = 0; e <= C3D_MAX_OBJECTS; e++) CUDA_OK(cudaEventCreate(&ctx->ev_sweep[e]));
   for (int e = 0; e < 2 * C3D_MAX_OBJECTS; e++) CUDA_OK(cudaEventCreate(&ctx->ev_upload[e]));
+  for (int e = 0; e < C3D_DETAIL_EVENTS; e++) CUDA_OK(cudaEventCreate(&ctx->ev_detail[e]));
   /* case tables -> device */
   c3d_tables_t *host_tab = (c3d_tables_t *)malloc(sizeof(c3d_tables_t));
   if (NULL == host_tab) return c3d_error("out of host memory");
@@ -317,7 +323,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
   release_exchange(ctx);
-  cudaFree(ctx->merge_base); cudaFree(ctx->part_cursors);
+  cudaFree(ctx->merge_base); cudaFree(ctx->part_cursors); cudaFree(ctx->part_masks);
   c3d_peer_destroy(&ctx->peer);
   cudaFree(ctx->table_mem);
   cudaFree(ctx->shade.work); cudaFree(ctx->shade.counters); cudaFree(ctx->shade.pix); cudaFree(ctx->shade.table); cudaFree(ctx->shade.vlist); cudaFree(ctx->shade.vn);
@@ -330,6 +336,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   for (int e = 0; e < EV_COUNT; e++) if (ctx->ev[e]) cudaEventDestroy(ctx->ev[e]);
   for (int e = 0; e <= C3D_MAX_OBJECTS; e++) if (ctx->ev_sweep[e]) cudaEventDestroy(ctx->ev_sweep[e]);
   for (int e = 0; e < 2 * C3D_MAX_OBJECTS; e++) if (ctx->ev_upload[e]) cudaEventDestroy(ctx->ev_upload[e]);
+  for (int e = 0; e < C3D_DETAIL_EVENTS; e++) if (ctx->ev_detail[e]) cudaEventDestroy(ctx->ev_detail[e]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
   free(ctx);
@@ -1044,7 +1051,7 @@ static int ensure_exchange(c3d_context *ctx, const size_t w, const size_t h, con
   x.off_hist = at; at += round_up((size_t)n * C3D_DEPTH_BUCKETS * sizeof(unsigned int), 256);
   x.off_rgba = at; at += round_up(x.npix * 4, 256);
   x.off_seg = at; at += round_up((size_t)n * x.seg_cap * sizeof(WorkItem), 256);
-  x.off_out = at; at += x.out_cap * 8;
+  x.off_out = at; at += x.out_cap * 8 + 256;     /* readers fetch aligned pairs: room for one entry beyond the last */
   x.bytes = at;
   void *base = NULL;
   const cudaError_t err = cudaMalloc(&base, x.bytes);
@@ -1088,9 +1095,14 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     return c3d_error("this frame needs the NCCL path (coordinate converter, unaligned rows or objects of different shapes), but the ranks share a GPU");
   }
   c3d_peer *peer = &ctx->peer;
+  ctx->ndetail = 0;
+  /* detail mark n closes step n of c3d_timings_t.detail (partitioned frames only) */
+  auto mark = [&]() { if (part && ctx->ndetail < C3D_DETAIL_EVENTS) cudaEventRecord(ctx->ev_detail[ctx->ndetail++], s); };
   CUDA_OK(cudaEventRecord(ctx->ev[EV_START], s));
+  mark();
   /* halos */
   if (part) { LAUNCH_OK(c3d_peer_barrier(peer, s)); launches += 1; }    /* every rank's arrays are complete; last frame's buffers are free */
+  mark();                                                               /* detail[0]: barrier at the start */
   for (size_t n = 0; n < nc; n++) {
     c3d_field *f = (c3d_field *)contours[n].field;
     if (!f->halo_valid) {
@@ -1103,6 +1115,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     }
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_HALO], s));
+  mark();                                                               /* detail[1]: halo pull */
   /* descriptors */
   FrameParams fp;
   memset(&fp, 0, sizeof(fp));
@@ -1166,6 +1179,13 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     ctx->rec_cap = want;
   }
   if (part && 0 != ensure_exchange(ctx, scene->width, scene->height, std::max<size_t>(ctx->list_cap, 64))) return 1;
+  if (part && ctx->part_masks_cap < ctx->rec_cap) {
+    cudaFree(ctx->part_masks);
+    ctx->part_masks = NULL;
+    ctx->part_masks_cap = 0;
+    CUDA_OK(cudaMalloc(&ctx->part_masks, std::max<size_t>(ctx->rec_cap, 1) * 32));
+    ctx->part_masks_cap = ctx->rec_cap;
+  }
   Exchange &xa = ctx->xa;
   unsigned int *rgba_out = ctx->rgba;                /* where finished colours go: the writer's image */
   if (part) rgba_out = (unsigned int *)((char *)xa.peer[0] + xa.off_rgba);
@@ -1234,6 +1254,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   }
   CUDA_OK(cudaEventRecord(ctx->ev_sweep[nsweeps], s));
   CUDA_OK(cudaEventRecord(ctx->ev[EV_SWEEP], s));
+  mark();                                                               /* detail[2]: staging, clear, sweeps */
   if (used_records || part) {
     /* range of the view depth n.(p - cam) over the corners of every array: the slabs of the front-to-back order.
        Partitioned frames take the corners of the GLOBAL domain, so that a bucket means the same depth on every rank. */
@@ -1277,9 +1298,10 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
       if (!(near_depth > far_depth)) { near_depth = 1.; far_depth = 0.; }      /* degenerate / NaN coordinates: one bucket */
       LAUNCH_OK(c3d_k_expand_part(&fp, (float)near_depth, (float)far_depth, ctx->records, ctx->counts_dev + CNT_REC, ctx->rec_cap,
                                   (unsigned long long *)(xa.base + xa.off_out), ctx->counts_dev + CNT_OUT, xa.out_cap,
-                                  (unsigned int *)(xa.base + xa.off_hist), ctx->part_cursors, (unsigned long long *)(xa.base + xa.off_seg_start),
+                                  (unsigned int *)(xa.base + xa.off_hist), ctx->part_cursors, (unsigned long long *)(xa.base + xa.off_seg_start), ctx->part_masks,
                                   ctx->counts_dev + CNT_OBJ, (unsigned int)nc, ctx->sm_count, s));
       launches += 3;
+      mark();                                                           /* detail[3]: cubes -> outboxes (count, scan, scatter) */
     } else {
       const int sorted = fp.cull.enabled && near_depth > far_depth;
       LAUNCH_OK(c3d_k_expand(&fp, sorted, (float)near_depth, (float)far_depth, ctx->records, ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->list,
@@ -1291,6 +1313,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   if (part) {
     /* 2b. all outboxes are complete -> every rank pulls what is addressed to it into ONE nearest-first list */
     LAUNCH_OK(c3d_peer_barrier(peer, s));
+    mark();                                                             /* detail[4]: barrier (all outboxes complete) */
     MergeSources ms;
     memset(&ms, 0, sizeof(ms));
     for (int r = 0; r < ctx->size; r++) {
@@ -1301,6 +1324,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     }
     LAUNCH_OK(c3d_k_merge_lists(&ms, ctx->size, ctx->rank, ctx->merge_base, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, s));
     launches += 3;
+    mark();                                                             /* detail[5]: pull + merge of the lists */
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_EXPAND], s));
   /* 2. tessellate + rasterise every active cube, contours in one launch (src/contour3d/main.c:105-117) */
@@ -1337,7 +1361,9 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
                                       (unsigned int *)(xa.base + xa.off_nseg), ctx->counts_dev + CNT_SEG_OVER, ctx->sm_count, s));
     launches += 1;
     CUDA_OK(cudaEventRecord(ctx->ev[EV_RESOLVE], s));
+    mark();                                                             /* detail[6]: raster, lines, select */
     LAUNCH_OK(c3d_peer_barrier(peer, s));
+    mark();                                                             /* detail[7]: barrier (all work segments complete) */
     WorkSources ws;
     memset(&ws, 0, sizeof(ws));
     for (int r = 0; r < ctx->size; r++) {
@@ -1349,10 +1375,12 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
                               ctx->counts_dev + CNT_SEG_OVER, s));
     launches += 2;
     CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
+    mark();                                                             /* detail[8]: pull of the shading work */
     /* 5'. shade what this rank's cubes have won, anywhere on the screen, straight into the writer's image */
     LAUNCH_OK(c3d_k_shade_finish(&fp, rgba_out, &ctx->shade, ctx->counts_dev + CNT_SHADE_SPILL, ctx->sm_count, s));
     launches += 3;
     CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
+    mark();                                                             /* detail[9]: shading */
     /* 6'. the image is complete when everybody is done; a buffer that overflowed anywhere makes everybody redo the frame */
     LAUNCH_OK(c3d_k_overflow_flag(ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->counts_dev + CNT_LIST, ctx->list_cap, ctx->counts_dev + CNT_OUT, xa.out_cap,
                                   ctx->counts_dev + CNT_SEG_OVER, (unsigned long long *)(xa.base + xa.off_flags), s));
@@ -1363,6 +1391,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     LAUNCH_OK(c3d_k_flags_max(&fs, ctx->size, ctx->counts_dev + CNT_OVERFLOW, s));
     launches += 3;
     CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE1], s));
+    mark();                                                             /* detail[10]: barrier at the end (+ overflow agreement) */
     if (0 == ctx->rank) {
       LAUNCH_OK(c3d_k_pack((const unsigned int *)(xa.base + xa.off_rgba), scene->bg, cam.w, cam.h, ctx->ppm_dev, s));
       launches += 1;
@@ -1470,6 +1499,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   t->launches = launches;
   t->nsweeps = nsweeps;
   t->exchange_mode = (uint32_t)(ctx->size < 2 ? 0 : (part ? 2 : 1));
+  for (int d = 0; d + 1 < ctx->ndetail && d < 16; d++) cudaEventElapsedTime(&t->detail[d], ctx->ev_detail[d], ctx->ev_detail[d + 1]);
   t->list_entries = ctx->counts_host[CNT_LIST];
   t->culled_cubes = ctx->counts_host[CNT_CULLED];
   t->culled_triangles = ctx->counts_host[CNT_CULLED_TRIS];

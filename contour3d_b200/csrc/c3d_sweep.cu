@@ -686,30 +686,66 @@ __device__ __forceinline__ unsigned int cube_owners(const FrameParams &p, const 
   return mask;
 }
 
-/* cubes per (destination rank, depth bucket); histogram[r * C3D_DEPTH_BUCKETS + b] */
+/*
+ * Pass 1: who draws each cut cube?  Warp-cooperative -- a warp takes 32 records and spreads their 1..32 cut cubes over
+ * its lanes (the records hold 3-4 on average; one thread per record would idle most lanes through the eight
+ * projections of cube_owners()).  The answer is kept, one byte per cube at masks[record * 32 + bit], for pass 2, and
+ * counted per (destination rank, depth bucket): histogram[r * C3D_DEPTH_BUCKETS + b].
+ */
 __global__ void __launch_bounds__(256) k_part_count(const __grid_constant__ FrameParams p, const DepthOrder o,
                                                     const SweepRecord *__restrict__ records, const unsigned long long *__restrict__ nrecords,
-                                                    const unsigned long long rec_capacity, unsigned int *__restrict__ histogram) {
+                                                    const unsigned long long rec_capacity, unsigned char *__restrict__ masks,
+                                                    unsigned int *__restrict__ histogram) {
   extern __shared__ unsigned int local[];
+  __shared__ unsigned int s_active[8][32], s_first[8][32], s_xj[8][32], s_kobj[8][32], s_bucket[8][32];
   const unsigned int nbins = (unsigned int)p.part.nranks * C3D_DEPTH_BUCKETS;
   for (unsigned int b = threadIdx.x; b < nbins; b += blockDim.x) local[b] = 0u;
   __syncthreads();
   unsigned long long n = *nrecords;
   if (n > rec_capacity) n = rec_capacity;
-  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(records) + 2ull * q + 1ull);
-    unsigned int active = b.x;
-    const unsigned int x = b.z & 65535u, j = b.z >> 16, k = b.w & 65535u, obj = b.w >> 16;
-    const unsigned int bucket = depth_bucket(p, o, obj, x, j, k);
-    const FieldView &f = p.view[obj];
-    while (active) {
-      const int bit = __ffs((int)active) - 1;
-      active &= active - 1u;
-      unsigned int owners = cube_owners(p, f, (long long)x + (bit & 3), (long long)j + (bit >> 2), (long long)k);
-      while (owners) {
-        const int r = __ffs((int)owners) - 1;
-        owners &= owners - 1u;
-        atomicAdd(local + (unsigned int)r * C3D_DEPTH_BUCKETS + bucket, 1u);
+  const unsigned int lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long q0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); q0 < n; q0 += stride) {
+    const unsigned long long q = q0 + lane;
+    uint4 b = make_uint4(0u, 0u, 0u, 0u);
+    if (q < n) b = __ldg(reinterpret_cast<const uint4 *>(records) + 2ull * q + 1ull);
+    const unsigned int active = b.x, mine = __popc(active);
+    unsigned int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned int up = __shfl_up_sync(SW_FULL, incl, d);
+      if (lane >= (unsigned int)d) incl += up;
+    }
+    const unsigned int total = __shfl_sync(SW_FULL, incl, 31), excl = incl - mine;
+    __syncwarp();
+    s_active[wid][lane] = active;
+    s_first[wid][lane] = excl;
+    s_xj[wid][lane] = b.z;
+    s_kobj[wid][lane] = b.w;
+    s_bucket[wid][lane] = 0u != mine ? depth_bucket(p, o, b.w >> 16, b.z & 65535u, b.z >> 16, b.w & 65535u) : 0u;
+    __syncwarp();
+    for (unsigned int t0 = 0; t0 < total; t0 += 32u) {
+      /* record of cube t0 + lane: the last record with cubes whose first cube is <= it */
+      const bool starts_here = mine > 0u && excl >= t0 && excl < t0 + 32u;
+      const unsigned int starts = __reduce_or_sync(SW_FULL, starts_here ? 1u << (excl - t0) : 0u);
+      const unsigned int has = __ballot_sync(SW_FULL, mine > 0u);
+      const unsigned int before = __popc(__ballot_sync(SW_FULL, mine > 0u && excl < t0));
+      if (t0 + lane < total) {
+        /* the (before + started so far)-th record that has cubes, counted over the lanes that have any */
+        const unsigned int nth = before + __popc(starts & (0xffffffffu >> (31u - lane)));      /* >= 1 */
+        const unsigned int src = __fns(has, 0u, (int)nth);
+        const unsigned int within = t0 + lane - s_first[wid][src];
+        const unsigned int bit = __fns(s_active[wid][src], 0u, (int)within + 1);
+        const unsigned int xj = s_xj[wid][src], kobj = s_kobj[wid][src];
+        const FieldView &f = p.view[kobj >> 16];
+        unsigned int owners = cube_owners(p, f, (long long)(xj & 65535u) + (bit & 3u), (long long)(xj >> 16) + (bit >> 2), (long long)(kobj & 65535u));
+        masks[(q0 + src) * 32ull + bit] = (unsigned char)owners;
+        const unsigned int bucket = s_bucket[wid][src];
+        while (owners) {
+          const int r = __ffs((int)owners) - 1;
+          owners &= owners - 1u;
+          atomicAdd(local + (unsigned int)r * C3D_DEPTH_BUCKETS + bucket, 1u);
+        }
       }
     }
   }
@@ -750,7 +786,8 @@ __global__ void __launch_bounds__(1024) k_part_scan(const unsigned int *__restri
    with this rank (bits 61-63): their cube indices refer to ITS array */
 __global__ void __launch_bounds__(256) k_part_expand(const __grid_constant__ FrameParams p, const DepthOrder o,
                                                      const SweepRecord *__restrict__ records, const unsigned long long *__restrict__ nrecords,
-                                                     const unsigned long long rec_capacity, unsigned long long *__restrict__ outbox,
+                                                     const unsigned long long rec_capacity, const unsigned char *__restrict__ masks,
+                                                     unsigned long long *__restrict__ outbox,
                                                      const unsigned long long capacity, unsigned long long *__restrict__ cursors,
                                                      unsigned long long *__restrict__ per_object, const unsigned int nobjects) {
   unsigned long long n = *nrecords;
@@ -778,15 +815,17 @@ __global__ void __launch_bounds__(256) k_part_expand(const __grid_constant__ Fra
     const unsigned long long flag = (p.cull.enabled && patch_irregular(f, x, j, k, active)) ? C3D_ENTRY_IRREGULAR_BIT : 0ull;
     const unsigned long long pl = a.x | ((unsigned long long)(b.y & 15u) << 32), ql = a.y | ((unsigned long long)((b.y >> 4) & 15u) << 32);
     const unsigned long long pu = a.z | ((unsigned long long)((b.y >> 8) & 15u) << 32), qu = a.w | ((unsigned long long)((b.y >> 12) & 15u) << 32);
-    /* who must draw each of my cubes; then one cursor bump per (record, rank) */
+    /* who must draw each of my cubes (pass 1 left one byte per cube); then one cursor bump per (record, rank) */
     unsigned char owners[32];
     unsigned int present = 0u;
     {
+      const uint4 m0 = __ldg(reinterpret_cast<const uint4 *>(masks) + 2ull * q), m1 = __ldg(reinterpret_cast<const uint4 *>(masks) + 2ull * q + 1ull);
+      const unsigned int word[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
       unsigned int todo = active;
       while (todo) {
         const int bit = __ffs((int)todo) - 1;
         todo &= todo - 1u;
-        const unsigned int m = cube_owners(p, f, (long long)x + (bit & 3), (long long)j + (bit >> 2), (long long)k);
+        const unsigned int m = (word[bit >> 2] >> (8 * (bit & 3))) & 255u;
         owners[bit] = (unsigned char)m;
         present |= m;
       }
@@ -989,7 +1028,7 @@ extern "C" int c3d_k_expand(const FrameParams *fp, int sorted, float near_depth,
 
 extern "C" int c3d_k_expand_part(const FrameParams *fp, float near_depth, float far_depth, const void *records, const unsigned long long *nrecords,
                                  unsigned long long rec_capacity, unsigned long long *outbox, unsigned long long *count, unsigned long long capacity,
-                                 unsigned int *histogram, unsigned long long *cursors, unsigned long long *seg_start,
+                                 unsigned int *histogram, unsigned long long *cursors, unsigned long long *seg_start, unsigned char *masks,
                                  unsigned long long *per_object, unsigned int nobjects, int sm_count, cudaStream_t s) {
   const SweepRecord *rec = static_cast<const SweepRecord *>(records);
   const int nranks = fp->part.nranks;
@@ -1002,8 +1041,8 @@ extern "C" int c3d_k_expand_part(const FrameParams *fp, float near_depth, float 
   if (cudaSuccess != err) return (int)err;
   err = cudaFuncSetAttribute(k_part_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bins * sizeof(unsigned int)));
   if (cudaSuccess != err) return (int)err;
-  k_part_count<<<sm_count * 2, 256, bins * sizeof(unsigned int), s>>>(*fp, o, rec, nrecords, rec_capacity, histogram);
+  k_part_count<<<sm_count * 2, 256, bins * sizeof(unsigned int), s>>>(*fp, o, rec, nrecords, rec_capacity, masks, histogram);
   k_part_scan<<<1, 1024, 0, s>>>(histogram, nranks, cursors, seg_start, count);
-  k_part_expand<<<sm_count * 8, 256, 0, s>>>(*fp, o, rec, nrecords, rec_capacity, outbox, capacity, cursors, per_object, nobjects);
+  k_part_expand<<<sm_count * 8, 256, 0, s>>>(*fp, o, rec, nrecords, rec_capacity, masks, outbox, capacity, cursors, per_object, nobjects);
   return (int)cudaGetLastError();
 }

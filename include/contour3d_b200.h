@@ -106,6 +106,9 @@ typedef struct {
   uint32_t exchange_mode;        /* 0 one rank; 1 every rank draws its own cubes, whole images reduced through NCCL;
                                     2 screen-partitioned: cube lists, shading work and colours move through peer memory */
   uint64_t list_entries;         /* cubes this rank's raster walked (mode 2: from all ranks, for its screen tiles) */
+  float detail[16];              /* mode 2, ms: [0] barrier at the start, [1] halo pull, [2] staging + clear + sweeps, [3] cubes -> outboxes,
+                                    [4] barrier, [5] pull + merge of the lists, [6] raster + lines + select, [7] barrier, [8] pull of the
+                                    shading work, [9] shading, [10] barrier at the end */
 } c3d_timings_t;
 
 /* ---- life cycle ---- */
