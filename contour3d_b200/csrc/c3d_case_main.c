@@ -2,7 +2,11 @@
  * c3d_case_main.c -- a small MPI program around the PUBLIC API only
  * (contour3d_execute + SimpleDecomp getters): renders a "case file".
  *
- *   [MINIMPI_NP=<ranks>] c3d_case <case.bin> <out.ppm> [dim_y dim_z] [repeat] [warmup]
+ *   [MINIMPI_NP=<ranks>] c3d_case <case.bin> <out.ppm> [dim_y dim_z] [repeat] [warmup] [flags]
+ *
+ *   dim_y dim_z = 0 0 leaves the process grid to SimpleDecomp (MPI_Dims_create, sdecomp/main.c:133-139);
+ *   flags: 1 = construct the decomposition periodic in all directions, as the reference's demo does (src/main.c:119-125);
+ *          2 = hand the arrays over as X2 pencils (y split by the third, z by the second grid dimension, sdecomp/get.c:44-57)
  *
  * Because it touches nothing but include/contour3d.h it is built twice from
  * this one source: against libcontour3d_b200.so (-> contour3d_b200/c3d_case,
@@ -75,7 +79,7 @@ static double now(void) {
 
 int main(int argc, char **argv) {
   if (argc < 3) {
-    fprintf(stderr, "usage: %s case.bin out.ppm [dim_y dim_z] [repeat] [warmup]\n", argv[0]);
+    fprintf(stderr, "usage: %s case.bin out.ppm [dim_y dim_z] [repeat] [warmup] [flags]\n", argv[0]);
     return 2;
   }
   MPI_Init(NULL, NULL);
@@ -83,15 +87,18 @@ int main(int argc, char **argv) {
   MPI_Comm_size(MPI_COMM_WORLD, &nranks);
   MPI_Comm_rank(MPI_COMM_WORLD, &rank);
   size_t dims[3] = {0, 0, 0};
-  if (argc >= 5) {
+  if (argc >= 5 && (0 != atol(argv[3]) || 0 != atol(argv[4]))) {
     dims[0] = 1;
     dims[1] = (size_t)atol(argv[3]);
     dims[2] = (size_t)atol(argv[4]);
   }
   const int repeat = argc >= 6 ? atoi(argv[5]) : 1;
   const int warmup = argc >= 7 ? atoi(argv[6]) : 0;      /* untimed calls before the `repeat` timed ones */
+  const int flags = argc >= 8 ? atoi(argv[7]) : 0;
+  const bool periodic = 0 != (flags & 1);
+  const sdecomp_pencil_t pencil = 0 != (flags & 2) ? SDECOMP_X2PENCIL : SDECOMP_X1PENCIL;
   sdecomp_info_t *info = NULL;
-  if (0 != sdecomp.construct(MPI_COMM_WORLD, 3, dims, (bool[3]){false, false, false}, &info)) return 1;
+  if (0 != sdecomp.construct(MPI_COMM_WORLD, 3, dims, (bool[3]){periodic, periodic, periodic}, &info)) return 1;
   FILE *fp = fopen(argv[1], "rb");
   if (NULL == fp) { perror(argv[1]); return 1; }
   case_header_t h;
@@ -109,11 +116,11 @@ int main(int argc, char **argv) {
   if (h.ncontours != fread(cc, sizeof(*cc), h.ncontours, fp)) return 1;
   if (h.nlines != fread(cl, sizeof(*cl), h.nlines, fp)) return 1;
   const long fields_at = ftell(fp);
-  /* my X1 pencil */
+  /* my x pencil */
   size_t mysizes[3], offsets[3];
   for (sdecomp_dir_t d = 0; d < 3; d++) {
-    sdecomp.get_pencil_mysize(info, SDECOMP_X1PENCIL, d, h.n[d], mysizes + d);
-    sdecomp.get_pencil_offset(info, SDECOMP_X1PENCIL, d, h.n[d], offsets + d);
+    sdecomp.get_pencil_mysize(info, pencil, d, h.n[d], mysizes + d);
+    sdecomp.get_pencil_offset(info, pencil, d, h.n[d], offsets + d);
   }
   const size_t nlocal = mysizes[0] * mysizes[1] * mysizes[2];
   double **fields = malloc(h.nfields * sizeof(double *));
@@ -135,7 +142,7 @@ int main(int argc, char **argv) {
   fclose(fp);
   contour3d_contour_obj_t *cobjs = calloc(h.ncontours ? h.ncontours : 1, sizeof(*cobjs));
   for (uint64_t n = 0; n < h.ncontours; n++) {
-    cobjs[n].pencil = SDECOMP_X1PENCIL;
+    cobjs[n].pencil = pencil;
     for (int d = 0; d < 3; d++) { cobjs[n].glsizes[d] = h.n[d]; cobjs[n].grids[d] = grids[d]; }
     cobjs[n].converter = converter_of(h.pad[0]);
     cobjs[n].threshold = cc[n].threshold;

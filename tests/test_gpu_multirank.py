@@ -92,3 +92,47 @@ def test_dropin_program_two_ranks_matches_the_reference(tmp_path, kind, dims):
     want, got = api.read_ppm(want_ppm), api.read_ppm(got_ppm)
     assert (want != 0).any()
     assert np.array_equal(got, want), f"{int((got != want).any(axis=2).sum())} pixels differ from the reference image"
+
+
+@pytest.mark.parametrize("ranks,dims,flags", [
+    (2, (0, 0), 1),      # MPI_Dims_create -> {1, 2, 1}; periodic in all directions, as the reference's demo constructs it (src/main.c:119-125)
+    (4, (0, 0), 1),      # {1, 2, 2}
+    (8, (0, 0), 1),      # {1, 4, 2}
+    (8, (0, 0), 3),      # the same grid, arrays handed over as X2 pencils: y split by 2, z by 4 (sdecomp/get.c:44-57)
+    (4, (4, 1), 2),      # X2 pencils of a {1, 4, 1} grid: z slabs
+    (6, (3, 2), 0),
+])
+def test_dropin_against_the_genuine_simpledecomp(tmp_path, ranks, dims, flags):
+    """SURVEY 8(f) rank 1, as far as it goes without an MPI installation: the case-file program compiled against the
+    REFERENCE's headers and linked with the GENUINE SimpleDecomp sources (sdecomp.construct -> MPI_Dims_create,
+    MPI_Cart_create(reorder = 1), pencil getters through table_3d), contour3d_execute taken from this library.
+    Ranks are processes of the MPI stand-in, one per GPU (sharing GPUs when the box has fewer).  The PPM must equal,
+    byte for byte, what the same program linked against the unmodified reference writes on one CPU rank."""
+    import numpy as np
+
+    from contour3d_b200 import api, casefile, scenes
+    from oracle import reference
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "c3d_case_sd")
+    if _gpus() < 1:
+        pytest.skip("needs a GPU")
+    if not reference.available() or not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built")
+    n = 48
+    f = scenes.noise(n, seed=17 + ranks)
+    g = scenes.uniform_grids(n, n, n)
+    scene = scenes.scene(400, 225)
+    contours = [dict(field=0, threshold=float(np.float32(-0.1)), color=(250, 200, 60)), dict(field=0, threshold=float(np.float32(0.25)), color=(60, 200, 250))]
+    case = str(tmp_path / "case.bin")
+    casefile.write_case(case, scene, g, [f], contours, scenes.box_lines(nitems=24, width=3.0))
+    want_ppm, got_ppm = str(tmp_path / "ref.ppm"), str(tmp_path / "ours.ppm")
+    reference.run_case(case, want_ppm, ranks=1)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT", "MASTER_ADDR")}
+    env["MINIMPI_NP"] = str(ranks)
+    env.setdefault("CONTOUR3D_PEER_TIMEOUT", "120")
+    proc = subprocess.run([exe, case, got_ppm, str(dims[0]), str(dims[1]), "2", "0", str(flags)], env=env, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-1000:] + proc.stderr[-2000:]
+    assert '"status": 0' in proc.stdout
+    want, got = api.read_ppm(want_ppm), api.read_ppm(got_ppm)
+    assert (want != 0).any()
+    assert np.array_equal(got, want), f"{int((got != want).any(axis=2).sum())} pixels differ from the reference image"

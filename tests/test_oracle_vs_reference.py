@@ -86,3 +86,27 @@ def test_coordinate_converters_oracle_matches_reference(tmp_path, kind):
     rgb, _, _ = oracle.frame(scene, ocs, ols, nthreads=3)
     assert (want != 0).any()
     assert np.array_equal(rgb[::-1], want)
+
+
+@pytest.mark.parametrize("ranks,dims,flags", [(4, (0, 0), 1), (8, (0, 0), 3), (4, (4, 1), 2)])
+def test_reference_with_default_grids_periodic_and_x2_pencils(tmp_path, ranks, dims, flags):
+    """what tests/test_gpu_multirank.py::test_dropin_against_the_genuine_simpledecomp compares with: the unmodified reference
+    itself gives the one-rank image on SimpleDecomp's default process grids, periodic constructs and X2 pencils"""
+    import subprocess
+
+    from contour3d_b200 import api, casefile, scenes
+
+    n = 24
+    f = scenes.noise(n, seed=3)
+    g = scenes.uniform_grids(n, n, n)
+    scene = scenes.scene(160, 90)
+    contours = [dict(field=0, threshold=float(np.float32(0.05)), color=(250, 200, 60))]
+    case = str(tmp_path / "case.bin")
+    casefile.write_case(case, scene, g, [f], contours, scenes.box_lines(nitems=8, width=2.0))
+    one, many = str(tmp_path / "one.ppm"), str(tmp_path / "many.ppm")
+    reference.run_case(case, one, ranks=1)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT", "MASTER_ADDR")}
+    env["MINIMPI_NP"] = str(ranks)
+    proc = subprocess.run([reference.REF_DRIVER, case, many, str(dims[0]), str(dims[1]), "1", "0", str(flags)], env=env, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert np.array_equal(api.read_ppm(one), api.read_ppm(many))
