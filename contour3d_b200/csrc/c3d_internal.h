@@ -105,6 +105,7 @@ struct __align__(16) Pixel { unsigned long long depth, key; };
 
 #define C3D_MAX_OBJECTS 16
 #define C3D_DEPTH_BUCKETS 2048        /* view-depth slabs of the front-to-back ordering (multiple of 1024) */
+#define C3D_PART_BUCKETS 1024         /* the same in screen-partitioned frames, where every rank keeps one set per destination rank */
 #define C3D_HIZ_TILE 8                /* pixels per side of a coarse z-buffer tile */
 #define C3D_RASTER_PARTS 64u          /* the raster's list is cut at multiples of 1/64 of its length */
 #define C3D_SWEEP_MAX_THR 4        /* iso-values of one array classified by a single sweep launch */

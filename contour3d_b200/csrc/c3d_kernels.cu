@@ -308,10 +308,11 @@ extern "C" int c3d_k_sweep(const FieldView *f, const SweepRange *r, unsigned int
 /* pixel box imin | imax << 16 | jmin << 32 | jmax << 48 that certainly holds every pixel centre a triangle can cover
    (triangle_hidden), or C3D_NO_BOX when the pre-test did not get that far */
 #define C3D_NO_BOX 0xffffffffffffffffull
+#define C3D_QUEUE 64              /* triangles a warp can hold back until 32 of them are ready for the exact path */
 
 template <bool MAPPED, bool PEER>
 __device__ __forceinline__ void raster_triangle(const FrameParams &p, const FieldView *staged, const unsigned long long entry, const unsigned int s,
-                                                const unsigned long long box, Pixel *__restrict__ canvas) {
+                                                const unsigned long long box, const double *qval, Pixel *__restrict__ canvas) {
   const unsigned int obj = C3D_ENTRY_OBJ(entry), code = C3D_ENTRY_CODE(entry);
   const FieldView &f = entry_view<PEER>(p, staged, entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
@@ -327,15 +328,10 @@ __device__ __forceinline__ void raster_triangle(const FrameParams &p, const Fiel
       t.q[m] = V3{v.x, v.y, v.z};
     }
   } else {
-    /* all loads of the three vertices first: six corner values, six coordinates */
-    const long long base = k * f.sz + j * f.sy + i;
+    /* the six corner values came with the triangle (read once per cube, k_raster); the six coordinates are loaded together */
     double val[6];
 #pragma unroll
-    for (int m = 0; m < 3; m++) {
-      const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
-      val[2 * m] = ld_value(f, base + ((tail & 1u) + ((tail & 2u) ? f.sy : 0ll) + ((tail & 4u) ? f.sz : 0ll)));
-      val[2 * m + 1] = ld_value(f, base + ((head & 1u) + ((head & 2u) ? f.sy : 0ll) + ((head & 4u) ? f.sz : 0ll)));
-    }
+    for (int v = 0; v < 6; v++) val[v] = qval[v * C3D_QUEUE];
     const double gx0 = __ldg(f.g[0] + i), gx1 = __ldg(f.g[0] + i + 1), gy0 = __ldg(f.g[1] + j), gy1 = __ldg(f.g[1] + j + 1);
     const double gz0 = __ldg(f.g[2] + k), gz1 = __ldg(f.g[2] + k + 1);
 #pragma unroll
@@ -549,14 +545,13 @@ __device__ __forceinline__ bool cube_hidden(const FrameParams &p, const FieldVie
  */
 template <bool MAPPED, bool PEER>
 __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const FieldView *staged, const unsigned long long entry, const unsigned int s,
-                                                const Pixel *__restrict__ canvas, unsigned long long &box) {
+                                                const double *corner, const Pixel *__restrict__ canvas, unsigned long long &box) {
   box = C3D_NO_BOX;
   const CullCam &q = p.cull;
   const unsigned int code = C3D_ENTRY_CODE(entry);
   const FieldView &f = entry_view<PEER>(p, staged, entry);
   const long long i = C3D_ENTRY_I(entry), j = C3D_ENTRY_J(entry), k = C3D_ENTRY_K(entry);
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
-  const long long base = k * f.sz + j * f.sy + i;
   const float thr = (float)f.thr;
   /* the cube's six grid coordinates once, not per vertex (identity converter) */
   float gx0 = 0.f, gx1 = 0.f, gy0 = 0.f, gy1 = 0.f, gz0 = 0.f, gz1 = 0.f;
@@ -569,20 +564,12 @@ __device__ __forceinline__ bool triangle_hidden(const FrameParams &p, const Fiel
   /* fp32 with explicit fused multiply-adds (the translation unit is compiled with -fmad=false for the exact fp64 path;
      here fewer roundings only help) and ONE reciprocal per vertex: rcp is within 1 ulp and the product adds half an ulp,
      so the factor is off by < 2e-7 on top of the bound below -- covered by the extra 3e-7 in ferr */
-  /* the six corner values of the three vertices are requested before any is used: the loop below stays rolled (code size),
-     but meets the memory latency once, not three times -- in a partitioned frame these may be peer reads over NVLink */
-  float tv[3], hv[3];
-#pragma unroll
-  for (int m = 0; m < 3; m++) {
-    const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
-    tv[m] = (float)ld_value(f, base + ((tail & 1u) + ((tail & 2u) ? f.sy : 0ll) + ((tail & 4u) ? f.sz : 0ll)));
-    hv[m] = (float)ld_value(f, base + ((head & 1u) + ((head & 2u) ? f.sy : 0ll) + ((head & 4u) ? f.sz : 0ll)));
-  }
+  /* the cube's eight corner values sit in shared memory (corner[n * 32]: read from the array once per cube by k_raster) */
 #pragma unroll 1
   for (int m = 0; m < 3; m++) {
     const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
-    const float v0 = 0 == m ? tv[0] : (1 == m ? tv[1] : tv[2]);
-    const float v1 = 0 == m ? hv[0] : (1 == m ? hv[1] : hv[2]);
+    const float v0 = (float)corner[tail * 32u];
+    const float v1 = (float)corner[head * 32u];
     const float dv = v1 - v0;
     const float inv = __frcp_rn(dv);
     const float ferr = 2.00002e-7f * (fabsf(thr) + fabsf(v0) + fabsf(v1)) * fabsf(inv) + 3.e-7f;
@@ -643,9 +630,14 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
                                                      const HiZ hiz, const unsigned int part_begin, const unsigned int part_end) {
   __shared__ unsigned long long s_entry[4][32];
   __shared__ unsigned int s_first[4][32];
-  __shared__ unsigned long long s_queue[4][64];       /* triangles that passed the pre-test, waiting for a full warp */
-  __shared__ unsigned long long s_qbox[4][64];        /* ... and the pixel boxes the pre-test left them */
-  __shared__ unsigned char s_qsrc[4][PEER ? 64 : 1];  /* ... and the rank their cube indices refer to */
+  __shared__ unsigned long long s_queue[4][C3D_QUEUE];       /* triangles that passed the pre-test, waiting for a full warp */
+  __shared__ unsigned long long s_qbox[4][C3D_QUEUE];        /* ... and the pixel boxes the pre-test left them */
+  __shared__ unsigned char s_qsrc[4][PEER ? C3D_QUEUE : 1];  /* ... and the rank their cube indices refer to */
+  /* The corner values of a surviving cube are read from the array ONCE (8 loads in flight per lane, one exposure to the
+     memory latency -- in a partitioned frame most are peer reads over NVLink) and kept here for the cube's 1..12 triangles;
+     a queued triangle takes the values of its three cut edges along (tail and head of each). */
+  __shared__ double s_corner[4][8][32];
+  __shared__ double s_qval[4][6][C3D_QUEUE];
   /* the views of a partitioned frame live in device memory (ranks x objects of them); the few in use are staged here, so that
      the per-cube tests read them like the single-rank kernel reads its constant bank */
   constexpr unsigned int STAGED = PEER ? 32u : 1u;
@@ -693,6 +685,13 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
       const unsigned int slot = __popc(alive & ((1u << lane) - 1u));
       s_entry[wid][slot] = entry;
       s_first[wid][slot] = excl;
+      const FieldView &f = entry_view<PEER>(p, staged, entry);
+      const long long at = C3D_ENTRY_K(entry) * f.sz + C3D_ENTRY_J(entry) * f.sy + C3D_ENTRY_I(entry);
+      double c[8];
+#pragma unroll
+      for (int nn = 0; nn < 8; nn++) c[nn] = ld_value(f, at + (nn & 1) + ((nn >> 1) & 1) * f.sy + (nn >> 2) * f.sz);
+#pragma unroll
+      for (int nn = 0; nn < 8; nn++) s_corner[wid][nn][slot] = c[nn];
     }
     __syncwarp();
     for (unsigned int t0 = 0; t0 < total; t0 += 32u) {
@@ -709,7 +708,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
         const unsigned int s = t0 + lane - s_first[wid][src];
         mine = C3D_TRI_PACK(e, s);
         mysrc = C3D_ENTRY_SRC(e);
-        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden<MAPPED, PEER>(p, staged, e, s, canvas, mybox));
+        keep = !(p.cull.enabled && !C3D_ENTRY_IRREGULAR(e) && triangle_hidden<MAPPED, PEER>(p, staged, e, s, &s_corner[wid][0][src], canvas, mybox));
       }
       const unsigned int kept = __ballot_sync(C3D_FULL_MASK, keep);
       hidden_tris += __popc(__ballot_sync(C3D_FULL_MASK, t0 + lane < total)) - __popc(kept);
@@ -718,6 +717,12 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
         s_queue[wid][at] = mine;
         s_qbox[wid][at] = mybox;
         if (PEER) s_qsrc[wid][at] = (unsigned char)mysrc;
+        const unsigned int pairs = __ldg(p.tab.pairs + C3D_ENTRY_CODE(mine) * C3D_MAX_TRIS + C3D_TRI_INDEX(mine));
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          s_qval[wid][2 * m][at] = s_corner[wid][(pairs >> (6 * m)) & 7u][src];
+          s_qval[wid][2 * m + 1][at] = s_corner[wid][(pairs >> (6 * m + 3)) & 7u][src];
+        }
       }
       queued += __popc(kept);
       __syncwarp();
@@ -725,14 +730,29 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
         /* a full warp of triangles that need the exact treatment */
         const unsigned long long q = s_queue[wid][lane], qb = s_qbox[wid][lane];
         const unsigned long long qs = PEER ? (unsigned long long)s_qsrc[wid][lane] << C3D_ENTRY_SRC_SHIFT : 0ull;
+        /* the exact path reads its values from the first 32 queue slots while the rest moves down: keep them in registers */
+        double qv[6];
+#pragma unroll
+        for (int v = 0; v < 6; v++) qv[v] = s_qval[wid][v][lane];
         const unsigned long long rest = (lane + 32u < queued) ? s_queue[wid][lane + 32u] : 0ull;
         const unsigned long long restb = (lane + 32u < queued) ? s_qbox[wid][lane + 32u] : 0ull;
         const unsigned char rests = (PEER && lane + 32u < queued) ? s_qsrc[wid][lane + 32u] : (unsigned char)0;
+        double restv[6];
+#pragma unroll
+        for (int v = 0; v < 6; v++) restv[v] = (lane + 32u < queued) ? s_qval[wid][v][lane + 32u] : 0.;
         __syncwarp();
-        if (lane + 32u < queued) { s_queue[wid][lane] = rest; s_qbox[wid][lane] = restb; if (PEER) s_qsrc[wid][lane] = rests; }
+        /* slots 32..63 take the drawn triangles' values (read back below through the same pointer arithmetic as the final flush) */
+#pragma unroll
+        for (int v = 0; v < 6; v++) s_qval[wid][v][lane + 32u] = qv[v];
+        if (lane + 32u < queued) {
+          s_queue[wid][lane] = rest; s_qbox[wid][lane] = restb; if (PEER) s_qsrc[wid][lane] = rests;
+#pragma unroll
+          for (int v = 0; v < 6; v++) s_qval[wid][v][lane] = restv[v];
+        }
         queued -= 32u;
         __syncwarp();
-        raster_triangle<MAPPED, PEER>(p, staged, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), qb, canvas);
+        raster_triangle<MAPPED, PEER>(p, staged, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), qb, &s_qval[wid][0][lane + 32u], canvas);
+        __syncwarp();
       }
     }
   }
@@ -740,7 +760,7 @@ __global__ void __launch_bounds__(128, MINB) k_raster(const __grid_constant__ Fr
   if (lane < queued) {
     const unsigned long long q = s_queue[wid][lane];
     const unsigned long long qs = PEER ? (unsigned long long)s_qsrc[wid][lane] << C3D_ENTRY_SRC_SHIFT : 0ull;
-    raster_triangle<MAPPED, PEER>(p, staged, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), s_qbox[wid][lane], canvas);
+    raster_triangle<MAPPED, PEER>(p, staged, C3D_TRI_ENTRY(q) | qs, C3D_TRI_INDEX(q), s_qbox[wid][lane], &s_qval[wid][0][lane], canvas);
   }
   if (0u == lane && nullptr != culled) {
     if (hidden_total > 0u) atomicAdd(culled, (unsigned long long)hidden_total);

@@ -339,19 +339,19 @@ int c3d_k_halo_pull_z(void *mine, const void *theirs, int elem_bytes, size_t cou
 /* -------------------------------------------------------------- list merge */
 
 /*
- * Every source rank s has sorted the cubes it addresses to me by view depth (counting sort, C3D_DEPTH_BUCKETS slabs
+ * Every source rank s has sorted the cubes it addresses to me by view depth (counting sort, C3D_PART_BUCKETS slabs
  * of the SAME global depth range on all ranks).  The merged list is bucket-major, source-minor: still nearest first,
  * which is all the raster's occlusion test wants.  merge_base[b * n + s] = first merged index of (bucket b, source s).
  */
 __global__ void __launch_bounds__(1024) k_merge_scan(const MergeSources src, const int n, const int me, unsigned long long *__restrict__ merge_base,
                                                      unsigned long long *__restrict__ count) {
   __shared__ unsigned long long part[1024];
-  const unsigned int per = (unsigned int)(C3D_DEPTH_BUCKETS / 1024) * (unsigned int)n;     /* consecutive bins of a thread */
+  const unsigned int per = (unsigned int)(C3D_PART_BUCKETS / 1024) * (unsigned int)n;     /* consecutive bins of a thread */
   const unsigned int first = threadIdx.x * per;
   unsigned long long mine = 0ull;
   for (unsigned int q = 0; q < per; q++) {
     const unsigned int bin = first + q, b = bin / (unsigned int)n, s = bin % (unsigned int)n;
-    mine += src.hist[s][(unsigned int)me * C3D_DEPTH_BUCKETS + b];
+    mine += src.hist[s][(unsigned int)me * C3D_PART_BUCKETS + b];
   }
   part[threadIdx.x] = mine;
   __syncthreads();
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(1024) k_merge_scan(const MergeSources src, con
   for (unsigned int q = 0; q < per; q++) {
     const unsigned int bin = first + q, b = bin / (unsigned int)n, s = bin % (unsigned int)n;
     merge_base[bin] = at;
-    at += src.hist[s][(unsigned int)me * C3D_DEPTH_BUCKETS + b];
+    at += src.hist[s][(unsigned int)me * C3D_PART_BUCKETS + b];
   }
   if (1023u == threadIdx.x) *count = part[1023];
 }
@@ -375,11 +375,11 @@ __global__ void __launch_bounds__(1024) k_merge_scan(const MergeSources src, con
 __global__ void __launch_bounds__(MERGE_THREADS) k_merge_copy(const MergeSources src, const int n, const int me,
                                                               const unsigned long long *__restrict__ merge_base,
                                                               unsigned long long *__restrict__ list, const unsigned long long capacity) {
-  __shared__ unsigned int prefix[C3D_DEPTH_BUCKETS + 1];       /* of source s: entries for me before bucket b */
+  __shared__ unsigned int prefix[C3D_PART_BUCKETS + 1];       /* of source s: entries for me before bucket b */
   __shared__ unsigned int warp_sum[MERGE_THREADS / 32];
   const int s = (int)blockIdx.y;
-  const unsigned int *hist = src.hist[s] + (unsigned int)me * C3D_DEPTH_BUCKETS;
-  constexpr unsigned int PER = C3D_DEPTH_BUCKETS / MERGE_THREADS;
+  const unsigned int *hist = src.hist[s] + (unsigned int)me * C3D_PART_BUCKETS;
+  constexpr unsigned int PER = C3D_PART_BUCKETS / MERGE_THREADS;
   unsigned int v[PER], sum = 0u;
 #pragma unroll
   for (unsigned int q = 0; q < PER; q++) { v[q] = hist[threadIdx.x * PER + q]; sum += v[q]; }
@@ -397,9 +397,9 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_copy(const MergeSources
   unsigned int at = before + incl - sum;
 #pragma unroll
   for (unsigned int q = 0; q < PER; q++) { prefix[threadIdx.x * PER + q] = at; at += v[q]; }
-  if (MERGE_THREADS - 1 == threadIdx.x) prefix[C3D_DEPTH_BUCKETS] = at;
+  if (MERGE_THREADS - 1 == threadIdx.x) prefix[C3D_PART_BUCKETS] = at;
   __syncthreads();
-  const unsigned int total = prefix[C3D_DEPTH_BUCKETS];
+  const unsigned int total = prefix[C3D_PART_BUCKETS];
   const unsigned long long start = src.seg_start[s][me];
   const unsigned long long *outbox = src.outbox[s] + start;
   /* entries travel in aligned pairs (16 bytes); the segment may start on an odd entry */
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_copy(const MergeSources
   const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(outbox - odd);
   auto place = [&](const unsigned int e, const unsigned long long entry) {
     /* largest b with prefix[b] <= e */
-    unsigned int lo = 0u, hi = C3D_DEPTH_BUCKETS;
+    unsigned int lo = 0u, hi = C3D_PART_BUCKETS;
     while (hi - lo > 1u) {
       const unsigned int mid = (lo + hi) >> 1;
       if (prefix[mid] <= e) lo = mid; else hi = mid;
@@ -444,27 +444,90 @@ int c3d_k_merge_lists(const MergeSources *src, int nranks, int me, unsigned long
 
 /* --------------------------------------------------------------- work pull */
 
-__global__ void __launch_bounds__(256) k_work_pull(const WorkSources src, const int n, WorkItem *__restrict__ work, unsigned int *__restrict__ nwork,
-                                                   const unsigned int capacity, unsigned long long *__restrict__ overflowed) {
-  unsigned int first = 0u;
+/*
+ * Who shades what.  Rank d has queued, per owner o, the pixels of its tiles won by cubes of o's array: count C[d][o], items
+ * in seg[d][o].  Owner o's pixels in the order d = 0, 1, .. form its list of T[o] = sum_d C[d][o] items.  An owner with
+ * more than the mean keeps the first `keep` items and hands the rest to the ranks below the mean (they read the owner's array
+ * through peer memory): the front slab of a z-decomposed volume otherwise shades a third of the image on its own.
+ * Every rank runs this same integer plan on the same counts, and writes down only what IT has to pull.
+ */
+__global__ void k_work_plan(const WorkExchange ex, const int n, const int me, const float share, PullPlan *__restrict__ plan,
+                            unsigned int *__restrict__ nwork, const unsigned int capacity, unsigned long long *__restrict__ overflowed) {
+  if (0 != threadIdx.x || 0 != blockIdx.x) return;
+  unsigned int C[C3D_MAX_RANKS][C3D_MAX_RANKS], T[C3D_MAX_RANKS], keep[C3D_MAX_RANKS], room[C3D_MAX_RANKS];
+  unsigned long long total = 0ull;
+  for (int o = 0; o < n; o++) T[o] = 0u;
   for (int d = 0; d < n; d++) {
-    const unsigned int cnt = *src.count[d];
-    const uint4 *from = reinterpret_cast<const uint4 *>(src.seg[d]);
-    uint4 *to = reinterpret_cast<uint4 *>(work);
-    for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
-      if (first + q < capacity) to[first + q] = from[q];
-    }
-    first += cnt;
+    for (int o = 0; o < n; o++) { C[d][o] = ex.nseg[d][o]; T[o] += C[d][o]; }
   }
-  if (0u == blockIdx.x && 0u == threadIdx.x) {
-    *nwork = first < capacity ? first : capacity;
-    if (first > capacity) atomicAdd(overflowed, 1ull);
+  for (int o = 0; o < n; o++) total += T[o];
+  const unsigned int mean = (unsigned int)((total + (unsigned long long)n - 1ull) / (unsigned long long)n);
+  for (int o = 0; o < n; o++) {
+    const unsigned int excess = T[o] > mean ? (unsigned int)((float)(T[o] - mean) * share) : 0u;
+    keep[o] = T[o] - excess;
+    room[o] = T[o] < mean ? mean - T[o] : 0u;
+  }
+  unsigned int nchunks = 0u, dest = 0u;
+  /* a range [a, a + cnt) of owner o's list, as pieces of the ranks' segments */
+  auto take = [&](const int o, unsigned int a, unsigned int cnt) {
+    unsigned int before = 0u;
+    for (int d = 0; d < n && cnt > 0u; d++) {
+      const unsigned int end = before + C[d][o];
+      if (a < end) {
+        const unsigned int piece = (end - a) < cnt ? (end - a) : cnt;
+        PullChunk c;
+        c.owner = (unsigned int)o; c.d = (unsigned int)d; c.first = a - before; c.count = piece; c.dest = dest;
+        if (nchunks < C3D_PULL_CHUNKS) plan->chunk[nchunks++] = c;
+        dest += piece; a += piece; cnt -= piece;
+      }
+      before = end;
+    }
+  };
+  take(me, 0u, keep[me]);
+  int r = 0;
+  for (int o = 0; o < n; o++) {
+    unsigned int a = keep[o], left = T[o] - keep[o];
+    while (left > 0u) {
+      while (r < n && 0u == room[r]) r++;
+      if (r >= n) {                           /* rounding left a few: the owner keeps them after all */
+        if (o == me) take(o, a, left);
+        break;
+      }
+      const unsigned int give = left < room[r] ? left : room[r];
+      if (r == me) take(o, a, give);
+      room[r] -= give; a += give; left -= give;
+    }
+  }
+  plan->nchunks = nchunks;
+  plan->nwork = dest < capacity ? dest : capacity;
+  *nwork = plan->nwork;
+  if (dest > capacity) atomicAdd(overflowed, 1ull);
+}
+
+__global__ void __launch_bounds__(256) k_work_copy(const WorkExchange ex, const PullPlan *__restrict__ plan, WorkItem *__restrict__ work,
+                                                   const unsigned int capacity) {
+  const unsigned int nchunks = plan->nchunks;
+  uint4 *to = reinterpret_cast<uint4 *>(work);
+  const unsigned int stride = gridDim.x * blockDim.x;
+  for (unsigned int c = 0; c < nchunks; c++) {
+    const PullChunk ch = plan->chunk[c];
+    const uint4 *from = reinterpret_cast<const uint4 *>(ex.seg[ch.d] + (size_t)ch.owner * ex.seg_cap + ch.first);
+    unsigned int q = blockIdx.x * blockDim.x + threadIdx.x;
+    /* four independent 16-byte requests per thread in flight (peer reads) */
+    for (; q + 3u * stride < ch.count; q += 4u * stride) {
+      const uint4 a = from[q], b = from[q + stride], cc = from[q + 2u * stride], d = from[q + 3u * stride];
+      if (ch.dest + q + 3u * stride < capacity) { to[ch.dest + q] = a; to[ch.dest + q + stride] = b; to[ch.dest + q + 2u * stride] = cc; to[ch.dest + q + 3u * stride] = d; }
+    }
+    for (; q < ch.count; q += stride) {
+      if (ch.dest + q < capacity) to[ch.dest + q] = from[q];
+    }
   }
 }
 
-int c3d_k_work_pull(const WorkSources *src, int nranks, WorkItem *work, unsigned int *nwork, unsigned int capacity,
-                    unsigned long long *overflowed, cudaStream_t s) {
-  k_work_pull<<<148 * 4, 256, 0, s>>>(*src, nranks, work, nwork, capacity, overflowed);
+int c3d_k_work_exchange(const WorkExchange *ex, int nranks, int me, float share, PullPlan *plan, WorkItem *work, unsigned int *nwork,
+                        unsigned int capacity, unsigned long long *overflowed, cudaStream_t s) {
+  k_work_plan<<<1, 32, 0, s>>>(*ex, nranks, me, share, plan, nwork, capacity, overflowed);
+  k_work_copy<<<148 * 2, 256, 0, s>>>(*ex, plan, work, capacity);
   return (int)cudaGetLastError();
 }
 

@@ -66,12 +66,18 @@ struct MergeSources {
 int c3d_k_merge_lists(const MergeSources *src, int nranks, int me, unsigned long long *merge_base, unsigned long long *list,
                       unsigned long long *count, unsigned long long capacity, cudaStream_t s);
 
-struct WorkSources {
-  const WorkItem *seg[C3D_MAX_RANKS];                  /* rank d: the pixels it has resolved to cubes of this rank */
-  const unsigned int *count[C3D_MAX_RANKS];
+struct WorkExchange {
+  const unsigned int *nseg[C3D_MAX_RANKS];             /* rank d: pixels it has resolved, per owner rank */
+  const WorkItem *seg[C3D_MAX_RANKS];                  /* rank d: the items, owner o's at + o * seg_cap */
+  unsigned int seg_cap;
 };
-int c3d_k_work_pull(const WorkSources *src, int nranks, WorkItem *work, unsigned int *nwork, unsigned int capacity,
-                    unsigned long long *overflowed, cudaStream_t s);
+#define C3D_PULL_CHUNKS (C3D_MAX_RANKS * (C3D_MAX_RANKS + 2))
+struct PullChunk { unsigned int owner, d, first, count, dest; };
+struct PullPlan { unsigned int nchunks, nwork; PullChunk chunk[C3D_PULL_CHUNKS]; };
+/* decides which pixels this rank shades (its own cubes' up to the mean load, plus its share of what the busiest ranks hand
+   over: share = fraction of their excess, 0 = everybody shades exactly the pixels its own cubes won) and pulls them */
+int c3d_k_work_exchange(const WorkExchange *ex, int nranks, int me, float share, PullPlan *plan, WorkItem *work, unsigned int *nwork,
+                        unsigned int capacity, unsigned long long *overflowed, cudaStream_t s);
 
 /* flag[0] of every rank -> max into mine */
 struct FlagSources { const unsigned long long *flag[C3D_MAX_RANKS]; };

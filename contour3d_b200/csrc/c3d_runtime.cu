@@ -143,10 +143,12 @@ struct c3d_context {
   bool has_comm;
   c3d_peer peer;                                   /* device-to-device exchange between the ranks of this node */
   Exchange xa;
-  unsigned long long *merge_base, *part_cursors;   /* C3D_DEPTH_BUCKETS x ranks each: merged-list offsets / outbox cursors */
+  unsigned long long *merge_base, *part_cursors;   /* C3D_PART_BUCKETS x ranks each: merged-list offsets / outbox cursors */
   unsigned char *part_masks;                       /* 32 bytes per sweep record: which ranks draw each of its cubes */
   size_t part_masks_cap;                           /* in records */
   int tile_shift;                                  /* log2 of the screen-tile edge of partitioned frames */
+  PullPlan *pull_plan;                             /* device: which shading work this rank pulls (k_work_plan) */
+  float shade_share;                               /* fraction of the busiest ranks' excess shading that the others take over */
   void *table_mem;
   DevTables tab;
   /* canvases */
@@ -266,8 +268,12 @@ static int context_init(c3d_context *ctx, const int comm_rank, const int comm_si
     /* 1. device-to-device exchange between the ranks of this node (CUDA IPC): the data path of multi-rank frames */
     if (0 != c3d_peer_init(&ctx->peer, comm_rank, comm_size, nccl_id128, ctx->device)) return 1;
     if (ctx->peer.active) {
-      CUDA_OK(cudaMalloc(&ctx->merge_base, (size_t)C3D_DEPTH_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
-      CUDA_OK(cudaMalloc(&ctx->part_cursors, (size_t)C3D_DEPTH_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
+      CUDA_OK(cudaMalloc(&ctx->merge_base, (size_t)C3D_PART_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
+      CUDA_OK(cudaMalloc(&ctx->part_cursors, (size_t)C3D_PART_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
+      CUDA_OK(cudaMalloc(&ctx->pull_plan, sizeof(PullPlan)));
+      const char *env = getenv("CONTOUR3D_SHADE_SHARE");
+      ctx->shade_share = (NULL != env && '\0' != *env) ? (float)atof(env) : 1.f;
+      if (!(ctx->shade_share >= 0.f && ctx->shade_share <= 1.f)) ctx->shade_share = 1.f;
     }
     /* 2. NCCL communicator: frames with coordinate converters and nodes without peer access reduce whole images through it.
           Ranks that share a GPU (test boxes) cannot form one: they have the peer path only. */
@@ -323,7 +329,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
   release_exchange(ctx);
-  cudaFree(ctx->merge_base); cudaFree(ctx->part_cursors); cudaFree(ctx->part_masks);
+  cudaFree(ctx->merge_base); cudaFree(ctx->part_cursors); cudaFree(ctx->part_masks); cudaFree(ctx->pull_plan);
   c3d_peer_destroy(&ctx->peer);
   cudaFree(ctx->table_mem);
   cudaFree(ctx->shade.work); cudaFree(ctx->shade.counters); cudaFree(ctx->shade.pix); cudaFree(ctx->shade.table); cudaFree(ctx->shade.vlist); cudaFree(ctx->shade.vn);
@@ -1048,7 +1054,7 @@ static int ensure_exchange(c3d_context *ctx, const size_t w, const size_t h, con
   x.off_flags = at; at += 256;
   x.off_seg_start = at; at += 256;
   x.off_nseg = at; at += 256;
-  x.off_hist = at; at += round_up((size_t)n * C3D_DEPTH_BUCKETS * sizeof(unsigned int), 256);
+  x.off_hist = at; at += round_up((size_t)n * C3D_PART_BUCKETS * sizeof(unsigned int), 256);
   x.off_rgba = at; at += round_up(x.npix * 4, 256);
   x.off_seg = at; at += round_up((size_t)n * x.seg_cap * sizeof(WorkItem), 256);
   x.off_out = at; at += x.out_cap * 8 + 256;     /* readers fetch aligned pairs: room for one entry beyond the last */
@@ -1364,15 +1370,16 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     mark();                                                             /* detail[6]: raster, lines, select */
     LAUNCH_OK(c3d_peer_barrier(peer, s));
     mark();                                                             /* detail[7]: barrier (all work segments complete) */
-    WorkSources ws;
+    WorkExchange ws;
     memset(&ws, 0, sizeof(ws));
     for (int r = 0; r < ctx->size; r++) {
       const char *pb = (const char *)xa.peer[r];
-      ws.seg[r] = (const WorkItem *)(pb + xa.off_seg) + (size_t)ctx->rank * xa.seg_cap;
-      ws.count[r] = (const unsigned int *)(pb + xa.off_nseg) + ctx->rank;
+      ws.seg[r] = (const WorkItem *)(pb + xa.off_seg);
+      ws.nseg[r] = (const unsigned int *)(pb + xa.off_nseg);
     }
-    LAUNCH_OK(c3d_k_work_pull(&ws, ctx->size, ctx->shade.work, ctx->shade.counters, (unsigned int)std::min<size_t>(npix, 0xffffffffu),
-                              ctx->counts_dev + CNT_SEG_OVER, s));
+    ws.seg_cap = (unsigned int)xa.seg_cap;
+    LAUNCH_OK(c3d_k_work_exchange(&ws, ctx->size, ctx->rank, ctx->shade_share, ctx->pull_plan, ctx->shade.work, ctx->shade.counters,
+                                  (unsigned int)std::min<size_t>(npix, 0xffffffffu), ctx->counts_dev + CNT_SEG_OVER, s));
     launches += 2;
     CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
     mark();                                                             /* detail[8]: pull of the shading work */

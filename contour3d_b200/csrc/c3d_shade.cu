@@ -80,58 +80,67 @@ __global__ void __launch_bounds__(256) k_shade_select(const __grid_constant__ Fr
  * the rank that holds the winning cube's array -- it alone can form the vertex normals (normal.c:78-158 needs the
  * neighbouring cubes) -- in the segment that rank will pull: seg[r * seg_cap ...], nseg[r].
  */
+#define SEL_UNIT 4096u          /* pixels a block resolves at a time: a whole tile of 64 x 64, or a band of a larger one */
 __global__ void __launch_bounds__(256) k_shade_select_part(const __grid_constant__ FrameParams p, const LineDev *__restrict__ lines,
                                                            const Pixel *__restrict__ canvas, unsigned int *__restrict__ rgba_out,
                                                            WorkItem *__restrict__ seg, const unsigned int seg_cap, unsigned int *__restrict__ nseg,
                                                            unsigned long long *__restrict__ overflowed) {
+  /* One block per unit; the pixels are counted per destination rank in shared memory first, so that this rank's eight
+     segment counters see one atomic per (unit, rank) instead of one per warp. */
+  __shared__ unsigned char s_home[SEL_UNIT];
+  __shared__ unsigned int s_count[C3D_MAX_RANKS], s_base[C3D_MAX_RANKS];
   const Partition &part = p.part;
-  const unsigned int lane = threadIdx.x & 31u;
   const unsigned int w = (unsigned int)p.cam.w, h = (unsigned int)p.cam.h;
   const unsigned int tile = 1u << part.tile_shift;
-  const unsigned int sub_x = tile >> 3, sub_y = tile >> 2, per_tile = sub_x * sub_y;       /* 8 x 4 pixel warps per tile */
+  const unsigned int unit_px = tile * tile < SEL_UNIT ? tile * tile : SEL_UNIT;
+  const unsigned int rows = unit_px >> part.tile_shift;                 /* rows of the tile per unit */
+  const unsigned int per_tile = (tile * tile) / unit_px;
   const unsigned int ntiles = (unsigned int)(part.tiles_x * part.tiles_y);
-  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  /* own tiles are every nranks-th of a row, shifted from row to row: walk all (tile, sub-tile) pairs and skip foreign tiles */
-  for (unsigned long long unit = warp; unit < (unsigned long long)ntiles * per_tile; unit += nwarps) {
+  for (unsigned long long unit = blockIdx.x; unit < (unsigned long long)ntiles * per_tile; unit += gridDim.x) {
     const unsigned int t = (unsigned int)(unit / per_tile), sub = (unsigned int)(unit % per_tile);
     const unsigned int tx = t % (unsigned int)part.tiles_x, ty = t / (unsigned int)part.tiles_x;
-    if (tile_owner(part, tx, ty) != (unsigned int)part.me) continue;
-    const unsigned int pi = tx * tile + (sub % sub_x) * 8u + (lane & 7u), pj = ty * tile + (sub / sub_x) * 4u + (lane >> 3);
-    const size_t pix = (size_t)pj * w + pi;
-    unsigned int home = 0xffffffffu;
-    unsigned long long mykey = 0ull;
-    if (pi < w && pj < h) {
-      const ulonglong2 px = *reinterpret_cast<const ulonglong2 *>(canvas + pix);
-      unsigned int out = 0u;
-      mykey = px.y;
-      if (0ull != px.y) {
-        const unsigned int obj = (unsigned int)(px.y >> C3D_KEY_OBJ_SHIFT) - 1u;
-        if (obj >= p.ncontours) {
-          const LineDev &ln = lines[obj - p.ncontours];
-          out = 0xFF000000u | ((unsigned int)ln.color[2] << 16) | ((unsigned int)ln.color[1] << 8) | ln.color[0];
-        } else {
-          const unsigned long long prim = px.y & C3D_KEY_PRIM_MASK;
-          home = cube_home(part, (unsigned int)((prim >> 20) & 65535ull), (unsigned int)((prim >> 36) & 65535ull));
+    if (tile_owner(part, tx, ty) != (unsigned int)part.me) continue;      /* block-uniform */
+    if (threadIdx.x < C3D_MAX_RANKS) s_count[threadIdx.x] = 0u;
+    __syncthreads();
+    for (unsigned int q = threadIdx.x; q < unit_px; q += blockDim.x) {
+      const unsigned int pi = tx * tile + (q & (tile - 1u)), pj = ty * tile + sub * rows + (q >> part.tile_shift);
+      unsigned int home = 0xffu;
+      if (pi < w && pj < h) {
+        const size_t pix = (size_t)pj * w + pi;
+        const ulonglong2 px = *reinterpret_cast<const ulonglong2 *>(canvas + pix);
+        unsigned int out = 0u;
+        if (0ull != px.y) {
+          const unsigned int obj = (unsigned int)(px.y >> C3D_KEY_OBJ_SHIFT) - 1u;
+          if (obj >= p.ncontours) {
+            const LineDev &ln = lines[obj - p.ncontours];
+            out = 0xFF000000u | ((unsigned int)ln.color[2] << 16) | ((unsigned int)ln.color[1] << 8) | ln.color[0];
+          } else {
+            const unsigned long long prim = px.y & C3D_KEY_PRIM_MASK;
+            home = cube_home(part, (unsigned int)((prim >> 20) & 65535ull), (unsigned int)((prim >> 36) & 65535ull));
+            atomicAdd(&s_count[home], 1u);
+          }
         }
+        if (0xffu == home) rgba_out[pix] = out;
       }
-      if (0xffffffffu == home) rgba_out[pix] = out;
+      s_home[q] = (unsigned char)home;
     }
-    /* one append per rank that has pixels in this warp */
-    unsigned int pending = __ballot_sync(C3D_FULL_MASK, 0xffffffffu != home);
-    while (pending) {
-      const unsigned int leader = (unsigned int)__ffs((int)pending) - 1u;
-      const unsigned int r = __shfl_sync(C3D_FULL_MASK, home, (int)leader);
-      const unsigned int who = __ballot_sync(C3D_FULL_MASK, home == r);
-      unsigned int at = 0u;
-      if (lane == leader) at = atomicAdd(nseg + r, (unsigned int)__popc(who));
-      at = __shfl_sync(C3D_FULL_MASK, at, (int)leader);
-      if (home == r) {
-        const unsigned int slot = at + __popc(who & ((1u << lane) - 1u));
-        if (slot < seg_cap) seg[(size_t)r * seg_cap + slot] = WorkItem{(unsigned int)pix, 0u, mykey};
-        else atomicAdd(overflowed, 1ull);
-      }
-      pending &= ~who;
+    __syncthreads();
+    if (threadIdx.x < (unsigned int)part.nranks) {
+      const unsigned int cnt = s_count[threadIdx.x];
+      s_base[threadIdx.x] = 0u != cnt ? atomicAdd(nseg + threadIdx.x, cnt) : 0u;
+      s_count[threadIdx.x] = 0u;
     }
+    __syncthreads();
+    for (unsigned int q = threadIdx.x; q < unit_px; q += blockDim.x) {
+      const unsigned int home = s_home[q];
+      if (0xffu == home) continue;
+      const unsigned int pi = tx * tile + (q & (tile - 1u)), pj = ty * tile + sub * rows + (q >> part.tile_shift);
+      const size_t pix = (size_t)pj * w + pi;
+      const unsigned int slot = s_base[home] + atomicAdd(&s_count[home], 1u);
+      if (slot < seg_cap) seg[(size_t)home * seg_cap + slot] = WorkItem{(unsigned int)pix, home, canvas[pix].key};
+      else atomicAdd(overflowed, 1ull);
+    }
+    __syncthreads();
   }
 }
 
@@ -206,9 +215,15 @@ __device__ __forceinline__ V3 face_term_of(const FieldView &f, const unsigned in
   return v_mul(area, fn);
 }
 
-__device__ __forceinline__ V3 face_term(const FrameParams &p, const unsigned int obj, const long long i, const long long j, const long long k,
+/* object `obj` as rank `owner` holds it: this rank's own array, or (a partitioned frame's shading helper) the owner's
+   through peer memory */
+__device__ __forceinline__ const FieldView &owner_view(const FrameParams &p, const unsigned int owner, const unsigned int obj) {
+  if (nullptr != p.pviews && owner != (unsigned int)p.part.me) return p.pviews[C3D_PEER_VIEW(owner, obj)];
+  return p.view[obj];
+}
+
+__device__ __forceinline__ V3 face_term(const FrameParams &p, const FieldView &f, const long long i, const long long j, const long long k,
                                         const unsigned int code, const unsigned int s) {
-  const FieldView &f = p.view[obj];
   const unsigned int pairs = __ldg(p.tab.pairs + code * C3D_MAX_TRIS + s);
   if (nullptr != f.map) {      /* tabulated converter: corner positions come from the tables, one vertex at a time */
     V3 v[3], fn;
@@ -227,8 +242,9 @@ struct ShadePix {              /* 56 bytes per listed pixel */
   double w[3];                 /* barycentric weights of the pixel centre (render.c:102-110) */
   unsigned int vslot[3];       /* table slots of the three vertices; C3D_NO_SLOT: table full, normal computed on the spot */
   unsigned int pix;
-  unsigned short i, j, k;      /* cube of the winning triangle */
+  unsigned short i, j, k;      /* cube of the winning triangle (indices on the owner's array) */
   unsigned char obj, edges[3]; /* cube-edge ids of its three vertices */
+  unsigned char owner;         /* rank whose array the cube indices refer to (partitioned frames; else 0) */
 };
 static_assert(sizeof(ShadePix) == C3D_SHADE_PIX_BYTES, "ShadePix layout");
 
@@ -239,9 +255,9 @@ static_assert(sizeof(ShadePix) == C3D_SHADE_PIX_BYTES, "ShadePix layout");
 /* the global edge a cube-local edge id names: the cube whose edge 0 / 4 / 8 / 12 / 14 / 16 / 18 it is (the numbering of
    triangulate.c:15-32: 0-3 x edges at (dj, dk), 4-7 y edges at (di, dk), 8-11 z edges at (di, dj), 12/13 yz-face
    diagonals at di, 14/15 xz at dj, 16/17 xy at dk, 18 the body diagonal), packed as
-   1:1 | object:4 | type:3 | k:16 | j:16 | i:16 (never 0 = empty slot) */
-__device__ __forceinline__ unsigned long long vertex_key(const unsigned int obj, const unsigned int i, const unsigned int j, const unsigned int k,
-                                                         const unsigned int e) {
+   1:1 | owner:3 | object:4 | type:3 | k:16 | j:16 | i:16 (never 0 = empty slot); owner = the rank on whose array (i, j, k) count */
+__device__ __forceinline__ unsigned long long vertex_key(const unsigned int owner, const unsigned int obj, const unsigned int i, const unsigned int j,
+                                                         const unsigned int k, const unsigned int e) {
   unsigned int ci = i, cj = j, ck = k, type;
   if (e < 12u) {
     const unsigned int axis = e >> 2, a = e & 1u, b = (e >> 1) & 1u;
@@ -258,7 +274,7 @@ __device__ __forceinline__ unsigned long long vertex_key(const unsigned int obj,
   } else {
     type = 6u;
   }
-  return (1ull << 63) | ((unsigned long long)obj << 51) | ((unsigned long long)type << 48) | ((unsigned long long)ck << 32)
+  return (1ull << 63) | ((unsigned long long)owner << 55) | ((unsigned long long)obj << 51) | ((unsigned long long)type << 48) | ((unsigned long long)ck << 32)
        | ((unsigned long long)cj << 16) | (unsigned long long)ci;
 }
 
@@ -278,7 +294,7 @@ __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ Fra
     ShadePix me;
     me.w[0] = me.w[1] = me.w[2] = 0.;
     me.vslot[0] = me.vslot[1] = me.vslot[2] = C3D_NO_SLOT;
-    me.pix = 0u; me.i = me.j = me.k = 0; me.obj = 0; me.edges[0] = me.edges[1] = me.edges[2] = 0;
+    me.pix = 0u; me.i = me.j = me.k = 0; me.obj = 0; me.edges[0] = me.edges[1] = me.edges[2] = 0; me.owner = 0;
     unsigned long long vkey[3] = {0ull, 0ull, 0ull};
     if (valid) {
       const uint4 item = __ldg(reinterpret_cast<const uint4 *>(work) + idx);
@@ -287,8 +303,9 @@ __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ Fra
       const unsigned int obj = (unsigned int)(key >> C3D_KEY_OBJ_SHIFT) - 1u;
       const unsigned long long prim = key & C3D_KEY_PRIM_MASK;
       const unsigned int s = (unsigned int)(prim & 15ull);
-      const FieldView &f = p.view[obj];
-      /* the key names the cube by its GLOBAL indices; this rank's array starts at f.off */
+      const unsigned int owner = item.y;
+      const FieldView &f = owner_view(p, owner, obj);
+      /* the key names the cube by its GLOBAL indices; the owner's array starts at f.off */
       const long long i = (long long)((prim >> 4) & 65535ull) - f.off[0], j = (long long)((prim >> 20) & 65535ull) - f.off[1],
                       k = (long long)((prim >> 36) & 65535ull) - f.off[2];
       const unsigned int code = cube_code(f, i, j, k);
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ Fra
       bool ok = true;
 #pragma unroll
       for (int m = 0; m < 3; m++) {
-        const ProjectedVertex v = exact_vertex(p, obj, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
+        const ProjectedVertex v = exact_vertex_t<true>(p.cam, f, i, j, k, (pairs >> (6 * m)) & 7u, (pairs >> (6 * m + 3)) & 7u);
         ok = ok && (0. != v.w);
         t.q[m] = V3{v.x, v.y, v.z};
       }
@@ -309,10 +326,11 @@ __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ Fra
       me.pix = pix;
       me.i = (unsigned short)i; me.j = (unsigned short)j; me.k = (unsigned short)k;
       me.obj = (unsigned char)obj;
+      me.owner = (unsigned char)owner;
 #pragma unroll
       for (int m = 0; m < 3; m++) {
         me.edges[m] = (unsigned char)((edges >> (5 * m)) & 31u);
-        vkey[m] = vertex_key(obj, (unsigned int)i, (unsigned int)j, (unsigned int)k, me.edges[m]);
+        vkey[m] = vertex_key(owner, obj, (unsigned int)i, (unsigned int)j, (unsigned int)k, me.edges[m]);
       }
     }
     /* the three vertices probe the table side by side: an atomic round trip costs about a microsecond, and a warp waits
@@ -374,7 +392,7 @@ __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ Fra
 struct ShadeSlot {             /* one cube sharing the edge of one vertex */
   unsigned short i, j, k;
   unsigned short touch;        /* triangles of that cube with a vertex on the shared edge (bit s) */
-  unsigned char obj, code;
+  unsigned char obj, code, owner;
 };
 
 /*
@@ -413,18 +431,19 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
       const unsigned int q = r * SH_THREADS + tid;
       const unsigned int v = base + (q >> 2), c = q & 3u;
       ShadeSlot slot;
-      slot.i = slot.j = slot.k = 0; slot.touch = 0; slot.obj = 0; slot.code = 0;
+      slot.i = slot.j = slot.k = 0; slot.touch = 0; slot.obj = 0; slot.code = 0; slot.owner = 0;
       const unsigned int at = v < nv ? __ldg(vlist + v) : C3D_NO_SLOT;
       if (C3D_NO_SLOT != at) {
         const unsigned long long key = table[at];
-        const unsigned int type = (unsigned int)(key >> 48) & 7u, obj = (unsigned int)(key >> 51) & 15u;
+        const unsigned int type = (unsigned int)(key >> 48) & 7u, obj = (unsigned int)(key >> 51) & 15u, owner = (unsigned int)(key >> 55) & 7u;
         const unsigned int e = type < 3u ? 4u * type : (type < 6u ? 6u + 2u * type : 18u);   /* edge 0 / 4 / 8 / 12 / 14 / 16 / 18 of that cube */
         int di, dj, dk;
         unsigned int local;
         slot.obj = (unsigned char)obj;
+        slot.owner = (unsigned char)owner;
         if (edge_neighbour(e, c, di, dj, dk, local)) {
           const long long ii = (long long)(key & 65535ull) + di, jj = (long long)((key >> 16) & 65535ull) + dj, kk = (long long)((key >> 32) & 65535ull) + dk;
-          const unsigned int code = cube_code(p.view[obj], ii, jj, kk);
+          const unsigned int code = cube_code(owner_view(p, owner, obj), ii, jj, kk);
           slot.i = (unsigned short)ii; slot.j = (unsigned short)jj; slot.k = (unsigned short)kk;
           slot.code = (unsigned char)code;
           slot.touch = __ldg(p.tab.touch + code * 19u + local);
@@ -472,7 +491,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
       for (unsigned int it = tid; it < total_items; it += SH_THREADS) {
         const unsigned int q = s_item[it] >> 4, s = s_item[it] & 15u;
         const ShadeSlot slot = s_slot[q];
-        const V3 term = face_term(p, slot.obj, slot.i, slot.j, slot.k, slot.code, s);
+        const V3 term = face_term(p, owner_view(p, slot.owner, slot.obj), slot.i, slot.j, slot.k, slot.code, s);
         s_term[it][0] = term.x; s_term[it][1] = term.y; s_term[it][2] = term.z;
       }
       __syncthreads();
@@ -496,7 +515,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
           while (touch) {
             const unsigned int s = (unsigned int)__ffs((int)touch) - 1u;
             touch &= touch - 1u;
-            sum = v_add(sum, face_term(p, slot.obj, slot.i, slot.j, slot.k, slot.code, s));
+            sum = v_add(sum, face_term(p, owner_view(p, slot.owner, slot.obj), slot.i, slot.j, slot.k, slot.code, s));
           }
         }
         store_normal(v_unit(sum), base + tid, __ldg(vlist + base + tid), vn, vn_cap, table);
@@ -514,7 +533,7 @@ __global__ void __launch_bounds__(128) k_shade_blend(const __grid_constant__ Fra
   const unsigned int n = counters[0];
   for (unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const ShadePix sp = in[idx];
-    const FieldView &f = p.view[sp.obj];
+    const FieldView &f = owner_view(p, sp.owner, sp.obj);
     V3 nv[3];
 #pragma unroll
     for (int m = 0; m < 3; m++) {

@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tiles(const __grid_cons
  */
 struct DepthOrder {
   float near_depth, scale;          /* bucket = (near_depth - n.(p - cam)) * scale, clamped */
+  float last;                       /* highest bucket */
 };
 
 __device__ __forceinline__ unsigned int depth_bucket(const FrameParams &p, const DepthOrder &o, const unsigned int obj, const unsigned int x,
@@ -438,7 +439,7 @@ __device__ __forceinline__ unsigned int depth_bucket(const FrameParams &p, const
   rx -= p.cull.cam[0]; ry -= p.cull.cam[1]; rz -= p.cull.cam[2];
   const float nr = p.cull.n[0] * rx + p.cull.n[1] * ry + p.cull.n[2] * rz;
   const float b = (o.near_depth - nr) * o.scale;
-  return (unsigned int)fminf(fmaxf(b, 0.f), (float)(C3D_DEPTH_BUCKETS - 1));    /* NaN -> 0 */
+  return (unsigned int)fminf(fmaxf(b, 0.f), o.last);    /* NaN -> 0 */
 }
 
 __global__ void __launch_bounds__(256) k_bucket_count(const __grid_constant__ FrameParams p, const DepthOrder o,
@@ -690,7 +691,7 @@ __device__ __forceinline__ unsigned int cube_owners(const FrameParams &p, const 
  * Pass 1: who draws each cut cube?  Warp-cooperative -- a warp takes 32 records and spreads their 1..32 cut cubes over
  * its lanes (the records hold 3-4 on average; one thread per record would idle most lanes through the eight
  * projections of cube_owners()).  The answer is kept, one byte per cube at masks[record * 32 + bit], for pass 2, and
- * counted per (destination rank, depth bucket): histogram[r * C3D_DEPTH_BUCKETS + b].
+ * counted per (destination rank, depth bucket): histogram[r * C3D_PART_BUCKETS + b].
  */
 __global__ void __launch_bounds__(256) k_part_count(const __grid_constant__ FrameParams p, const DepthOrder o,
                                                     const SweepRecord *__restrict__ records, const unsigned long long *__restrict__ nrecords,
@@ -698,7 +699,7 @@ __global__ void __launch_bounds__(256) k_part_count(const __grid_constant__ Fram
                                                     unsigned int *__restrict__ histogram) {
   extern __shared__ unsigned int local[];
   __shared__ unsigned int s_active[8][32], s_first[8][32], s_xj[8][32], s_kobj[8][32], s_bucket[8][32];
-  const unsigned int nbins = (unsigned int)p.part.nranks * C3D_DEPTH_BUCKETS;
+  const unsigned int nbins = (unsigned int)p.part.nranks * C3D_PART_BUCKETS;
   for (unsigned int b = threadIdx.x; b < nbins; b += blockDim.x) local[b] = 0u;
   __syncthreads();
   unsigned long long n = *nrecords;
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(256) k_part_count(const __grid_constant__ Fram
         while (owners) {
           const int r = __ffs((int)owners) - 1;
           owners &= owners - 1u;
-          atomicAdd(local + (unsigned int)r * C3D_DEPTH_BUCKETS + bucket, 1u);
+          atomicAdd(local + (unsigned int)r * C3D_PART_BUCKETS + bucket, 1u);
         }
       }
     }
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(256) k_part_count(const __grid_constant__ Fram
 __global__ void __launch_bounds__(1024) k_part_scan(const unsigned int *__restrict__ histogram, const int nranks, unsigned long long *__restrict__ cursors,
                                                     unsigned long long *__restrict__ seg_start, unsigned long long *__restrict__ count) {
   __shared__ unsigned long long part[1024];
-  const unsigned int per = (unsigned int)(C3D_DEPTH_BUCKETS / 1024) * (unsigned int)nranks;
+  const unsigned int per = (unsigned int)(C3D_PART_BUCKETS / 1024) * (unsigned int)nranks;
   const unsigned int first = threadIdx.x * per;
   unsigned long long mine = 0ull;
   for (unsigned int q = 0; q < per; q++) mine += histogram[first + q];
@@ -776,7 +777,7 @@ __global__ void __launch_bounds__(1024) k_part_scan(const unsigned int *__restri
   for (unsigned int q = 0; q < per; q++) {
     const unsigned int bin = first + q;
     cursors[bin] = at;
-    if (0u == bin % C3D_DEPTH_BUCKETS) seg_start[bin / C3D_DEPTH_BUCKETS] = at;
+    if (0u == bin % C3D_PART_BUCKETS) seg_start[bin / C3D_PART_BUCKETS] = at;
     at += histogram[bin];
   }
   if (1023u == threadIdx.x) *count = part[1023];
@@ -842,7 +843,7 @@ __global__ void __launch_bounds__(256) k_part_expand(const __grid_constant__ Fra
           cnt += (owners[bit] >> r) & 1u;
         }
       }
-      unsigned long long at = atomicAdd(cursors + (unsigned int)r * C3D_DEPTH_BUCKETS + bucket, (unsigned long long)cnt);
+      unsigned long long at = atomicAdd(cursors + (unsigned int)r * C3D_PART_BUCKETS + bucket, (unsigned long long)cnt);
       unsigned int todo = active;
       while (todo) {
         const int bit = __ffs((int)todo) - 1;
@@ -1014,6 +1015,7 @@ extern "C" int c3d_k_expand(const FrameParams *fp, int sorted, float near_depth,
   DepthOrder o;
   o.near_depth = near_depth;
   o.scale = (near_depth > far_depth) ? (float)C3D_DEPTH_BUCKETS / (near_depth - far_depth) : 0.f;
+  o.last = (float)(C3D_DEPTH_BUCKETS - 1);
   if (sorted) {
     const cudaError_t err = cudaMemsetAsync(histogram, 0, C3D_DEPTH_BUCKETS * sizeof(unsigned int), s);
     if (cudaSuccess != err) return (int)err;
@@ -1035,8 +1037,9 @@ extern "C" int c3d_k_expand_part(const FrameParams *fp, float near_depth, float 
   if (nranks < 2 || nranks > C3D_MAX_RANKS) return (int)cudaErrorInvalidValue;
   DepthOrder o;
   o.near_depth = near_depth;
-  o.scale = (near_depth > far_depth) ? (float)C3D_DEPTH_BUCKETS / (near_depth - far_depth) : 0.f;
-  const size_t bins = (size_t)nranks * C3D_DEPTH_BUCKETS;
+  o.scale = (near_depth > far_depth) ? (float)C3D_PART_BUCKETS / (near_depth - far_depth) : 0.f;
+  o.last = (float)(C3D_PART_BUCKETS - 1);
+  const size_t bins = (size_t)nranks * C3D_PART_BUCKETS;
   cudaError_t err = cudaMemsetAsync(histogram, 0, bins * sizeof(unsigned int), s);
   if (cudaSuccess != err) return (int)err;
   err = cudaFuncSetAttribute(k_part_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bins * sizeof(unsigned int)));
