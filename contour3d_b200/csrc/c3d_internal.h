@@ -178,7 +178,7 @@ struct __align__(16) WorkItem { unsigned int pix, pad; unsigned long long key; }
 #define C3D_SHADE_PIX_BYTES 56
 struct ShadeScratch {
   WorkItem *work;                /* pixels won by a contour triangle, compacted: npix items */
-  unsigned int *counters;        /* [0] listed pixels, [1] distinct vertices */
+  unsigned int *counters;        /* [0] listed pixels, [1] distinct vertices, [2] pixels of the first pass, [3] vertices of the first pass */
   void *pix;                     /* per listed pixel: weights, cube, vertex slots: npix x C3D_SHADE_PIX_BYTES */
   unsigned long long *table;     /* open-addressing set of the vertices (global cube edges) the listed pixels reference */
   unsigned int table_mask;       /* slots - 1 (a power of two) */
@@ -222,7 +222,7 @@ int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const Pixel *can
                 unsigned int *rgba, size_t npix, const ShadeScratch *scratch, unsigned long long *overflowed,
                 int sm_count, cudaStream_t s);
 int c3d_k_shade_begin(const ShadeScratch *scratch, cudaStream_t s);
-int c3d_k_shade_finish(const FrameParams *p, unsigned int *rgba, const ShadeScratch *scratch, unsigned long long *overflowed, int sm_count, cudaStream_t s);
+int c3d_k_shade_finish(const FrameParams *p, unsigned int *rgba, const ShadeScratch *scratch, unsigned long long *overflowed, int helpers, int sm_count, cudaStream_t s);
 int c3d_k_shade_select_part(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, unsigned int *rgba_out,
                             WorkItem *seg, unsigned int seg_cap, unsigned int *nseg, unsigned long long *overflowed, int sm_count, cudaStream_t s);
 /* screen-partitioned frames (c3d_sweep.cu, c3d_kernels.cu) */

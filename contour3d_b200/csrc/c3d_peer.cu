@@ -446,26 +446,40 @@ int c3d_k_merge_lists(const MergeSources *src, int nranks, int me, unsigned long
 
 /*
  * Who shades what.  Rank d has queued, per owner o, the pixels of its tiles won by cubes of o's array: count C[d][o], items
- * in seg[d][o].  Owner o's pixels in the order d = 0, 1, .. form its list of T[o] = sum_d C[d][o] items.  An owner with
- * more than the mean keeps the first `keep` items and hands the rest to the ranks below the mean (they read the owner's array
- * through peer memory): the front slab of a z-decomposed volume otherwise shades a third of the image on its own.
- * Every rank runs this same integer plan on the same counts, and writes down only what IT has to pull.
+ * in seg[d][o].  Owner o's pixels in the order d = 0, 1, .. form its list of T[o] = sum_d C[d][o] items.  The front slab of
+ * a z-decomposed volume wins a third of the image on its own; ranks with little to shade take some of it over, reading the
+ * owner's array through peer memory -- at `remote_cost` times the price of a pixel of their own (measured: about five).
+ * The plan levels the ESTIMATED TIME: the level tau solves  sum_{T > tau} (T - tau) = sum_{T < tau} (tau - T) / remote_cost;
+ * owners above keep their first tau items, ranks below fill up to tau with foreign ones, dealt out in rank order.
+ * Every rank runs this same plan on the same counts and writes down only what IT has to pull.
+ * counters[0] <- all items of this rank, counters[2] <- those of its own array (they come first).
  */
-__global__ void k_work_plan(const WorkExchange ex, const int n, const int me, const float share, PullPlan *__restrict__ plan,
-                            unsigned int *__restrict__ nwork, const unsigned int capacity, unsigned long long *__restrict__ overflowed) {
+__global__ void k_work_plan(const WorkExchange ex, const int n, const int me, const float remote_cost, PullPlan *__restrict__ plan,
+                            unsigned int *__restrict__ counters, const unsigned int capacity, unsigned long long *__restrict__ overflowed) {
   if (0 != threadIdx.x || 0 != blockIdx.x) return;
   unsigned int C[C3D_MAX_RANKS][C3D_MAX_RANKS], T[C3D_MAX_RANKS], keep[C3D_MAX_RANKS], room[C3D_MAX_RANKS];
-  unsigned long long total = 0ull;
+  unsigned int most = 0u;
   for (int o = 0; o < n; o++) T[o] = 0u;
   for (int d = 0; d < n; d++) {
     for (int o = 0; o < n; o++) { C[d][o] = ex.nseg[d][o]; T[o] += C[d][o]; }
   }
-  for (int o = 0; o < n; o++) total += T[o];
-  const unsigned int mean = (unsigned int)((total + (unsigned long long)n - 1ull) / (unsigned long long)n);
+  for (int o = 0; o < n; o++) most = T[o] > most ? T[o] : most;
+  float tau = (float)most;
+  if (remote_cost >= 1.f) {
+    float lo = 0.f, hi = (float)most;
+    for (int it = 0; it < 40; it++) {
+      const float mid = 0.5f * (lo + hi);
+      float give = 0.f, takes = 0.f;
+      for (int o = 0; o < n; o++) {
+        if ((float)T[o] > mid) give += (float)T[o] - mid; else takes += (mid - (float)T[o]) / remote_cost;
+      }
+      if (give > takes) lo = mid; else hi = mid;
+    }
+    tau = hi;
+  }
   for (int o = 0; o < n; o++) {
-    const unsigned int excess = T[o] > mean ? (unsigned int)((float)(T[o] - mean) * share) : 0u;
-    keep[o] = T[o] - excess;
-    room[o] = T[o] < mean ? mean - T[o] : 0u;
+    keep[o] = (float)T[o] > tau ? (unsigned int)tau : T[o];
+    room[o] = (remote_cost >= 1.f && (float)T[o] < tau) ? (unsigned int)((tau - (float)T[o]) / remote_cost) : 0u;
   }
   unsigned int nchunks = 0u, dest = 0u;
   /* a range [a, a + cnt) of owner o's list, as pieces of the ranks' segments */
@@ -483,24 +497,44 @@ __global__ void k_work_plan(const WorkExchange ex, const int n, const int me, co
       before = end;
     }
   };
-  take(me, 0u, keep[me]);
-  int r = 0;
-  for (int o = 0; o < n; o++) {
-    unsigned int a = keep[o], left = T[o] - keep[o];
-    while (left > 0u) {
-      while (r < n && 0u == room[r]) r++;
-      if (r >= n) {                           /* rounding left a few: the owner keeps them after all */
-        if (o == me) take(o, a, left);
-        break;
+  /* this rank's own: what it keeps, plus what nobody had room for (rounding) */
+  unsigned int left_over[C3D_MAX_RANKS], handed[C3D_MAX_RANKS];
+  {
+    int r = 0;
+    for (int o = 0; o < n; o++) {
+      unsigned int left = T[o] - keep[o];
+      handed[o] = 0u;
+      while (left > 0u) {
+        while (r < n && 0u == room[r]) r++;
+        if (r >= n) break;
+        const unsigned int give = left < room[r] ? left : room[r];
+        room[r] -= give; left -= give; handed[o] += give;
       }
-      const unsigned int give = left < room[r] ? left : room[r];
-      if (r == me) take(o, a, give);
-      room[r] -= give; a += give; left -= give;
+      left_over[o] = left;
+    }
+  }
+  take(me, 0u, keep[me]);
+  if (left_over[me] > 0u) take(me, keep[me] + handed[me], left_over[me]);
+  const unsigned int nlocal = dest;
+  /* the same dealing once more, now writing down the pieces that come to this rank */
+  for (int o = 0; o < n; o++) room[o] = (remote_cost >= 1.f && (float)T[o] < tau) ? (unsigned int)((tau - (float)T[o]) / remote_cost) : 0u;
+  {
+    int r = 0;
+    for (int o = 0; o < n; o++) {
+      unsigned int a = keep[o], left = T[o] - keep[o];
+      while (left > 0u) {
+        while (r < n && 0u == room[r]) r++;
+        if (r >= n) break;
+        const unsigned int give = left < room[r] ? left : room[r];
+        if (r == me) take(o, a, give);
+        room[r] -= give; a += give; left -= give;
+      }
     }
   }
   plan->nchunks = nchunks;
   plan->nwork = dest < capacity ? dest : capacity;
-  *nwork = plan->nwork;
+  counters[0] = plan->nwork;
+  counters[2] = nlocal < plan->nwork ? nlocal : plan->nwork;
   if (dest > capacity) atomicAdd(overflowed, 1ull);
 }
 
@@ -524,9 +558,9 @@ __global__ void __launch_bounds__(256) k_work_copy(const WorkExchange ex, const 
   }
 }
 
-int c3d_k_work_exchange(const WorkExchange *ex, int nranks, int me, float share, PullPlan *plan, WorkItem *work, unsigned int *nwork,
+int c3d_k_work_exchange(const WorkExchange *ex, int nranks, int me, float remote_cost, PullPlan *plan, WorkItem *work, unsigned int *counters,
                         unsigned int capacity, unsigned long long *overflowed, cudaStream_t s) {
-  k_work_plan<<<1, 32, 0, s>>>(*ex, nranks, me, share, plan, nwork, capacity, overflowed);
+  k_work_plan<<<1, 32, 0, s>>>(*ex, nranks, me, remote_cost, plan, counters, capacity, overflowed);
   k_work_copy<<<148 * 2, 256, 0, s>>>(*ex, plan, work, capacity);
   return (int)cudaGetLastError();
 }

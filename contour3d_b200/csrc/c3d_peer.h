@@ -74,9 +74,10 @@ struct WorkExchange {
 #define C3D_PULL_CHUNKS (C3D_MAX_RANKS * (C3D_MAX_RANKS + 2))
 struct PullChunk { unsigned int owner, d, first, count, dest; };
 struct PullPlan { unsigned int nchunks, nwork; PullChunk chunk[C3D_PULL_CHUNKS]; };
-/* decides which pixels this rank shades (its own cubes' up to the mean load, plus its share of what the busiest ranks hand
-   over: share = fraction of their excess, 0 = everybody shades exactly the pixels its own cubes won) and pulls them */
-int c3d_k_work_exchange(const WorkExchange *ex, int nranks, int me, float share, PullPlan *plan, WorkItem *work, unsigned int *nwork,
+/* decides which pixels this rank shades (those its own cubes won, up to a level; ranks below the level take over what the
+   busiest hand off, at remote_cost times the price: remote_cost < 1 = everybody shades exactly its own) and pulls them:
+   counters[0] <- items pulled, counters[2] <- those of this rank's own array (first in `work`) */
+int c3d_k_work_exchange(const WorkExchange *ex, int nranks, int me, float remote_cost, PullPlan *plan, WorkItem *work, unsigned int *counters,
                         unsigned int capacity, unsigned long long *overflowed, cudaStream_t s);
 
 /* flag[0] of every rank -> max into mine */

@@ -148,7 +148,7 @@ struct c3d_context {
   size_t part_masks_cap;                           /* in records */
   int tile_shift;                                  /* log2 of the screen-tile edge of partitioned frames */
   PullPlan *pull_plan;                             /* device: which shading work this rank pulls (k_work_plan) */
-  float shade_share;                               /* fraction of the busiest ranks' excess shading that the others take over */
+  float shade_share;                               /* relative cost of a pixel shaded by a helper rank (0: no helping) */
   void *table_mem;
   DevTables tab;
   /* canvases */
@@ -240,7 +240,7 @@ static int context_init(c3d_context *ctx, const int comm_rank, const int comm_si
   CUDA_OK(cudaMalloc(&ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long)));
   CUDA_OK(cudaMallocHost(&ctx->counts_host, CNT_TOTAL * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->tile_cursor, sizeof(unsigned int)));
-  CUDA_OK(cudaMalloc(&ctx->shade.counters, 2 * sizeof(unsigned int)));
+  CUDA_OK(cudaMalloc(&ctx->shade.counters, 4 * sizeof(unsigned int)));
   CUDA_OK(cudaMalloc(&ctx->bucket_hist, C3D_DEPTH_BUCKETS * sizeof(unsigned int)));
   CUDA_OK(cudaMalloc(&ctx->bucket_cursors, C3D_DEPTH_BUCKETS * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&ctx->views_dev, C3D_MAX_OBJECTS * sizeof(FieldView)));
@@ -271,9 +271,11 @@ static int context_init(c3d_context *ctx, const int comm_rank, const int comm_si
       CUDA_OK(cudaMalloc(&ctx->merge_base, (size_t)C3D_PART_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
       CUDA_OK(cudaMalloc(&ctx->part_cursors, (size_t)C3D_PART_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
       CUDA_OK(cudaMalloc(&ctx->pull_plan, sizeof(PullPlan)));
-      const char *env = getenv("CONTOUR3D_SHADE_SHARE");
-      ctx->shade_share = (NULL != env && '\0' != *env) ? (float)atof(env) : 1.f;
-      if (!(ctx->shade_share >= 0.f && ctx->shade_share <= 1.f)) ctx->shade_share = 1.f;
+      /* what shading a pixel costs a helper (reading the owner's array through peer memory) relative to the owner itself;
+         0 = no helping: every rank shades exactly the pixels its own cubes won */
+      const char *env = getenv("CONTOUR3D_SHADE_REMOTE_COST");
+      ctx->shade_share = (NULL != env && '\0' != *env) ? (float)atof(env) : 5.f;
+      if (!(ctx->shade_share >= 1.f)) ctx->shade_share = 0.f;
     }
     /* 2. NCCL communicator: frames with coordinate converters and nodes without peer access reduce whole images through it.
           Ranks that share a GPU (test boxes) cannot form one: they have the peer path only. */
@@ -1384,8 +1386,8 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE0], s));
     mark();                                                             /* detail[8]: pull of the shading work */
     /* 5'. shade what this rank's cubes have won, anywhere on the screen, straight into the writer's image */
-    LAUNCH_OK(c3d_k_shade_finish(&fp, rgba_out, &ctx->shade, ctx->counts_dev + CNT_SHADE_SPILL, ctx->sm_count, s));
-    launches += 3;
+    LAUNCH_OK(c3d_k_shade_finish(&fp, rgba_out, &ctx->shade, ctx->counts_dev + CNT_SHADE_SPILL, 1, ctx->sm_count, s));
+    launches += 7;
     CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
     mark();                                                             /* detail[9]: shading */
     /* 6'. the image is complete when everybody is done; a buffer that overflowed anywhere makes everybody redo the frame */
@@ -1417,7 +1419,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     /* 5. shade only what survived */
     LAUNCH_OK(c3d_k_shade(&fp, lines_dev, ctx->canvas, depth_global, ctx->rgba, npix, &ctx->shade,
                           ctx->counts_dev + CNT_SHADE_SPILL, ctx->sm_count, s));
-    launches += 4;
+    launches += 5;
     CUDA_OK(cudaEventRecord(ctx->ev[EV_SHADE], s));
     /* 6. colours to the writer (the colour half of the reference's reduce) */
     if (ctx->size > 1) {

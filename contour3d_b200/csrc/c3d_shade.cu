@@ -217,9 +217,26 @@ __device__ __forceinline__ V3 face_term_of(const FieldView &f, const unsigned in
 
 /* object `obj` as rank `owner` holds it: this rank's own array, or (a partitioned frame's shading helper) the owner's
    through peer memory */
+template <bool HELP>
 __device__ __forceinline__ const FieldView &owner_view(const FrameParams &p, const unsigned int owner, const unsigned int obj) {
-  if (nullptr != p.pviews && owner != (unsigned int)p.part.me) return p.pviews[C3D_PEER_VIEW(owner, obj)];
+  if (HELP) return p.pviews[C3D_PEER_VIEW(owner, obj)];
   return p.view[obj];
+}
+
+/*
+ * The shading kernels run over a RANGE of the work list / vertex list, read from the counters on the device:
+ *   counters[0] work items, [1] vertices listed so far, [2] work items of the first pass, [3] vertices listed by the first pass.
+ * HELP = false: items [0, counters[2]) -- pixels won by cubes of this rank's own array (all of them on one rank);
+ * HELP = true:  items [counters[2], counters[0]) -- pixels another rank has handed over; their cubes are read from the
+ *               owner's array through peer memory (a separate instantiation: the common pass keeps its views in the constant bank).
+ */
+template <bool HELP> __device__ __forceinline__ void item_range(const unsigned int *counters, unsigned int &begin, unsigned int &end) {
+  begin = HELP ? counters[2] : 0u;
+  end = HELP ? counters[0] : counters[2];
+}
+template <bool HELP> __device__ __forceinline__ void vertex_range(const unsigned int *counters, unsigned int &begin, unsigned int &end) {
+  begin = HELP ? counters[3] : 0u;
+  end = counters[1];
 }
 
 __device__ __forceinline__ V3 face_term(const FrameParams &p, const FieldView &f, const long long i, const long long j, const long long k,
@@ -278,17 +295,19 @@ __device__ __forceinline__ unsigned long long vertex_key(const unsigned int owne
        | ((unsigned long long)cj << 16) | (unsigned long long)ci;
 }
 
+template <bool HELP>
 __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ FrameParams p,
                                                      const WorkItem *__restrict__ work, unsigned int *__restrict__ counters,
                                                      ShadePix *__restrict__ out, unsigned long long *__restrict__ table, const unsigned int mask,
                                                      unsigned int *__restrict__ vlist, unsigned long long *__restrict__ overflowed) {
   const unsigned int lane = threadIdx.x & 31u;
-  const unsigned int n = counters[0];
+  unsigned int first, n;
+  item_range<HELP>(counters, first, n);
   /* The vertex list is handed out in chunks of SH_CHUNK entries per warp: one counter for everybody costs a serialised
      round trip per append (measured: 58 % of this kernel's stall samples).  Unused entries of a chunk hold C3D_NO_SLOT. */
   unsigned int chunk_next = 0u, chunk_end = 0u;
   /* whole warps iterate together (ballots inside) */
-  for (unsigned int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+  for (unsigned int base = first + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u); base < n; base += gridDim.x * blockDim.x) {
     const unsigned int idx = base + lane;
     const bool valid = idx < n;
     ShadePix me;
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(128) k_shade_setup(const __grid_constant__ Fra
       const unsigned long long prim = key & C3D_KEY_PRIM_MASK;
       const unsigned int s = (unsigned int)(prim & 15ull);
       const unsigned int owner = item.y;
-      const FieldView &f = owner_view(p, owner, obj);
+      const FieldView &f = owner_view<HELP>(p, owner, obj);
       /* the key names the cube by its GLOBAL indices; the owner's array starts at f.off */
       const long long i = (long long)((prim >> 4) & 65535ull) - f.off[0], j = (long long)((prim >> 20) & 65535ull) - f.off[1],
                       k = (long long)((prim >> 36) & 65535ull) - f.off[2];
@@ -413,6 +432,7 @@ __device__ __forceinline__ void store_normal(const V3 unit, const unsigned int v
   }
 }
 
+template <bool HELP>
 __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_constant__ FrameParams p, unsigned long long *__restrict__ table,
                                                               const unsigned int *__restrict__ vlist, const unsigned int *__restrict__ counters,
                                                               double *__restrict__ vn, const unsigned int vn_cap, unsigned long long *__restrict__ overflowed) {
@@ -422,8 +442,9 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
   __shared__ double s_term[SH_ITEMS][3];
   __shared__ unsigned int s_warp_total[SH_THREADS / 32];
   const unsigned int tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-  const unsigned int nv = counters[1];
-  for (unsigned int base = blockIdx.x * SH_VERTS; base < nv; base += gridDim.x * SH_VERTS) {
+  unsigned int v0, nv;
+  vertex_range<HELP>(counters, v0, nv);
+  for (unsigned int base = v0 + blockIdx.x * SH_VERTS; base < nv; base += gridDim.x * SH_VERTS) {
     /* ---- slots = (vertex, sharing cube) in the reference's visiting order; count the triangles touching the edge ---- */
     unsigned int mycount[SH_SLOTS / SH_THREADS];
 #pragma unroll
@@ -443,7 +464,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
         slot.owner = (unsigned char)owner;
         if (edge_neighbour(e, c, di, dj, dk, local)) {
           const long long ii = (long long)(key & 65535ull) + di, jj = (long long)((key >> 16) & 65535ull) + dj, kk = (long long)((key >> 32) & 65535ull) + dk;
-          const unsigned int code = cube_code(owner_view(p, owner, obj), ii, jj, kk);
+          const unsigned int code = cube_code(owner_view<HELP>(p, owner, obj), ii, jj, kk);
           slot.i = (unsigned short)ii; slot.j = (unsigned short)jj; slot.k = (unsigned short)kk;
           slot.code = (unsigned char)code;
           slot.touch = __ldg(p.tab.touch + code * 19u + local);
@@ -491,7 +512,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
       for (unsigned int it = tid; it < total_items; it += SH_THREADS) {
         const unsigned int q = s_item[it] >> 4, s = s_item[it] & 15u;
         const ShadeSlot slot = s_slot[q];
-        const V3 term = face_term(p, owner_view(p, slot.owner, slot.obj), slot.i, slot.j, slot.k, slot.code, s);
+        const V3 term = face_term(p, owner_view<HELP>(p, slot.owner, slot.obj), slot.i, slot.j, slot.k, slot.code, s);
         s_term[it][0] = term.x; s_term[it][1] = term.y; s_term[it][2] = term.z;
       }
       __syncthreads();
@@ -515,7 +536,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
           while (touch) {
             const unsigned int s = (unsigned int)__ffs((int)touch) - 1u;
             touch &= touch - 1u;
-            sum = v_add(sum, face_term(p, owner_view(p, slot.owner, slot.obj), slot.i, slot.j, slot.k, slot.code, s));
+            sum = v_add(sum, face_term(p, owner_view<HELP>(p, slot.owner, slot.obj), slot.i, slot.j, slot.k, slot.code, s));
           }
         }
         store_normal(v_unit(sum), base + tid, __ldg(vlist + base + tid), vn, vn_cap, table);
@@ -527,13 +548,15 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
 
 /* ------------------------------------------------------------------- blend */
 
+template <bool HELP>
 __global__ void __launch_bounds__(128) k_shade_blend(const __grid_constant__ FrameParams p, const ShadePix *__restrict__ in,
                                                      const unsigned int *__restrict__ counters, const unsigned long long *__restrict__ table,
                                                      const double *__restrict__ vn, unsigned int *__restrict__ rgba) {
-  const unsigned int n = counters[0];
-  for (unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+  unsigned int first, n;
+  item_range<HELP>(counters, first, n);
+  for (unsigned int idx = first + blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const ShadePix sp = in[idx];
-    const FieldView &f = owner_view(p, sp.owner, sp.obj);
+    const FieldView &f = owner_view<HELP>(p, sp.owner, sp.obj);
     V3 nv[3];
 #pragma unroll
     for (int m = 0; m < 3; m++) {
@@ -561,19 +584,34 @@ template <typename K> static int resident_blocks(K kernel, const int threads, co
 
 /* clears the counters and the vertex table of a frame's shading */
 extern "C" int c3d_k_shade_begin(const ShadeScratch *sc, cudaStream_t s) {
-  cudaError_t err = cudaMemsetAsync(sc->counters, 0, 2 * sizeof(unsigned int), s);
+  cudaError_t err = cudaMemsetAsync(sc->counters, 0, 4 * sizeof(unsigned int), s);
   if (cudaSuccess != err) return (int)err;
   err = cudaMemsetAsync(sc->table, 0, ((size_t)sc->table_mask + 1u) * sizeof(unsigned long long), s);
   return (int)err;
 }
 
-/* shades the sc->counters[0] work items of sc->work into rgba (which may be another rank's image, through peer memory) */
+__global__ void k_shade_mark(unsigned int *counters, const int after_select) {
+  if (after_select) counters[2] = counters[0];        /* one pass over everything */
+  else counters[3] = counters[1];                     /* the vertices of the first pass end here */
+}
+
+/* shades the work items of sc->work into rgba (which may be another rank's image, through peer memory).  helpers != 0:
+   counters[2] (set by the work plan) separates this rank's own pixels from those handed over by other ranks, which take
+   a second pass that reads the owners' arrays through p->pviews. */
 extern "C" int c3d_k_shade_finish(const FrameParams *p, unsigned int *rgba, const ShadeScratch *sc, unsigned long long *overflowed,
-                                  int sm_count, cudaStream_t s) {
-  k_shade_setup<<<resident_blocks(k_shade_setup, 128, sm_count), 128, 0, s>>>(*p, sc->work, sc->counters, static_cast<ShadePix *>(sc->pix),
-                                                                              sc->table, sc->table_mask, sc->vlist, overflowed);
-  k_shade_normals<<<resident_blocks(k_shade_normals, SH_THREADS, sm_count), SH_THREADS, 0, s>>>(*p, sc->table, sc->vlist, sc->counters, sc->vn, sc->vn_cap, overflowed);
-  k_shade_blend<<<resident_blocks(k_shade_blend, 128, sm_count), 128, 0, s>>>(*p, static_cast<const ShadePix *>(sc->pix), sc->counters, sc->table, sc->vn, rgba);
+                                  int helpers, int sm_count, cudaStream_t s) {
+  if (!helpers) k_shade_mark<<<1, 1, 0, s>>>(sc->counters, 1);
+  k_shade_setup<false><<<resident_blocks(k_shade_setup<false>, 128, sm_count), 128, 0, s>>>(*p, sc->work, sc->counters, static_cast<ShadePix *>(sc->pix),
+                                                                                            sc->table, sc->table_mask, sc->vlist, overflowed);
+  k_shade_normals<false><<<resident_blocks(k_shade_normals<false>, SH_THREADS, sm_count), SH_THREADS, 0, s>>>(*p, sc->table, sc->vlist, sc->counters, sc->vn, sc->vn_cap, overflowed);
+  k_shade_blend<false><<<resident_blocks(k_shade_blend<false>, 128, sm_count), 128, 0, s>>>(*p, static_cast<const ShadePix *>(sc->pix), sc->counters, sc->table, sc->vn, rgba);
+  if (helpers) {
+    k_shade_mark<<<1, 1, 0, s>>>(sc->counters, 0);
+    k_shade_setup<true><<<resident_blocks(k_shade_setup<true>, 128, sm_count), 128, 0, s>>>(*p, sc->work, sc->counters, static_cast<ShadePix *>(sc->pix),
+                                                                                            sc->table, sc->table_mask, sc->vlist, overflowed);
+    k_shade_normals<true><<<resident_blocks(k_shade_normals<true>, SH_THREADS, sm_count), SH_THREADS, 0, s>>>(*p, sc->table, sc->vlist, sc->counters, sc->vn, sc->vn_cap, overflowed);
+    k_shade_blend<true><<<resident_blocks(k_shade_blend<true>, 128, sm_count), 128, 0, s>>>(*p, static_cast<const ShadePix *>(sc->pix), sc->counters, sc->table, sc->vn, rgba);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -583,7 +621,7 @@ extern "C" int c3d_k_shade(const FrameParams *p, const LineDev *lines_dev, const
   const int rc = c3d_k_shade_begin(sc, s);
   if (0 != rc) return rc;
   k_shade_select<<<sm_count * 8, 256, 0, s>>>(*p, lines_dev, canvas, depth_global, rgba, npix, sc->work, sc->counters);
-  return c3d_k_shade_finish(p, rgba, sc, overflowed, sm_count, s);
+  return c3d_k_shade_finish(p, rgba, sc, overflowed, 0, sm_count, s);
 }
 
 extern "C" int c3d_k_shade_select_part(const FrameParams *p, const LineDev *lines_dev, const Pixel *canvas, unsigned int *rgba_out,
