@@ -363,6 +363,7 @@ def ours(args):
         mine["cut_cubes_listed"] = int(sum(active[:nct]))
         mine["cubes_walked_by_raster"] = int(t["list_entries"])
         mine["culled_cubes"] = int(t["culled_cubes"])
+        mine["tile_share"] = [round(v, 4) for v in t["tile_share"][:world]]
         names = ("barrier0", "halo_pull", "stage_clear_sweep", "to_outboxes", "barrier1", "merge_lists", "raster_lines_select", "barrier2", "work_pull", "shading", "barrier3")
         mine["detail"] = {k: round(v / args.steps, 4) for k, v in zip(names, detail_sum)}
         gathered = [None] * world

@@ -135,6 +135,7 @@ class Timings(C.Structure):
         ("exchange_mode", C.c_uint32),
         ("list_entries", C.c_uint64),
         ("detail", C.c_float * 16),
+        ("tile_share", C.c_float * 8),
     ]
 
     def as_dict(self):
@@ -151,6 +152,7 @@ class Timings(C.Structure):
         d["exchange_mode"] = int(self.exchange_mode)
         d["list_entries"] = int(self.list_entries)
         d["detail"] = [float(self.detail[i]) for i in range(11)]
+        d["tile_share"] = [float(self.tile_share[i]) for i in range(8)]
         return d
 
 

@@ -138,10 +138,13 @@ struct Partition {
   int py, pz;                          /* process grid (x is never split) */
   unsigned short yoff[C3D_MAX_RANKS + 1], zoff[C3D_MAX_RANKS + 1];   /* global index of the first point of block c; [p] = N */
   unsigned char home[C3D_MAX_RANKS];   /* communicator rank of block (cy, cz): home[cy * pz + cz] */
+  const unsigned char *tile_map;       /* device: owner of tile ty * tiles_x + tx; nullptr: the fixed pattern (tx + 3 ty) mod nranks.
+                                          The same table on every rank; rebuilt when the ranks' loads drift apart (frame_once) */
 };
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ unsigned int tile_owner(const Partition &q, const unsigned int tx, const unsigned int ty) {
+  if (nullptr != q.tile_map) return (unsigned int)__ldg(q.tile_map + ty * (unsigned int)q.tiles_x + tx);
   const unsigned int v = tx + 3u * ty;
   return v - __umulhi(v, q.recip) * (unsigned int)q.nranks;
 }

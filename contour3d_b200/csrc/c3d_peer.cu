@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_copy(const MergeSources
   __syncthreads();
   const unsigned int total = prefix[C3D_PART_BUCKETS];
   const unsigned long long start = src.seg_start[s][me];
+  const unsigned long long readable = *src.out_cap[s];         /* entries rank s's outbox really holds (the counts may exceed it: overflow, frame redone) */
   const unsigned long long *outbox = src.outbox[s] + start;
   /* entries travel in aligned pairs (16 bytes); the segment may start on an odd entry */
   const unsigned int odd = (unsigned int)(start & 1ull);
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_copy(const MergeSources
 #pragma unroll
     for (int q = 0; q < MERGE_QUADS; q++) {
       const unsigned int p = p0 + (unsigned int)q * stride;
-      got[q] = p < npairs ? pairs[p] : make_ulonglong2(0ull, 0ull);
+      got[q] = (p < npairs && start - odd + 2ull * p + 1ull < readable) ? pairs[p] : make_ulonglong2(0ull, 0ull);
     }
 #pragma unroll
     for (int q = 0; q < MERGE_QUADS; q++) {
@@ -456,12 +457,16 @@ int c3d_k_merge_lists(const MergeSources *src, int nranks, int me, unsigned long
  */
 __global__ void k_work_plan(const WorkExchange ex, const int n, const int me, const float remote_cost, PullPlan *__restrict__ plan,
                             unsigned int *__restrict__ counters, const unsigned int capacity, unsigned long long *__restrict__ overflowed) {
+  /* the counts live on the other ranks: one thread each fetches them, then one thread plans */
+  __shared__ unsigned int s_C[C3D_MAX_RANKS][C3D_MAX_RANKS];
+  if ((int)threadIdx.x < n * n) s_C[threadIdx.x / n][threadIdx.x % n] = ex.nseg[threadIdx.x / n][threadIdx.x % n];
+  __syncthreads();
   if (0 != threadIdx.x || 0 != blockIdx.x) return;
   unsigned int C[C3D_MAX_RANKS][C3D_MAX_RANKS], T[C3D_MAX_RANKS], keep[C3D_MAX_RANKS], room[C3D_MAX_RANKS];
   unsigned int most = 0u;
   for (int o = 0; o < n; o++) T[o] = 0u;
   for (int d = 0; d < n; d++) {
-    for (int o = 0; o < n; o++) { C[d][o] = ex.nseg[d][o]; T[o] += C[d][o]; }
+    for (int o = 0; o < n; o++) { C[d][o] = s_C[d][o]; T[o] += C[d][o]; }
   }
   for (int o = 0; o < n; o++) most = T[o] > most ? T[o] : most;
   float tau = (float)most;
@@ -560,21 +565,25 @@ __global__ void __launch_bounds__(256) k_work_copy(const WorkExchange ex, const 
 
 int c3d_k_work_exchange(const WorkExchange *ex, int nranks, int me, float remote_cost, PullPlan *plan, WorkItem *work, unsigned int *counters,
                         unsigned int capacity, unsigned long long *overflowed, cudaStream_t s) {
-  k_work_plan<<<1, 32, 0, s>>>(*ex, nranks, me, remote_cost, plan, counters, capacity, overflowed);
+  k_work_plan<<<1, 64, 0, s>>>(*ex, nranks, me, remote_cost, plan, counters, capacity, overflowed);
   k_work_copy<<<148 * 2, 256, 0, s>>>(*ex, plan, work, capacity);
   return (int)cudaGetLastError();
 }
 
-__global__ void k_flags_max(const FlagSources src, const int n, unsigned long long *mine) {
-  unsigned long long m = 0ull;
-  for (int r = 0; r < n; r++) {
-    const unsigned long long v = *src.flag[r];
-    m = v > m ? v : m;
+__global__ void k_flags_max(const FlagSources src, const int n, unsigned long long *mine, unsigned long long *loads) {
+  const int r = (int)threadIdx.x;
+  if (r < n) loads[r] = src.flag[r][8];
+  if (0 == r) {
+    unsigned long long m = 0ull;
+    for (int q = 0; q < n; q++) {
+      const unsigned long long v = *src.flag[q];
+      m = v > m ? v : m;
+    }
+    *mine = m;
   }
-  *mine = m;
 }
 
-int c3d_k_flags_max(const FlagSources *src, int nranks, unsigned long long *mine, cudaStream_t s) {
-  k_flags_max<<<1, 1, 0, s>>>(*src, nranks, mine);
+int c3d_k_flags_max(const FlagSources *src, int nranks, unsigned long long *mine, unsigned long long *loads, cudaStream_t s) {
+  k_flags_max<<<1, 32, 0, s>>>(*src, nranks, mine, loads);
   return (int)cudaGetLastError();
 }

@@ -61,6 +61,7 @@ struct MergeSources {
   const unsigned int *hist[C3D_MAX_RANKS];             /* rank s: cubes per (destination, depth bucket) */
   const unsigned long long *seg_start[C3D_MAX_RANKS];  /* rank s: where each destination's segment starts in its outbox */
   const unsigned long long *outbox[C3D_MAX_RANKS];
+  const unsigned long long *out_cap[C3D_MAX_RANKS];    /* rank s: entries its outbox has room for */
 };
 /* the cube lists every rank has addressed to this one -> ONE nearest-first list (bucket-major, source-minor) */
 int c3d_k_merge_lists(const MergeSources *src, int nranks, int me, unsigned long long *merge_base, unsigned long long *list,
@@ -80,8 +81,9 @@ struct PullPlan { unsigned int nchunks, nwork; PullChunk chunk[C3D_PULL_CHUNKS];
 int c3d_k_work_exchange(const WorkExchange *ex, int nranks, int me, float remote_cost, PullPlan *plan, WorkItem *work, unsigned int *counters,
                         unsigned int capacity, unsigned long long *overflowed, cudaStream_t s);
 
-/* flag[0] of every rank -> max into mine */
+/* flag[0] of every rank -> max into mine; flag[8] of every rank (two floats: what its last frame spent drawing / shading)
+   -> loads[r] */
 struct FlagSources { const unsigned long long *flag[C3D_MAX_RANKS]; };
-int c3d_k_flags_max(const FlagSources *src, int nranks, unsigned long long *mine, cudaStream_t s);
+int c3d_k_flags_max(const FlagSources *src, int nranks, unsigned long long *mine, unsigned long long *loads, cudaStream_t s);
 
 #endif /* C3D_PEER_H */

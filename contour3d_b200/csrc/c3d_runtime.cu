@@ -116,6 +116,8 @@ enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_CULLED_TRIS = 3, CNT_SHADE
        CNT_OUT = CNT_SNAP + C3D_MAX_OBJECTS + 1,      /* screen-partitioned frames: entries this rank addressed to the ranks (outbox cursor) */
        CNT_SEG_OVER,                                  /* ... pixels / work items that found no room (sized for the worst case: stays 0) */
        CNT_PEER,                                      /* ... host copy only: a flag barrier timed out */
+       CNT_LOADS,                                     /* ... C3D_MAX_RANKS words: what every rank's previous frame spent drawing / shading (two floats each) */
+       CNT_LOADS_END = CNT_LOADS + C3D_MAX_RANKS - 1,
        CNT_TOTAL };
 #define C3D_HIZ_CUTS_MULTI ""
 #define C3D_HIZ_CUTS_SINGLE ""
@@ -148,6 +150,15 @@ struct c3d_context {
   size_t part_masks_cap;                           /* in records */
   int tile_shift;                                  /* log2 of the screen-tile edge of partitioned frames */
   PullPlan *pull_plan;                             /* device: which shading work this rank pulls (k_work_plan) */
+  /* Screen tiles are dealt out in proportion to `tile_share`: a rank whose cubes win much of the image (the slab facing the
+     camera) has more to shade and gets fewer tiles to draw.  The shares follow the ranks' measured times of earlier frames
+     (published in the exchange arena, gathered at the end of every frame: the same numbers on every rank, so the same table). */
+  double tile_share[C3D_MAX_RANKS];
+  unsigned char *tile_map_dev;
+  std::vector<unsigned char> *tile_map_host;
+  size_t tile_map_w, tile_map_h;
+  int tile_balance;                                /* 0: fixed pattern */
+  float my_loads[2];                               /* my last frame: ms drawing (raster + lines + select), ms shading */
   float shade_share;                               /* relative cost of a pixel shaded by a helper rank (0: no helping) */
   void *table_mem;
   DevTables tab;
@@ -262,6 +273,10 @@ static int context_init(c3d_context *ctx, const int comm_rank, const int comm_si
   {
     const char *env = getenv("CONTOUR3D_TILE_SHIFT");
     ctx->tile_shift = (NULL != env && atoi(env) >= 3 && atoi(env) <= 10) ? atoi(env) : 6;
+    env = getenv("CONTOUR3D_TILE_BALANCE");
+    ctx->tile_balance = (NULL != env && '0' == env[0]) ? 0 : 1;
+    for (int r = 0; r < C3D_MAX_RANKS; r++) ctx->tile_share[r] = 1. / (double)comm_size;
+    ctx->tile_map_host = new std::vector<unsigned char>();
   }
   if (comm_size > 1) {
     if (NULL == nccl_id128) return c3d_error("c3d_context_create: %d ranks need the shared 128-byte id (c3d_nccl_unique_id)", comm_size);
@@ -331,7 +346,8 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
   release_exchange(ctx);
-  cudaFree(ctx->merge_base); cudaFree(ctx->part_cursors); cudaFree(ctx->part_masks); cudaFree(ctx->pull_plan);
+  cudaFree(ctx->merge_base); cudaFree(ctx->part_cursors); cudaFree(ctx->part_masks); cudaFree(ctx->pull_plan); cudaFree(ctx->tile_map_dev);
+  delete ctx->tile_map_host;
   c3d_peer_destroy(&ctx->peer);
   cudaFree(ctx->table_mem);
   cudaFree(ctx->shade.work); cudaFree(ctx->shade.counters); cudaFree(ctx->shade.pix); cudaFree(ctx->shade.table); cudaFree(ctx->shade.vlist); cudaFree(ctx->shade.vn);
@@ -1037,6 +1053,60 @@ static size_t own_tiles(const int nranks, const int r, const int tiles_x, const 
   return n;
 }
 
+#define C3D_SHARE_CAP 1.75
+
+/* the tile -> rank table for the current shares: tiles are visited in a scattered order (a stride coprime to their number) and
+   each goes to the rank that is furthest behind its share, so every rank's tiles are spread over the whole screen */
+static void tile_map_build(const double *share, const int n, const int tiles_x, const int tiles_y, std::vector<unsigned char> &map) {
+  const long long nt = (long long)tiles_x * tiles_y;
+  map.assign((size_t)nt, 0);
+  long long stride = (long long)((double)nt * 0.6180339887498949) | 1ll;
+  auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+  while (stride > 1 && 1 != gcd(stride, nt)) stride += 2;
+  if (stride >= nt) stride = 1;
+  double credit[C3D_MAX_RANKS] = {0.};
+  for (long long u = 0; u < nt; u++) {
+    const long long t = (u * stride) % nt;
+    int best = 0;
+    for (int r = 0; r < n; r++) {
+      credit[r] += share[r];
+      if (credit[r] > credit[best]) best = r;
+    }
+    credit[best] -= 1.;
+    map[(size_t)t] = (unsigned char)best;
+  }
+}
+
+/* New shares from what every rank's frame spent drawing (d_r, proportional to its share of the tiles) and shading (h_r, given by
+   whose cubes win the image -- not by the tiles): the level L with  D s_r + h_r = L,  sum s_r = 1,  D = sum d_r.  Damped, clamped. */
+static bool tile_shares_update(c3d_context *ctx, const unsigned long long *gathered) {
+  const int n = ctx->size;
+  double d[C3D_MAX_RANKS], h[C3D_MAX_RANKS], D = 0., H = 0.;
+  for (int r = 0; r < n; r++) {
+    float two[2];
+    memcpy(two, &gathered[r], sizeof(two));
+    if (!(two[0] > 0.f) || !(two[1] >= 0.f) || !(two[0] < 1.e6f) || !(two[1] < 1.e6f)) return false;     /* somebody has no measurement yet */
+    d[r] = two[0]; h[r] = two[1];
+    D += d[r]; H += h[r];
+  }
+  const double level = (D + H) / (double)n;
+  double want[C3D_MAX_RANKS], sum = 0., worst = 0.;
+  for (int r = 0; r < n; r++) {
+    double s = (level - h[r]) / D;
+    s = 0.5 * ctx->tile_share[r] + 0.5 * s;
+    s = std::min(std::max(s, 0.25 / (double)n), C3D_SHARE_CAP / (double)n);
+    want[r] = s;
+    sum += s;
+  }
+  for (int r = 0; r < n; r++) {
+    want[r] /= sum;
+    worst = std::max(worst, fabs(want[r] - ctx->tile_share[r]) * (double)n);
+  }
+  if (worst < 0.03) return false;                    /* within 3 % of an even share: leave the table alone */
+  for (int r = 0; r < n; r++) ctx->tile_share[r] = want[r];
+  return true;
+}
+
 /* collective: (re)creates this rank's exchange arena and maps everybody's */
 static int ensure_exchange(c3d_context *ctx, const size_t w, const size_t h, const size_t out_cap) {
   Exchange &x = ctx->xa;
@@ -1048,6 +1118,9 @@ static int ensure_exchange(c3d_context *ctx, const size_t w, const size_t h, con
   const int tiles_x = (int)((w + ((size_t)1 << ctx->tile_shift) - 1) >> ctx->tile_shift), tiles_y = (int)((h + ((size_t)1 << ctx->tile_shift) - 1) >> ctx->tile_shift);
   size_t most = 0;
   for (int r = 0; r < n; r++) most = std::max(most, own_tiles(n, r, tiles_x, tiles_y));
+  /* the shares move with the load (tile_shares_update): at most C3D_SHARE_CAP times the even share */
+  most = std::max(most, (size_t)(C3D_SHARE_CAP * (double)tiles_x * (double)tiles_y / (double)n) + 2);
+  most = std::min(most, (size_t)tiles_x * (size_t)tiles_y);
   x.nranks = n;
   x.width = w; x.height = h; x.npix = w * h;
   x.seg_cap = most << (2 * ctx->tile_shift);          /* every pixel of my tiles may be won by cubes of ONE rank */
@@ -1064,7 +1137,11 @@ static int ensure_exchange(c3d_context *ctx, const size_t w, const size_t h, con
   void *base = NULL;
   const cudaError_t err = cudaMalloc(&base, x.bytes);
   if (cudaSuccess != err) { cudaGetLastError(); base = NULL; c3d_error("failed to allocate %zu bytes for the ranks' exchange buffers: %s", x.bytes, cudaGetErrorString(err)); }
-  if (NULL != base) cudaMemset(base, 0, x.off_hist);
+  if (NULL != base) {
+    cudaMemset(base, 0, x.off_hist);
+    const unsigned long long cap = (unsigned long long)x.out_cap;       /* readers of my outbox stop here (flags word 9) */
+    cudaMemcpy((char *)base + x.off_flags + 72, &cap, sizeof(cap), cudaMemcpyHostToDevice);
+  }
   if (0 != c3d_peer_share(&ctx->peer, base, x.peer)) {
     if (NULL != base) cudaFree(base);
     memset(&x, 0, sizeof(x));
@@ -1109,6 +1186,11 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   CUDA_OK(cudaEventRecord(ctx->ev[EV_START], s));
   mark();
   /* halos */
+  if (part && NULL != ctx->xa.base) {
+    /* what my previous frame spent drawing / shading, where the others can read it (gathered at the end of this frame) */
+    memcpy(ctx->counts_host + CNT_LOADS, ctx->my_loads, sizeof(ctx->my_loads));
+    CUDA_OK(cudaMemcpyAsync(ctx->xa.base + ctx->xa.off_flags + 64, ctx->counts_host + CNT_LOADS, 8, cudaMemcpyHostToDevice, s));
+  }
   if (part) { LAUNCH_OK(c3d_peer_barrier(peer, s)); launches += 1; }    /* every rank's arrays are complete; last frame's buffers are free */
   mark();                                                               /* detail[0]: barrier at the start */
   for (size_t n = 0; n < nc; n++) {
@@ -1148,6 +1230,21 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     q.tiles_y = (int)((scene->height + ((size_t)1 << q.tile_shift) - 1) >> q.tile_shift);
     q.recip = 0xffffffffu / (unsigned int)q.nranks + 1u;
     q.py = q.pz = 1;
+    q.tile_map = NULL;
+    if (ctx->tile_balance) {
+      const size_t nt = (size_t)q.tiles_x * (size_t)q.tiles_y;
+      if (ctx->tile_map_w != scene->width || ctx->tile_map_h != scene->height || ctx->tile_map_host->size() != nt) {
+        /* new screen: even shares again (every rank gets here in the same frame) */
+        for (int r = 0; r < ctx->size; r++) ctx->tile_share[r] = 1. / (double)ctx->size;
+        tile_map_build(ctx->tile_share, ctx->size, q.tiles_x, q.tiles_y, *ctx->tile_map_host);
+        cudaFree(ctx->tile_map_dev);
+        ctx->tile_map_dev = NULL;
+        CUDA_OK(cudaMalloc(&ctx->tile_map_dev, nt));
+        CUDA_OK(cudaMemcpyAsync(ctx->tile_map_dev, ctx->tile_map_host->data(), nt, cudaMemcpyHostToDevice, s));
+        ctx->tile_map_w = scene->width; ctx->tile_map_h = scene->height;
+      }
+      q.tile_map = ctx->tile_map_dev;
+    }
     if (nc > 0) {
       /* which rank holds which block: told by the ranks themselves when the field was created (any Cartesian numbering) */
       const c3d_field *f = contours[0].field;
@@ -1329,6 +1426,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
       ms.hist[r] = (const unsigned int *)(pb + xa.off_hist);
       ms.seg_start[r] = (const unsigned long long *)(pb + xa.off_seg_start);
       ms.outbox[r] = (const unsigned long long *)(pb + xa.off_out);
+      ms.out_cap[r] = (const unsigned long long *)(pb + xa.off_flags + 72);
     }
     LAUNCH_OK(c3d_k_merge_lists(&ms, ctx->size, ctx->rank, ctx->merge_base, ctx->list, ctx->counts_dev + CNT_LIST, ctx->list_cap, s));
     launches += 3;
@@ -1397,7 +1495,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     FlagSources fs;
     memset(&fs, 0, sizeof(fs));
     for (int r = 0; r < ctx->size; r++) fs.flag[r] = (const unsigned long long *)((const char *)xa.peer[r] + xa.off_flags);
-    LAUNCH_OK(c3d_k_flags_max(&fs, ctx->size, ctx->counts_dev + CNT_OVERFLOW, s));
+    LAUNCH_OK(c3d_k_flags_max(&fs, ctx->size, ctx->counts_dev + CNT_OVERFLOW, ctx->counts_dev + CNT_LOADS, s));
     launches += 3;
     CUDA_OK(cudaEventRecord(ctx->ev[EV_REDUCE1], s));
     mark();                                                             /* detail[10]: barrier at the end (+ overflow agreement) */
@@ -1508,6 +1606,16 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   t->launches = launches;
   t->nsweeps = nsweeps;
   t->exchange_mode = (uint32_t)(ctx->size < 2 ? 0 : (part ? 2 : 1));
+  if (part) {
+    ctx->my_loads[0] = t->raster + t->lines + t->resolve;
+    ctx->my_loads[1] = t->shade;
+    /* every rank holds the same gathered numbers, so every rank changes the table in the same frame, or none does */
+    if (ctx->tile_balance && nc > 0 && tile_shares_update(ctx, ctx->counts_host + CNT_LOADS)) {
+      tile_map_build(ctx->tile_share, ctx->size, fp.part.tiles_x, fp.part.tiles_y, *ctx->tile_map_host);
+      CUDA_OK(cudaMemcpyAsync(ctx->tile_map_dev, ctx->tile_map_host->data(), ctx->tile_map_host->size(), cudaMemcpyHostToDevice, s));
+    }
+    for (int r = 0; r < ctx->size && r < 8; r++) t->tile_share[r] = (float)ctx->tile_share[r];
+  }
   for (int d = 0; d + 1 < ctx->ndetail && d < 16; d++) cudaEventElapsedTime(&t->detail[d], ctx->ev_detail[d], ctx->ev_detail[d + 1]);
   t->list_entries = ctx->counts_host[CNT_LIST];
   t->culled_cubes = ctx->counts_host[CNT_CULLED];

@@ -109,6 +109,7 @@ typedef struct {
   float detail[16];              /* mode 2, ms: [0] barrier at the start, [1] halo pull, [2] staging + clear + sweeps, [3] cubes -> outboxes,
                                     [4] barrier, [5] pull + merge of the lists, [6] raster + lines + select, [7] barrier, [8] pull of the
                                     shading work, [9] shading, [10] barrier at the end */
+  float tile_share[8];           /* mode 2: fraction of the screen tiles each rank draws (follows the ranks' measured loads) */
 } c3d_timings_t;
 
 /* ---- life cycle ---- */
