@@ -20,6 +20,11 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/uio.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include "contour3d_b200.h"
 #include "c3d_internal.h"
 #include "c3d_peer.h"
@@ -159,6 +164,14 @@ struct c3d_context {
   size_t tile_map_w, tile_map_h;
   int tile_balance;                                /* 0: fixed pattern */
   float my_loads[2];                               /* my last frame: ms drawing (raster + lines + select), ms shading */
+  /* The PPM of the previous call, kept mapped and registered with the driver: a solver writes the same name every output
+     step, and the packed image can then travel from the device straight into the file's pages (RAM-backed file systems
+     and the page cache alike) -- no staging copy, no write().  Dropped as soon as name, size or inode differ. */
+  char *out_path;
+  unsigned char *out_map;
+  size_t out_len;
+  unsigned long long out_ino, out_dev;
+  bool out_registered;
   float shade_share;                               /* relative cost of a pixel shaded by a helper rank (0: no helping) */
   void *table_mem;
   DevTables tab;
@@ -273,8 +286,11 @@ static int context_init(c3d_context *ctx, const int comm_rank, const int comm_si
   {
     const char *env = getenv("CONTOUR3D_TILE_SHIFT");
     ctx->tile_shift = (NULL != env && atoi(env) >= 3 && atoi(env) <= 10) ? atoi(env) : 6;
+    /* Tile shares that follow the ranks' measured loads: built and measured (the slab facing the camera ends up with half the
+       tiles of the others), but the frame did not get shorter -- the shading of a rank's cubes can only start when EVERY rank
+       has resolved its tiles, so the stages are balanced one by one, not as a sum.  Off unless asked for. */
     env = getenv("CONTOUR3D_TILE_BALANCE");
-    ctx->tile_balance = (NULL != env && '0' == env[0]) ? 0 : 1;
+    ctx->tile_balance = (NULL != env && '1' == env[0]) ? 1 : 0;
     for (int r = 0; r < C3D_MAX_RANKS; r++) ctx->tile_share[r] = 1. / (double)comm_size;
     ctx->tile_map_host = new std::vector<unsigned char>();
   }
@@ -286,10 +302,10 @@ static int context_init(c3d_context *ctx, const int comm_rank, const int comm_si
       CUDA_OK(cudaMalloc(&ctx->merge_base, (size_t)C3D_PART_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
       CUDA_OK(cudaMalloc(&ctx->part_cursors, (size_t)C3D_PART_BUCKETS * C3D_MAX_RANKS * sizeof(unsigned long long)));
       CUDA_OK(cudaMalloc(&ctx->pull_plan, sizeof(PullPlan)));
-      /* what shading a pixel costs a helper (reading the owner's array through peer memory) relative to the owner itself;
+      /* what shading a pixel costs a helper (reading the owner's array through peer memory) relative to the owner itself (measured at 8 ranks: 8 gives the shortest frame);
          0 = no helping: every rank shades exactly the pixels its own cubes won */
       const char *env = getenv("CONTOUR3D_SHADE_REMOTE_COST");
-      ctx->shade_share = (NULL != env && '\0' != *env) ? (float)atof(env) : 5.f;
+      ctx->shade_share = (NULL != env && '\0' != *env) ? (float)atof(env) : 8.f;
       if (!(ctx->shade_share >= 1.f)) ctx->shade_share = 0.f;
     }
     /* 2. NCCL communicator: frames with coordinate converters and nodes without peer access reduce whole images through it.
@@ -332,6 +348,8 @@ extern "C" int c3d_context_create(c3d_context_t **out, int device, int comm_rank
   return 0;
 }
 
+static void release_output_map(c3d_context *ctx);
+
 static void release_exchange(c3d_context *ctx) {
   if (NULL != ctx->xa.base) {
     c3d_peer_unshare(&ctx->peer, ctx->xa.peer);
@@ -346,6 +364,7 @@ extern "C" int c3d_context_destroy(c3d_context_t *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->has_comm) g_nccl.CommDestroy(ctx->comm);
   release_exchange(ctx);
+  release_output_map(ctx);
   cudaFree(ctx->merge_base); cudaFree(ctx->part_cursors); cudaFree(ctx->part_masks); cudaFree(ctx->pull_plan); cudaFree(ctx->tile_map_dev);
   delete ctx->tile_map_host;
   c3d_peer_destroy(&ctx->peer);
@@ -1164,6 +1183,94 @@ static bool frame_can_partition(const c3d_context *ctx, const size_t nc, const c
   return true;
 }
 
+static void release_output_map(c3d_context *ctx) {
+  if (NULL != ctx->out_map) {
+    if (ctx->out_registered) cudaHostUnregister(ctx->out_map);
+    munmap(ctx->out_map, ctx->out_len);
+  }
+  free(ctx->out_path);
+  ctx->out_path = NULL;
+  ctx->out_map = NULL;
+  ctx->out_len = 0;
+  ctx->out_registered = false;
+  cudaGetLastError();
+}
+
+/* maps `fname` at its final length (header + payload) for direct device-to-file copies; false: use write_ppm() */
+static bool acquire_output_map(c3d_context *ctx, const char *fname, const char *header, const size_t hlen, const size_t bytes) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char *env = getenv("CONTOUR3D_MAP_OUTPUT");
+    enabled = (NULL != env && '0' == env[0]) ? 0 : 1;
+  }
+  if (!enabled) return false;
+  const size_t total = hlen + bytes;
+  struct stat st;
+  if (NULL != ctx->out_map && NULL != ctx->out_path && 0 == strcmp(ctx->out_path, fname) && ctx->out_len == total && 0 == stat(fname, &st)
+      && (unsigned long long)st.st_ino == ctx->out_ino && (unsigned long long)st.st_dev == ctx->out_dev && (size_t)st.st_size == total) {
+    return true;                                    /* the same file as last time: header and length are already in place */
+  }
+  release_output_map(ctx);
+  const int fd = open(fname, O_RDWR | O_CREAT, 0644);
+  if (fd < 0) return false;                         /* write_ppm() reports the error */
+  bool ok = 0 == ftruncate(fd, (off_t)total) && 0 == fstat(fd, &st) && S_ISREG(st.st_mode);
+  void *map = MAP_FAILED;
+  if (ok) map = mmap(NULL, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (!ok || MAP_FAILED == map) return false;
+  if (cudaSuccess != cudaHostRegister(map, total, cudaHostRegisterDefault)) {
+    cudaGetLastError();
+    munmap(map, total);
+    enabled = 0;                                    /* this file system's pages cannot be pinned: do not try again */
+    return false;
+  }
+  memcpy(map, header, hlen);
+  ctx->out_path = strdup(fname);
+  ctx->out_map = (unsigned char *)map;
+  ctx->out_len = total;
+  ctx->out_ino = (unsigned long long)st.st_ino;
+  ctx->out_dev = (unsigned long long)st.st_dev;
+  ctx->out_registered = true;
+  return NULL != ctx->out_path;
+}
+
+static int write_ppm(const char *fname, const size_t width, const size_t height, const unsigned char *rgb, const size_t bytes) {
+  errno = 0;
+  const int fd = open(fname, O_WRONLY | O_CREAT, 0644);
+  if (fd < 0) return c3d_error("%s: %s", fname, strerror(errno));
+  char header[64];
+  const int hlen = snprintf(header, sizeof(header), "P6\n%zu %zu\n255\n", width, height);
+  struct iovec io[2];
+  io[0].iov_base = header; io[0].iov_len = (size_t)hlen;
+  io[1].iov_base = const_cast<unsigned char *>(rgb); io[1].iov_len = bytes;
+  size_t done = 0;
+  const size_t total = (size_t)hlen + bytes;
+  while (done < total) {
+    /* writev may stop short: continue where it stopped */
+    struct iovec rest[2];
+    int nrest = 0;
+    size_t skip = done;
+    for (int q = 0; q < 2; q++) {
+      if (skip >= io[q].iov_len) { skip -= io[q].iov_len; continue; }
+      rest[nrest].iov_base = (char *)io[q].iov_base + skip;
+      rest[nrest].iov_len = io[q].iov_len - skip;
+      skip = 0;
+      nrest++;
+    }
+    const ssize_t w = writev(fd, rest, nrest);
+    if (w <= 0) {
+      if (w < 0 && EINTR == errno) continue;
+      const int err = errno;
+      close(fd);
+      return c3d_error("%s: write failed after %zu of %zu bytes (%s)", fname, done, total, strerror(err));
+    }
+    done += (size_t)w;
+  }
+  if (0 != ftruncate(fd, (off_t)total)) { const int err = errno; close(fd); return c3d_error("%s: %s", fname, strerror(err)); }
+  if (0 != close(fd)) return c3d_error("%s: %s", fname, strerror(errno));
+  return 0;
+}
+
 static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t nc, const c3d_contour_t *contours,
                       const size_t nl, const c3d_line_t *lines, uint8_t *host_rgb, const char *fname, bool *overflow) {
   *overflow = false;
@@ -1531,7 +1638,14 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   }
   CUDA_OK(cudaEventRecord(ctx->ev[EV_PACK], s));
   const bool want_host = (0 == ctx->rank) && (NULL != host_rgb || NULL != fname);
-  if (want_host) CUDA_OK(cudaMemcpyAsync(ctx->ppm_host, ctx->ppm_dev, 3 * npix, cudaMemcpyDeviceToHost, s));
+  bool mapped_out = false;
+  if (want_host && NULL != fname && NULL == host_rgb) {
+    char header[64];
+    const int hlen = snprintf(header, sizeof(header), "P6\n%zu %zu\n255\n", scene->width, scene->height);
+    mapped_out = acquire_output_map(ctx, fname, header, (size_t)hlen, 3 * npix);
+    if (mapped_out) CUDA_OK(cudaMemcpyAsync(ctx->out_map + hlen, ctx->ppm_dev, 3 * npix, cudaMemcpyDeviceToHost, s));
+  }
+  if (want_host && !mapped_out) CUDA_OK(cudaMemcpyAsync(ctx->ppm_host, ctx->ppm_dev, 3 * npix, cudaMemcpyDeviceToHost, s));
   if (ctx->size > 1 && !part) {
     /* the frame is redone when a work buffer overflowed: all ranks must agree, the frame is full of collectives */
     LAUNCH_OK(c3d_k_overflow_flag(ctx->counts_dev + CNT_REC, ctx->rec_cap, ctx->counts_dev + CNT_LIST, ctx->list_cap, NULL, 0, NULL, ctx->counts_dev + CNT_OVERFLOW, s));
@@ -1630,17 +1744,13 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     t->active_cubes[n] = ctx->counts_host[CNT_OBJ + n];
     if (snap_of[n] >= 0) t->active_cubes[n] += ctx->counts_host[CNT_SNAP + 1 + snap_of[n]] - ctx->counts_host[CNT_SNAP + snap_of[n]];
   }
-  if (want_host) {
+  if (want_host && !mapped_out) {
     if (NULL != host_rgb) memcpy(host_rgb, ctx->ppm_host, 3 * npix);
     if (NULL != fname) {
-      /* binary P6, output.c:125-146 */
-      errno = 0;
-      FILE *fp = fopen(fname, "w");
-      if (NULL == fp) return c3d_error("%s: %s", fname, strerror(errno));
-      fprintf(fp, "P6\n%zu %zu\n255\n", scene->width, scene->height);
-      const size_t wrote = fwrite(ctx->ppm_host, 3, npix, fp);
-      fclose(fp);
-      if (wrote != npix) return c3d_error("fwrite failed (%zu expected, %zu returned)", npix, wrote);
+      /* binary P6, output.c:125-146.  The file is complete when this returns, like the reference's; it is written in place
+         (no O_TRUNC: a solver writes the same name every output step, and on a RAM-backed file system giving all the pages
+         back and faulting them in again costs more than the copy) and cut to its length afterwards. */
+      if (0 != write_ppm(fname, scene->width, scene->height, ctx->ppm_host, 3 * npix)) return 1;
     }
   }
   return 0;
