@@ -215,6 +215,34 @@ __device__ __forceinline__ V3 face_term_of(const FieldView &f, const unsigned in
   return v_mul(area, fn);
 }
 
+/* the same with the cube's eight corner values already at hand (k_shade_normals keeps what the corner-bit test of a slot
+   has loaded: 6 shared-memory reads instead of 6 global ones with their 64-bit address arithmetic); identity converter only */
+__device__ __forceinline__ V3 face_term_held(const FieldView &f, const float *__restrict__ val, const unsigned int pairs, const long long i,
+                                             const long long j, const long long k) {
+  const double x0 = __ldg(f.g[0] + i), x1 = __ldg(f.g[0] + i + 1);
+  const double y0 = __ldg(f.g[1] + j), y1 = __ldg(f.g[1] + j + 1);
+  const double z0 = __ldg(f.g[2] + k), z1 = __ldg(f.g[2] + k + 1);
+  V3 v[3];
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const unsigned int tail = (pairs >> (6 * m)) & 7u, head = (pairs >> (6 * m + 3)) & 7u;
+    const double v0 = (double)val[tail], v1 = (double)val[head];
+    const V3 p0 = V3{(tail & 1u) ? x1 : x0, (tail & 2u) ? y1 : y0, (tail & 4u) ? z1 : z0};
+    const double dv = r_sub(v1, v0);
+    if (fabs(dv) < 1.e-8) {
+      v[m] = p0;
+    } else {
+      const double factor = r_div(r_sub(f.thr, v0), dv);
+      const V3 p1 = V3{(head & 1u) ? x1 : x0, (head & 2u) ? y1 : y0, (head & 4u) ? z1 : z0};
+      v[m] = v_add(p0, v_mul(factor, v_sub(p1, p0)));
+    }
+  }
+  V3 fn;
+  double area;
+  face_normal(v, fn, area);
+  return v_mul(area, fn);
+}
+
 /* object `obj` as rank `owner` holds it: this rank's own array, or (a partitioned frame's shading helper) the owner's
    through peer memory */
 template <bool HELP>
@@ -438,6 +466,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
                                                               double *__restrict__ vn, const unsigned int vn_cap, unsigned long long *__restrict__ overflowed) {
   __shared__ ShadeSlot s_slot[SH_SLOTS];
   __shared__ unsigned int s_first[SH_SLOTS + 1];          /* first item of each slot */
+  __shared__ float s_val[SH_SLOTS][8];                    /* fp32 arrays: the corner values the slot's corner-bit test has loaded */
   __shared__ unsigned short s_item[SH_ITEMS];             /* slot << 4 | triangle */
   __shared__ double s_term[SH_ITEMS][3];
   __shared__ unsigned int s_warp_total[SH_THREADS / 32];
@@ -464,7 +493,23 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
         slot.owner = (unsigned char)owner;
         if (edge_neighbour(e, c, di, dj, dk, local)) {
           const long long ii = (long long)(key & 65535ull) + di, jj = (long long)((key >> 16) & 65535ull) + dj, kk = (long long)((key >> 32) & 65535ull) + dk;
-          const unsigned int code = cube_code(owner_view<HELP>(p, owner, obj), ii, jj, kk);
+          const FieldView &f = owner_view<HELP>(p, owner, obj);
+          unsigned int code;
+          if (4 == f.elem_bytes) {
+            /* the eight values once: corner bits now, cut edges of the touching triangles later */
+            const float *at8 = static_cast<const float *>(f.data) + (kk * f.sz + jj * f.sy + ii);
+            float c8[8];
+#pragma unroll
+            for (int n = 0; n < 8; n++) c8[n] = __ldg(at8 + ((n & 1) + ((n >> 1) & 1) * f.sy + (n >> 2) * f.sz));
+            code = 0u;
+#pragma unroll
+            for (int n = 0; n < 8; n++) {
+              code |= (unsigned int)(f.thr < (double)c8[n]) << n;
+              s_val[q][n] = c8[n];
+            }
+          } else {
+            code = cube_code(f, ii, jj, kk);
+          }
           slot.i = (unsigned short)ii; slot.j = (unsigned short)jj; slot.k = (unsigned short)kk;
           slot.code = (unsigned char)code;
           slot.touch = __ldg(p.tab.touch + code * 19u + local);
@@ -512,7 +557,10 @@ __global__ void __launch_bounds__(SH_THREADS) k_shade_normals(const __grid_const
       for (unsigned int it = tid; it < total_items; it += SH_THREADS) {
         const unsigned int q = s_item[it] >> 4, s = s_item[it] & 15u;
         const ShadeSlot slot = s_slot[q];
-        const V3 term = face_term(p, owner_view<HELP>(p, slot.owner, slot.obj), slot.i, slot.j, slot.k, slot.code, s);
+        const FieldView &f = owner_view<HELP>(p, slot.owner, slot.obj);
+        const V3 term = (4 == f.elem_bytes && nullptr == f.map)
+                            ? face_term_held(f, s_val[q], __ldg(p.tab.pairs + slot.code * C3D_MAX_TRIS + s), slot.i, slot.j, slot.k)
+                            : face_term(p, f, slot.i, slot.j, slot.k, slot.code, s);
         s_term[it][0] = term.x; s_term[it][1] = term.y; s_term[it][2] = term.z;
       }
       __syncthreads();
