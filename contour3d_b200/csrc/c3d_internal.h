@@ -184,7 +184,8 @@ struct ShadeScratch {
   unsigned int *counters;        /* [0] listed pixels, [1] distinct vertices, [2] pixels of the first pass, [3] vertices of the first pass */
   void *pix;                     /* per listed pixel: weights, cube, vertex slots: npix x C3D_SHADE_PIX_BYTES */
   unsigned long long *table;     /* open-addressing set of the vertices (global cube edges) the listed pixels reference */
-  unsigned int table_mask;       /* slots - 1 (a power of two) */
+  unsigned int table_mask;       /* slots in use this frame - 1 (a power of two, at most table_slots) */
+  unsigned int table_slots;      /* slots allocated */
   unsigned int *vlist;           /* occupied slots in order of first insertion: min(slots, 3 npix) words */
   double *vn;                    /* unit normal of listed vertex v: 3 doubles each, vn_cap vertices */
   unsigned int vn_cap;

@@ -125,6 +125,33 @@ int c3d_positions_probe(c3d_converter_fn convert, void *user, const double *cons
       }
     }
   }
+  /* The lines above see the whole range of every direction but only a few base points.  A function that is the identity
+     (or lower-dimensional) except in some region away from those lines would be taken for what it is not: the identity
+     verdict is therefore checked on scattered points as well -- at least one in every z plane -- and a component caught
+     differing is tabulated in full.  This is sampling, not proof; CONTOUR3D_CONVERTER_FULL_TABLES=1 skips all guessing
+     and tabulates every component over all three directions (24 bytes per grid point). */
+  {
+    const char *env = getenv("CONTOUR3D_CONVERTER_FULL_TABLES");
+    if (NULL != env && '\0' != *env && '0' != *env) {
+      *identity = 0;
+      for (int c = 0; c < 3; c++) dep[c][0] = dep[c][1] = dep[c][2] = 1;
+    }
+  }
+  if (*identity) {
+    uint64_t vr = rng ^ 0x5DEECE66Dull;
+    const size_t nscatter = (size_t)VERIFY_SAMPLES + n[2];
+    for (size_t q = 0; q < nscatter; q++) {
+      const size_t idx[3] = {(size_t)(next_random(&vr) % n[0]), (size_t)(next_random(&vr) % n[1]), q < n[2] ? q : (size_t)(next_random(&vr) % n[2])};
+      double val[3];
+      evaluate(convert, user, g, idx, val);
+      for (int c = 0; c < 3; c++) {
+        if (!same_bits(val[c], g[c][idx[c]])) {
+          *identity = 0;
+          dep[c][0] = dep[c][1] = dep[c][2] = 1;
+        }
+      }
+    }
+  }
   if (*identity) return 0;
   /* 2. tables over the dependent directions, 3. verification on scattered points; a component that fails becomes 3-D */
   size_t bytes_left = max_bytes;

@@ -121,6 +121,7 @@ enum { CNT_LIST = 0, CNT_REC = 1, CNT_CULLED = 2, CNT_CULLED_TRIS = 3, CNT_SHADE
        CNT_OUT = CNT_SNAP + C3D_MAX_OBJECTS + 1,      /* screen-partitioned frames: entries this rank addressed to the ranks (outbox cursor) */
        CNT_SEG_OVER,                                  /* ... pixels / work items that found no room (sized for the worst case: stays 0) */
        CNT_PEER,                                      /* ... host copy only: a flag barrier timed out */
+       CNT_SHADE_ITEMS,                               /* pixels this rank shaded (sizes next frame's vertex table) */
        CNT_LOADS,                                     /* ... C3D_MAX_RANKS words: what every rank's previous frame spent drawing / shading (two floats each) */
        CNT_LOADS_END = CNT_LOADS + C3D_MAX_RANKS - 1,
        CNT_TOTAL };
@@ -151,6 +152,7 @@ struct c3d_context {
   c3d_peer peer;                                   /* device-to-device exchange between the ranks of this node */
   Exchange xa;
   unsigned long long *merge_base, *part_cursors;   /* C3D_PART_BUCKETS x ranks each: merged-list offsets / outbox cursors */
+  unsigned long long shade_items_prev;             /* pixels shaded in the previous frame; 0: unknown */
   unsigned char *part_masks;                       /* 32 bytes per sweep record: which ranks draw each of its cubes */
   size_t part_masks_cap;                           /* in records */
   int tile_shift;                                  /* log2 of the screen-tile edge of partitioned frames */
@@ -986,6 +988,7 @@ static int ensure_canvas(c3d_context *ctx, const size_t w, const size_t h) {
         if (NULL != env && '\0' != *env && (size_t)strtoull(env, NULL, 10) < normals) ctx->shade.vn_cap = (unsigned int)strtoull(env, NULL, 10);
       }
       ctx->shade.table_mask = (unsigned int)(slots - 1);
+      ctx->shade.table_slots = (unsigned int)slots;
     }
     CUDA_OK(cudaMalloc(&ctx->ppm_dev, npix * 3));
     CUDA_OK(cudaMallocHost(&ctx->ppm_host, npix * 3));
@@ -1402,6 +1405,19 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   unsigned int *rgba_out = ctx->rgba;                /* where finished colours go: the writer's image */
   if (part) rgba_out = (unsigned int *)((char *)xa.peer[0] + xa.off_rgba);
   CUDA_OK(cudaMemsetAsync(ctx->counts_dev, 0, CNT_TOTAL * sizeof(unsigned long long), s));
+  {
+    /* The vertex table is cleared every frame: size it by what the previous frame shaded (a rank of a partitioned frame shades a
+       fraction of the screen; three vertices per pixel at most, load below 1/2) instead of by the whole screen.  Too small costs
+       time, never correctness: a vertex that finds no slot is smoothed per pixel (k_shade_blend). */
+    size_t slots = ctx->shade.table_slots;
+    if (ctx->shade_items_prev > 0) {
+      const size_t want = 8 * (size_t)ctx->shade_items_prev + (1u << 16);
+      size_t fit = 1u << 16;
+      while (fit < want && fit < ctx->shade.table_slots) fit <<= 1;
+      slots = std::min<size_t>(fit, ctx->shade.table_slots);
+    }
+    ctx->shade.table_mask = (unsigned int)(slots - 1);
+  }
   if (part) {
     CUDA_OK(cudaMemsetAsync(xa.base + xa.off_nseg, 0, 256, s));
     LAUNCH_OK(c3d_k_clear_part(ctx->canvas, &fp.part, cam.w, cam.h, ctx->sm_count, s));
@@ -1652,6 +1668,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
     NCCL_OK(g_nccl.AllReduce(ctx->counts_dev + CNT_OVERFLOW, ctx->counts_dev + CNT_OVERFLOW, 1, ncclUint64, ncclMax, ctx->comm, s));
     launches += 1;
   }
+  CUDA_OK(cudaMemcpyAsync(ctx->counts_dev + CNT_SHADE_ITEMS, ctx->shade.counters, sizeof(unsigned int), cudaMemcpyDeviceToDevice, s));
   CUDA_OK(cudaMemcpyAsync(ctx->counts_host, ctx->counts_dev, CNT_TOTAL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   if (part) CUDA_OK(cudaMemcpyAsync(ctx->counts_host + CNT_PEER, peer->status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaEventRecord(ctx->ev[EV_DOWNLOAD], s));
@@ -1720,6 +1737,7 @@ static int frame_once(c3d_context *ctx, const c3d_scene_t *scene, const size_t n
   t->launches = launches;
   t->nsweeps = nsweeps;
   t->exchange_mode = (uint32_t)(ctx->size < 2 ? 0 : (part ? 2 : 1));
+  ctx->shade_items_prev = ctx->counts_host[CNT_SHADE_ITEMS] & 0xffffffffull;
   if (part) {
     ctx->my_loads[0] = t->raster + t->lines + t->resolve;
     ctx->my_loads[1] = t->shade;

@@ -256,3 +256,27 @@ def test_bench_workloads_follow_baseline_configs():
         w = bench.workload(argparse.Namespace(config=c, size=0, image=None, isovalues=None))
         assert (w["size"], w["image"], len(w["fields"]), len(w["contours"])) == (size, image, nfields, ncontours)
         assert all(v == float(np.float32(v)) for _, v in w["contours"])
+
+
+def test_converter_probe_catches_a_function_that_is_the_identity_almost_everywhere():
+    """the identity except inside a box away from the domain's corners and centre lines: whichever of the probe's stages
+    notices (sample lines, the scattered check of the identity verdict, the verification of the tables), the tables it
+    returns must reproduce the function inside and outside the box"""
+    n = 40
+    g = scenes.uniform_grids(n, n, n)
+    ylo, yhi, zlo, zhi = g[1][3], g[1][12], g[2][3], g[2][12]
+
+    def conv(x, y, z):
+        inside = ylo <= y <= yhi and zlo <= z <= zhi
+        return (x + (0.25 if inside else 0.0), y, z)
+
+    identity, tables, strides = api.positions_probe(conv, g, (0, 0, 0), (n, n, n))
+    assert not identity
+
+    def lookup(c, i, j, k):
+        return tables[c][i * strides[c][0] + j * strides[c][1] + k * strides[c][2]]
+
+    rng = np.random.default_rng(1)
+    for i, j, k in rng.integers(0, n, size=(400, 3)):
+        want = conv(g[0][i], g[1][j], g[2][k])
+        assert all(lookup(c, i, j, k) == want[c] for c in range(3)), (i, j, k)
