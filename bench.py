@@ -140,6 +140,26 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+def nvlink_bytes(index):
+    """cumulative NVLink payload bytes (tx, rx) of GPU `index`, summed over its links: the driver's per-link throughput counters
+    (`nvidia-smi nvlink -gt d`, KiB); None when the tool or the counters are not available"""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    tx = rx = 0
+    seen = False
+    for line in out.splitlines():
+        parts = line.replace(",", " ").split()
+        if "Tx:" in parts and "KiB" in parts:
+            tx += int(parts[parts.index("Tx:") + 1]) * 1024
+            seen = True
+        if "Rx:" in parts and "KiB" in parts:
+            rx += int(parts[parts.index("Rx:") + 1]) * 1024
+            seen = True
+    return (tx, rx) if seen else None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -330,6 +350,7 @@ def ours(args):
         for _ in range(args.warmup):
             frame(want_rgb=False)
         barrier()
+        nvl0 = nvlink_bytes(local) if world > 1 else None
         clocks.mark_start()
         start.record(stream)
         for _ in range(args.steps):
@@ -344,6 +365,7 @@ def ours(args):
         end.record(stream)
         barrier()
         clocks.mark_end()
+        nvl1 = nvlink_bytes(local) if world > 1 else None
         time.sleep(0.05)
     elapsed_ms = start.elapsed_time(end)
     tt = torch.tensor([elapsed_ms], device="cuda")
@@ -371,6 +393,19 @@ def ours(args):
         per_rank = gathered
     voxels = size ** 3 * nct
     value = voxels * args.steps / (elapsed_ms * 1e-3) / 1e9
+    # NVLink traffic of the timed frames by the driver's link counters (every rank reads its own GPU's)
+    nvlink = None
+    if world > 1:
+        mine = None
+        if nvl0 is not None and nvl1 is not None:
+            mine = {"tx_bytes_per_step": (nvl1[0] - nvl0[0]) / args.steps, "rx_bytes_per_step": (nvl1[1] - nvl0[1]) / args.steps}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if all(g is not None for g in gathered):
+            ms = elapsed_ms / args.steps
+            nvlink = {"per_rank": gathered, "source": "nvidia-smi nvlink -gt d (driver link counters, KiB granularity) around the timed frames",
+                      "max_rx_GBps_over_the_frame": max(g["rx_bytes_per_step"] for g in gathered) / (ms * 1e-3) / 1e9,
+                      "total_rx_bytes_per_step": sum(g["rx_bytes_per_step"] for g in gathered)}
 
     # ---- the exchange steps on their own (N > 1) ----
     collectives = None
@@ -449,6 +484,7 @@ def ours(args):
             "stages_ms": {k: v / args.steps for k, v in stage_sum.items()},
             "stages_ms_per_rank": per_rank,
             "collectives": collectives,
+            "nvlink_counters": nvlink,
             "active_cubes": active, "culled_cubes": t["culled_cubes"], "culled_triangles": t["culled_triangles"], "shade_spills": t["shade_spills"],
         }
         print(json.dumps(line))
