@@ -85,14 +85,19 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
+    """SM clock and throttle reasons during the timed region, through NVML in a thread of this process (a looping `nvidia-smi`
+    takes the driver's locks for milliseconds per poll and delays the kernel launches of the rank it runs beside: measured,
+    4 ms per frame on a 4-GPU box); `nvidia-smi` only where the NVML binding is missing."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.thread = index, [], None, None      # samples: (time, sm_mhz, max_mhz, set of reasons)
         self.t0 = self.t1 = None
+        self.stop = threading.Event()
+        self.how = None
 
     def mark_start(self):
         self.t0 = time.time()
@@ -100,44 +105,72 @@ class ClockSampler:
     def mark_end(self):
         self.t1 = time.time()
 
+    def _nvml_loop(self, nv, handle):
+        bits = ((nv.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap"))
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+        while not self.stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                self.samples.append((time.time(), sm, mx, {name for bit, name in bits if mask & bit}))
+            except Exception:      # noqa: BLE001 -- a failed poll is a missing sample, nothing more
+                pass
+            self.stop.wait(0.01)
+
+    def _smi_pump(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                self.samples.append((time.time(), float(parts[0]), float(parts[1]),
+                                     {name for name, flag in zip(self.NAMES, parts[3:7]) if flag.lower().startswith("active")}))
+            except ValueError:
+                continue
+
     def __enter__(self):
+        if self.index is None:          # ranks other than 0 do not sample
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
 
-            def pump():
-                for line in self.proc.stdout:
-                    self.lines.append((time.time(), line))
-
-            self.thread = threading.Thread(target=pump, daemon=True)
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[self.index]) if os.environ.get("CUDA_VISIBLE_DEVICES", "").replace(",", "").isdigit() else self.index)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
             self.thread.start()
+            self.how = "nvml"
+            return self
+        except Exception:      # noqa: BLE001
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._smi_pump, daemon=True)
+            self.thread.start()
+            self.how = "nvidia-smi"
         except OSError:
             self.proc = None
         return self
 
     def __exit__(self, *exc):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
+        if self.thread:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        inside = [l for (ts, l) in self.lines if self.t0 is not None and self.t1 is not None and self.t0 - 0.02 <= ts <= self.t1 + 0.05]
+        inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 - 0.02 <= x[0] <= self.t1 + 0.05]
         window = "timed region" if inside else "warm-up + timed region"
-        for line in (inside or [l for (_, l) in self.lines]):
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx = max(mx, float(parts[1]))
-            except ValueError:
-                continue
-            for name, flag in zip(names, parts[3:7]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
+        use = inside or self.samples
+        sm = [x[1] for x in use]
+        reasons = set()
+        for x in use:
+            reasons |= x[3]
+        mx = max([x[2] for x in use], default=0)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": window,
+                "source": self.how}
 
 
 def nvlink_bytes(index):
@@ -346,7 +379,7 @@ def ours(args):
     detail_sum = [0.0] * 11
     sweep_ms, sweep_bytes = [], []
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:          # nvidia-smi needs ~0.2 s to start: it runs through the warm-up too
+    with ClockSampler(local if rank == 0 else None) as clocks:          # nvidia-smi needs ~0.2 s to start: it runs through the warm-up too
         for _ in range(args.warmup):
             frame(want_rgb=False)
         barrier()

@@ -367,12 +367,21 @@ class Context:
         """contours: list of dict(field=Field, grids=[gx, gy, gz] (global), threshold, color)
         lines: list of dict(edges, nitems, width, color)
         returns the y-flipped image (H, W, 3) uint8 on rank 0 (None elsewhere / when want_rgb is False)."""
+        # a movie loop renders the same objects again and again: the C structures of the previous call are kept and reused
+        # when the very same Python objects come back (identity, not equality: cheap to check, and nothing here is mutated)
+        sig = (id(scene), tuple(sorted(scene.items())) if isinstance(scene, dict) else None,
+               tuple((id(c["field"]), id(c["grids"]), float(c["threshold"]), tuple(c.get("color", (255, 255, 255))), id(c.get("positions"))) for c in contours),
+               tuple((tuple(map(tuple, l["edges"])), int(l["nitems"]), float(l["width"]), tuple(l.get("color", (255, 255, 255))), id(l.get("points"))) for l in lines))
+        cached = getattr(self, "_render_cache", None)
+        if cached is not None and cached[0] == sig:
+            s, carr, larr, keep = cached[1]
+            return self._render_call(s, carr, larr, len(contours), len(lines), want_rgb, fname)
         s = Scene()
         for k in ("camera", "light", "center", "local_x", "local_y"):
             getattr(s, k)[:] = scene[k]
         s.width, s.height = int(scene["width"]), int(scene["height"])
         s.bg[:] = list(scene.get("bg", (0, 0, 0)))
-        keep = []
+        keep = [scene, contours, lines]
         carr = (ContourDesc * max(1, len(contours)))()
         for n, c in enumerate(contours):
             carr[n].field = c["field"].handle
@@ -406,12 +415,16 @@ class Context:
                 pts = np.ascontiguousarray(l["points"], dtype=np.float64).reshape(int(l["nitems"]), 3)
                 keep.append(pts)
                 larr[n].points = pts.ctypes.data_as(C.POINTER(C.c_double))
+        self._render_cache = (sig, (s, carr, larr, keep))
+        return self._render_call(s, carr, larr, len(contours), len(lines), want_rgb, fname)
+
+    def _render_call(self, s, carr, larr, nc, nl, want_rgb, fname):
         out = None
         ptr = None
         if want_rgb and self.rank == 0:
             out = np.empty((s.height, s.width, 3), dtype=np.uint8)
             ptr = out.ctypes.data
-        _check(lib().c3d_frame_render(self.handle, C.byref(s), len(contours), carr, len(lines), larr, ptr,
+        _check(lib().c3d_frame_render(self.handle, C.byref(s), nc, carr, nl, larr, ptr,
                                       fname.encode() if fname else None), "c3d_frame_render")
         return out
 
