@@ -382,8 +382,10 @@ def ours(args):
     with ClockSampler(local if rank == 0 else None) as clocks:          # nvidia-smi needs ~0.2 s to start: it runs through the warm-up too
         for _ in range(args.warmup):
             frame(want_rgb=False)
-        barrier()
+        # (the link counters are read OUTSIDE the barrier-to-barrier region: the tool takes a different time on every rank,
+        # and a rank that enters the timed loop late is waited for by all the others in the first frame)
         nvl0 = nvlink_bytes(local) if world > 1 else None
+        barrier()
         clocks.mark_start()
         start.record(stream)
         for _ in range(args.steps):
