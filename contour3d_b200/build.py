@@ -93,7 +93,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         # `sdecomp` and the MPI_* symbols stay undefined: the embedding program
         # (or libc3d_sdecomp_compat.so) provides them
         _run([nvcc, "-shared", "-o", LIB] + objs + ["-ldl", "-Xlinker", "--allow-shlib-undefined"])
-    if not have_real_mpi():
+    # SimpleDecomp stand-in (the getters contour3d_execute consumes + sdecomp.construct for the demo programs).  Without an MPI
+    # installation it carries the MPI stand-in too; with one it is compiled by mpicc against the real <mpi.h> (it only needs
+    # MPI_Cart_* / MPI_Dims_create), so that c3d_case links either way.  A solver that brings the genuine SimpleDecomp links that instead.
+    if have_real_mpi():
+        srcs = [os.path.join(CSRC, "c3d_sdecomp_compat.c")]
+        if force or _newer(COMPAT, srcs + headers):
+            _run(["mpicc", "-std=gnu11", "-O2", "-Wall", "-Wextra", "-fPIC", "-shared", "-D_GNU_SOURCE"] + inc + ["-o", COMPAT] + srcs)
+    else:
         srcs = [os.path.join(CSRC, "c3d_sdecomp_compat.c"), os.path.join(MINIMPI, "minimpi.c")]
         if force or _newer(COMPAT, srcs + headers):
             _run(["gcc", "-std=gnu11", "-O2", "-Wall", "-Wextra", "-fPIC", "-shared", "-D_GNU_SOURCE"] + inc + mpi_inc
@@ -103,10 +110,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         # same single-precision arithmetic as the kernel: no contraction into fused multiply-adds
         _run(["gcc", "-std=c99", "-O3", "-ffp-contract=off", "-Wall", "-Wextra", "-fPIC", "-shared", "-I", CSRC, "-o", SYNTH, synth_src, "-lpthread", "-lm"])
     src = os.path.join(CSRC, "c3d_case_main.c")
-    if force or _newer(CASE, [src, LIB] + ([COMPAT] if not have_real_mpi() else [])):
-        link = ["-L", PKG, "-lcontour3d_b200", "-Wl,-rpath,$ORIGIN"]
-        if not have_real_mpi():
-            link += ["-lc3d_sdecomp_compat"]
+    if force or _newer(CASE, [src, LIB, COMPAT]):
+        link = ["-L", PKG, "-lcontour3d_b200", "-lc3d_sdecomp_compat", "-Wl,-rpath,$ORIGIN"]
         _run([cc, "-std=c99", "-O3", "-D_POSIX_C_SOURCE=200809L"] + inc + mpi_inc + ["-o", CASE, src] + link + ["-lm"])  # the reference driver's flags (oracle/Makefile): the built-in converters must round alike
     return LIB
 
