@@ -128,17 +128,11 @@ void c3d_peer_unshare(c3d_peer *peer, void *mapped[C3D_MAX_RANKS]) {
   }
 }
 
-int c3d_peer_init(c3d_peer *peer, int rank, int size, const void *id128, int device) {
-  memset(peer, 0, sizeof(*peer));
-  peer->rank = rank;
-  peer->size = size;
-  if (size < 2) return 0;
-  {
-    const char *env = getenv("CONTOUR3D_P2P");
-    if (NULL != env && '0' == env[0]) return 0;                 /* exchange through NCCL only */
-  }
-  if (size > C3D_MAX_RANKS) return 0;                           /* list entries name the source rank in 3 bits */
-  if (NULL == id128) return 0;
+/* Joins the ranks' board: rank 0 creates the shared-memory segment named after the run's id, the others open it; everybody
+   waits until all have arrived, then the name is removed.  0: attached; 1: no board (another node, no /dev/shm, a rank
+   missing): the caller goes on without device-side exchange; 2: the ranks are out of step. */
+static int board_attach(c3d_peer *peer, const void *id128) {
+  const int rank = peer->rank, size = peer->size;
   unsigned long long w[2];
   memcpy(w, id128, sizeof(w));
   char name[64];
@@ -151,7 +145,7 @@ int c3d_peer_init(c3d_peer *peer, int rank, int size, const void *id128, int dev
     if (fd < 0 || 0 != ftruncate(fd, (off_t)sizeof(PeerBoard))) {
       if (fd >= 0) close(fd);
       fprintf(stderr, "[CONTOUR3D] no shared-memory board (%s): ranks exchange through NCCL only\n", strerror(errno));
-      return 0;
+      return 1;
     }
   } else {
     for (;;) {
@@ -161,21 +155,21 @@ int c3d_peer_init(c3d_peer *peer, int rank, int size, const void *id128, int dev
       if (fd >= 0) { close(fd); fd = -1; }
       if (wall_seconds() - t0 > limit) {
         fprintf(stderr, "[CONTOUR3D] rank %d found no shared-memory board within %.0f s (another node?): NCCL only\n", rank, limit);
-        return 0;
+        return 1;
       }
       usleep(200);
     }
   }
   PeerBoard *b = (PeerBoard *)mmap(NULL, sizeof(PeerBoard), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
   close(fd);
-  if (MAP_FAILED == (void *)b) return 0;
+  if (MAP_FAILED == (void *)b) return 1;
   if (0 == rank) {
     memset(b, 0, sizeof(*b));
     b->size = (unsigned int)size;
     __atomic_store_n(&b->magic, BOARD_MAGIC, __ATOMIC_RELEASE);
   } else {
     while (BOARD_MAGIC != __atomic_load_n(&b->magic, __ATOMIC_ACQUIRE)) {
-      if (wall_seconds() - t0 > limit) { munmap(b, sizeof(PeerBoard)); return 0; }
+      if (wall_seconds() - t0 > limit) { munmap(b, sizeof(PeerBoard)); return 1; }
       usleep(100);
     }
   }
@@ -191,12 +185,54 @@ int c3d_peer_init(c3d_peer *peer, int rank, int size, const void *id128, int dev
       munmap(b, sizeof(PeerBoard));
       peer->board = NULL;
       peer->attached = false;
-      return 0;
+      return 1;
     }
     usleep(100);
   }
-  if (0 != board_barrier(peer)) return 1;
+  if (0 != board_barrier(peer)) return 2;
   if (0 == rank) shm_unlink(name);
+  return 0;
+}
+
+/* Host-side self test of the bootstrap (no device needed): every rank joins the board named after id128, contributes
+   `value`, and receives the sum over the ranks of (rank + 1) * value -- three allgathers in a row, so that the generation
+   counting of the board's barrier is exercised.  Collective.  Returns 0, or 1 when the board is not available. */
+extern "C" int c3d_peer_selftest(int rank, int size, const void *id128, unsigned long long value, unsigned long long *sum) {
+  if (NULL == id128 || NULL == sum || size < 2 || size > C3D_MAX_RANKS || rank < 0 || rank >= size) return 1;
+  c3d_peer peer;
+  memset(&peer, 0, sizeof(peer));
+  peer.rank = rank;
+  peer.size = size;
+  if (0 != board_attach(&peer, id128)) return 1;
+  unsigned long long total = 0ull;
+  int rc = 0;
+  for (int round = 0; round < 3 && 0 == rc; round++) {
+    unsigned long long mine = (unsigned long long)(rank + 1) * value + (unsigned long long)round, all[C3D_MAX_RANKS];
+    rc = c3d_peer_allgather(&peer, &mine, sizeof(mine), all);
+    total = 0ull;
+    for (int r = 0; r < size && 0 == rc; r++) total += all[r] - (unsigned long long)round;
+  }
+  *sum = total;
+  munmap(peer.board, peer.board_bytes);
+  return rc;
+}
+
+int c3d_peer_init(c3d_peer *peer, int rank, int size, const void *id128, int device) {
+  memset(peer, 0, sizeof(*peer));
+  peer->rank = rank;
+  peer->size = size;
+  if (size < 2) return 0;
+  {
+    const char *env = getenv("CONTOUR3D_P2P");
+    if (NULL != env && '0' == env[0]) return 0;                 /* exchange through NCCL only */
+  }
+  if (size > C3D_MAX_RANKS) return 0;                           /* list entries name the source rank in 3 bits */
+  if (NULL == id128) return 0;
+  {
+    const int rc = board_attach(peer, id128);
+    if (2 == rc) return 1;
+    if (0 != rc) return 0;
+  }
   /* who shares a GPU with whom */
   struct Ident { char bus[48]; };
   Ident mine, all[C3D_MAX_RANKS];

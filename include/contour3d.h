@@ -11,6 +11,11 @@
  * Implemented in contour3d_b200/csrc/contour3d_execute.c (host C) on top of
  * the CUDA C-ABI of contour3d_b200.h.  There is no CPU fallback: without a
  * usable CUDA device the call logs "[CONTOUR3D ERROR] ..." and returns 1.
+ *
+ * The interface restated here is that of NaokiHori/Contour3D, distributed under
+ * the MIT License, Copyright (c) 2023 NaokiHori (the permission notice is
+ * reproduced in include/sdecomp.h, which restates the same author's SimpleDecomp
+ * interface under the same licence).
  */
 #if !defined(CONTOUR3D_H)
 #define CONTOUR3D_H

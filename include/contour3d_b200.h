@@ -223,6 +223,15 @@ void c3d_positions_free(c3d_positions_t *p);
 int c3d_camera_from_angles(double elevation_deg, double azimuth_deg, double roll_deg, double camera_distance, double screen_distance,
                            double screen_width, double screen_height, c3d_scene_t *scene);
 
+/* ---- diagnostics (host side, needs no device) ---- */
+
+/* Self test of the bootstrap the ranks of one node use to exchange the handles of each other's device memory (a POSIX
+   shared-memory board named after the 128-byte id of the run; it carries what the reference's MPI communicator carries
+   between ranks, contour/extend.c:10-147, output.c:82, before any device is involved).  Collective over `size` processes
+   that share id128: every rank contributes `value` and receives in *sum the sum over the ranks of (rank + 1) * value.
+   Returns 0, or non-zero when the board could not be set up (the library then exchanges through NCCL only). */
+int c3d_peer_selftest(int rank, int size, const void *id128, unsigned long long value, unsigned long long *sum);
+
 /* library / build information, e.g. "contour3d_b200 0.1 sm_100a" */
 const char *c3d_version(void);
 

@@ -83,3 +83,35 @@ def test_world_size_two_gloo(tmp_path):
     port = 29000 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()
+
+
+def _board_worker(rank, world, ident, out):
+    sys.path.insert(0, ROOT)
+    import ctypes as C
+
+    from contour3d_b200 import api
+
+    fn = api.lib().c3d_peer_selftest
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+    total = C.c_ulonglong(0)
+    rc = fn(rank, world, ident, 7, C.byref(total))
+    out.put((rank, rc, int(total.value)))
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_ranks_bootstrap_board_allgathers_between_processes(world):
+    """the shared-memory board over which the ranks of one node exchange the CUDA IPC handles of each other's device memory
+    (c3d_peer.cu): independent processes that share only the 128-byte id of the run meet on it, every one contributes a
+    value and all receive the same sum -- host logic of the N > 1 path, no device involved"""
+    ctx = mp.get_context("spawn")
+    ident = os.urandom(128)
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_board_worker, args=(r, world, ident, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(out.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    want = 7 * world * (world + 1) // 2
+    assert got == [(r, 0, want) for r in range(world)], got
