@@ -191,7 +191,7 @@ _compat = None
 
 EXPORTS = [
     "c3d_nccl_unique_id", "c3d_context_create", "c3d_context_destroy", "c3d_context_device", "c3d_context_stream",
-    "c3d_context_synchronize", "c3d_context_exchange_mode", "c3d_field_wrap", "c3d_peer_selftest", "c3d_positions_probe", "c3d_positions_free", "c3d_camera_from_angles", "c3d_frame_collectives_probe", "c3d_decomp_make", "c3d_decomp_local", "c3d_field_create", "c3d_field_destroy",
+    "c3d_context_synchronize", "c3d_context_exchange_mode", "c3d_field_wrap", "c3d_peer_selftest", "c3d_selftest_work_plan", "c3d_selftest_tile_map", "c3d_positions_probe", "c3d_positions_free", "c3d_camera_from_angles", "c3d_frame_collectives_probe", "c3d_decomp_make", "c3d_decomp_local", "c3d_field_create", "c3d_field_destroy",
     "c3d_field_upload", "c3d_field_geometry", "c3d_field_interior", "c3d_field_mark_dirty", "c3d_field_exchange",
     "c3d_field_download_ext", "c3d_field_synthesize", "c3d_frame_render", "c3d_frame_timings", "c3d_frame_canvas",
     "c3d_case_codes", "c3d_sweep", "c3d_tessellate", "c3d_version", "contour3d_execute",

@@ -491,36 +491,38 @@ int c3d_k_merge_lists(const MergeSources *src, int nranks, int me, unsigned long
  * Every rank runs this same plan on the same counts and writes down only what IT has to pull.
  * counters[0] <- all items of this rank, counters[2] <- those of its own array (they come first).
  */
-__global__ void k_work_plan(const WorkExchange ex, const int n, const int me, const float remote_cost, PullPlan *__restrict__ plan,
-                            unsigned int *__restrict__ counters, const unsigned int capacity, unsigned long long *__restrict__ overflowed) {
-  /* the counts live on the other ranks: one thread each fetches them, then one thread plans */
-  __shared__ unsigned int s_C[C3D_MAX_RANKS][C3D_MAX_RANKS];
-  if ((int)threadIdx.x < n * n) s_C[threadIdx.x / n][threadIdx.x % n] = ex.nseg[threadIdx.x / n][threadIdx.x % n];
-  __syncthreads();
-  if (0 != threadIdx.x || 0 != blockIdx.x) return;
-  unsigned int C[C3D_MAX_RANKS][C3D_MAX_RANKS], T[C3D_MAX_RANKS], keep[C3D_MAX_RANKS], room[C3D_MAX_RANKS];
+/* the plan itself: plain arithmetic on the n x n counts, the same on the host (c3d_selftest_work_plan) and on the device.
+   *nlocal = items of this rank's own array (they come first), *total = all items it pulls */
+__host__ __device__ static void work_plan_compute(const unsigned int (*C)[C3D_MAX_RANKS], const int n, const int me, const double remote_cost,
+                                                  PullPlan *plan, unsigned int *nlocal, unsigned int *total) {
+  unsigned int T[C3D_MAX_RANKS], keep[C3D_MAX_RANKS], room[C3D_MAX_RANKS];
   unsigned int most = 0u;
-  for (int o = 0; o < n; o++) T[o] = 0u;
-  for (int d = 0; d < n; d++) {
-    for (int o = 0; o < n; o++) { C[d][o] = s_C[d][o]; T[o] += C[d][o]; }
+  for (int o = 0; o < n; o++) {
+    T[o] = 0u;
+    for (int d = 0; d < n; d++) T[o] += C[d][o];
+    most = T[o] > most ? T[o] : most;
   }
-  for (int o = 0; o < n; o++) most = T[o] > most ? T[o] : most;
-  float tau = (float)most;
-  if (remote_cost >= 1.f) {
-    float lo = 0.f, hi = (float)most;
-    for (int it = 0; it < 40; it++) {
-      const float mid = 0.5f * (lo + hi);
-      float give = 0.f, takes = 0.f;
+  const bool help = remote_cost >= 1.;
+  double tau = (double)most;                     /* counts are far below 2^53: exact in double */
+  if (help) {
+    double lo = 0., hi = (double)most;
+    for (int it = 0; it < 60; it++) {
+      const double mid = 0.5 * (lo + hi);
+      double give = 0., takes = 0.;
       for (int o = 0; o < n; o++) {
-        if ((float)T[o] > mid) give += (float)T[o] - mid; else takes += (mid - (float)T[o]) / remote_cost;
+        if ((double)T[o] > mid) give += (double)T[o] - mid; else takes += (mid - (double)T[o]) / remote_cost;
       }
       if (give > takes) lo = mid; else hi = mid;
     }
     tau = hi;
   }
+  auto room_of = [&](const int o) -> unsigned int {
+    return (help && (double)T[o] < tau) ? (unsigned int)((tau - (double)T[o]) / remote_cost) : 0u;
+  };
   for (int o = 0; o < n; o++) {
-    keep[o] = (float)T[o] > tau ? (unsigned int)tau : T[o];
-    room[o] = (remote_cost >= 1.f && (float)T[o] < tau) ? (unsigned int)((tau - (float)T[o]) / remote_cost) : 0u;
+    const unsigned int level = (unsigned int)tau;
+    keep[o] = T[o] > level ? level : T[o];
+    room[o] = room_of(o);
   }
   unsigned int nchunks = 0u, dest = 0u;
   /* a range [a, a + cnt) of owner o's list, as pieces of the ranks' segments */
@@ -556,9 +558,9 @@ __global__ void k_work_plan(const WorkExchange ex, const int n, const int me, co
   }
   take(me, 0u, keep[me]);
   if (left_over[me] > 0u) take(me, keep[me] + handed[me], left_over[me]);
-  const unsigned int nlocal = dest;
+  *nlocal = dest;
   /* the same dealing once more, now writing down the pieces that come to this rank */
-  for (int o = 0; o < n; o++) room[o] = (remote_cost >= 1.f && (float)T[o] < tau) ? (unsigned int)((tau - (float)T[o]) / remote_cost) : 0u;
+  for (int o = 0; o < n; o++) room[o] = room_of(o);
   {
     int r = 0;
     for (int o = 0; o < n; o++) {
@@ -573,10 +575,43 @@ __global__ void k_work_plan(const WorkExchange ex, const int n, const int me, co
     }
   }
   plan->nchunks = nchunks;
-  plan->nwork = dest < capacity ? dest : capacity;
+  *total = dest;
+}
+
+__global__ void k_work_plan(const WorkExchange ex, const int n, const int me, const float remote_cost, PullPlan *__restrict__ plan,
+                            unsigned int *__restrict__ counters, const unsigned int capacity, unsigned long long *__restrict__ overflowed) {
+  /* the counts live on the other ranks: one thread each fetches them, then one thread plans */
+  __shared__ unsigned int s_C[C3D_MAX_RANKS][C3D_MAX_RANKS];
+  if ((int)threadIdx.x < n * n) s_C[threadIdx.x / n][threadIdx.x % n] = ex.nseg[threadIdx.x / n][threadIdx.x % n];
+  __syncthreads();
+  if (0 != threadIdx.x || 0 != blockIdx.x) return;
+  unsigned int nlocal = 0u, total = 0u;
+  work_plan_compute(s_C, n, me, (double)remote_cost, plan, &nlocal, &total);
+  plan->nwork = total < capacity ? total : capacity;
   counters[0] = plan->nwork;
   counters[2] = nlocal < plan->nwork ? nlocal : plan->nwork;
-  if (dest > capacity) atomicAdd(overflowed, 1ull);
+  if (total > capacity) atomicAdd(overflowed, 1ull);
+}
+
+/* host-side self test hook: the plan of rank `me` for the counts matrix counts[d * n + o]; chunks as 5 words each
+   (owner, d, first, count, dest).  Needs no device. */
+extern "C" int c3d_selftest_work_plan(const unsigned int *counts, int n, int me, double remote_cost, unsigned int *chunks, unsigned int *nchunks,
+                                      unsigned int *nlocal, unsigned int *total) {
+  if (NULL == counts || NULL == chunks || NULL == nchunks || NULL == nlocal || NULL == total || n < 1 || n > C3D_MAX_RANKS || me < 0 || me >= n) return 1;
+  unsigned int C[C3D_MAX_RANKS][C3D_MAX_RANKS];
+  memset(C, 0, sizeof(C));
+  for (int d = 0; d < n; d++) {
+    for (int o = 0; o < n; o++) C[d][o] = counts[d * n + o];
+  }
+  PullPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  work_plan_compute(C, n, me, remote_cost, &plan, nlocal, total);
+  *nchunks = plan.nchunks;
+  for (unsigned int c = 0; c < plan.nchunks; c++) {
+    chunks[5 * c + 0] = plan.chunk[c].owner; chunks[5 * c + 1] = plan.chunk[c].d; chunks[5 * c + 2] = plan.chunk[c].first;
+    chunks[5 * c + 3] = plan.chunk[c].count; chunks[5 * c + 4] = plan.chunk[c].dest;
+  }
+  return 0;
 }
 
 __global__ void __launch_bounds__(256) k_work_copy(const WorkExchange ex, const PullPlan *__restrict__ plan, WorkItem *__restrict__ work,

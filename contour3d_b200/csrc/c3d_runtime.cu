@@ -1099,6 +1099,15 @@ static void tile_map_build(const double *share, const int n, const int tiles_x, 
   }
 }
 
+/* host-side self test hook (needs no device): the table tile_map_build() derives from `share` */
+extern "C" int c3d_selftest_tile_map(const double *share, int n, int tiles_x, int tiles_y, unsigned char *out) {
+  if (NULL == share || NULL == out || n < 1 || n > C3D_MAX_RANKS || tiles_x < 1 || tiles_y < 1) return 1;
+  std::vector<unsigned char> map;
+  tile_map_build(share, n, tiles_x, tiles_y, map);
+  memcpy(out, map.data(), map.size());
+  return 0;
+}
+
 /* New shares from what every rank's frame spent drawing (d_r, proportional to its share of the tiles) and shading (h_r, given by
    whose cubes win the image -- not by the tiles): the level L with  D s_r + h_r = L,  sum s_r = 1,  D = sum d_r.  Damped, clamped. */
 static bool tile_shares_update(c3d_context *ctx, const unsigned long long *gathered) {

@@ -232,6 +232,16 @@ int c3d_camera_from_angles(double elevation_deg, double azimuth_deg, double roll
    Returns 0, or non-zero when the board could not be set up (the library then exchanges through NCCL only). */
 int c3d_peer_selftest(int rank, int size, const void *id128, unsigned long long value, unsigned long long *sum);
 
+/* The two plans the ranks of a screen-partitioned frame each compute for themselves from shared numbers, run on the host
+   (what the reference leaves to MPI_Reduce, output.c:82, is here a division of labour that every rank must derive identically):
+   - which pixels rank `me` shades, from counts[d * n + o] = pixels of rank d's tiles won by cubes of rank o's array;
+     chunks = nchunks x 5 words (owner, d, first, count, dest), room for 80; nlocal = pixels of its own array (they come
+     first), total = all it takes.  remote_cost < 1: no helping.
+   - which rank draws which screen tile (ty * tiles_x + tx), from the ranks' shares of the screen. */
+int c3d_selftest_work_plan(const unsigned int *counts, int n, int me, double remote_cost, unsigned int *chunks, unsigned int *nchunks,
+                           unsigned int *nlocal, unsigned int *total);
+int c3d_selftest_tile_map(const double *share, int n, int tiles_x, int tiles_y, unsigned char *out);
+
 /* library / build information, e.g. "contour3d_b200 0.1 sm_100a" */
 const char *c3d_version(void);
 

@@ -280,3 +280,90 @@ def test_converter_probe_catches_a_function_that_is_the_identity_almost_everywhe
     for i, j, k in rng.integers(0, n, size=(400, 3)):
         want = conv(g[0][i], g[1][j], g[2][k])
         assert all(lookup(c, i, j, k) == want[c] for c in range(3)), (i, j, k)
+
+
+def _work_plans(counts, remote_cost):
+    """c3d_selftest_work_plan for every rank: [(chunks as rows (owner, d, first, count, dest), nlocal, total)]"""
+    fn = api.lib().c3d_selftest_work_plan
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    n = counts.shape[0]
+    flat = np.ascontiguousarray(counts, dtype=np.uint32)
+    out = []
+    for me in range(n):
+        chunks = np.zeros((8 * 10, 5), dtype=np.uint32)
+        nch, nlocal, total = C.c_uint(0), C.c_uint(0), C.c_uint(0)
+        assert 0 == fn(flat.ctypes.data, n, me, float(remote_cost), chunks.ctypes.data, C.byref(nch), C.byref(nlocal), C.byref(total))
+        out.append((chunks[:nch.value].astype(np.int64), int(nlocal.value), int(total.value)))
+    return out
+
+
+@pytest.mark.parametrize("n,remote_cost,seed", [(2, 8.0, 0), (4, 8.0, 1), (8, 8.0, 2), (8, 3.0, 3), (8, 1.0, 4), (8, 0.0, 5), (3, 5.0, 6), (8, 8.0, 7)])
+def test_shading_work_plan_hands_out_every_pixel_exactly_once(n, remote_cost, seed):
+    """k_work_plan (c3d_peer.cu), run on the host: the ranks of a screen-partitioned frame decide, each for itself and from
+    the same n x n counts, which pixels they shade.  Whatever the counts: every queued pixel is taken by exactly one rank,
+    a rank's pieces tile its work list without gaps, its own array's pixels come first, nobody ends above the busiest owner,
+    and with helping switched off everybody takes exactly its own."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, 50000, size=(n, n))           # counts[d][o]: pixels of rank d's tiles won by cubes of rank o's array
+    counts[:, n - 1] *= 6 if seed != 7 else 0               # the slab facing the camera wins most of the image (or nothing at all)
+    if seed == 7:
+        counts[rng.integers(0, n)] = 0
+    plans = _work_plans(counts, remote_cost)
+    taken = {(d, o): np.zeros(counts[d, o], dtype=np.int32) for d in range(n) for o in range(n)}
+    owner_total = counts.sum(axis=0)
+    for me, (chunks, nlocal, total) in enumerate(plans):
+        at = 0
+        for owner, d, first, count, dest in chunks:
+            assert dest == at and count > 0, "pieces must tile the work list in order"
+            assert first + count <= counts[d, owner]
+            taken[(d, owner)][first:first + count] += 1
+            if at < nlocal:
+                assert owner == me, "a rank's own pixels come first"
+            else:
+                assert owner != me
+            at += count
+        assert at == total
+        assert total <= max(int(owner_total.max()), 1)
+        if remote_cost < 1.0:
+            assert total == nlocal == owner_total[me]
+    for key, hits in taken.items():
+        assert (hits == 1).all(), f"pixels of segment {key} taken {np.unique(hits)} times"
+    if remote_cost >= 1.0 and owner_total.max() > 0:
+        # the estimated time is levelled: an owner above the level keeps the level, a helper's foreign pixels count remote_cost times
+        est = [nl + remote_cost * (tot - nl) for _, nl, tot in plans]
+        assert max(est) <= owner_total.max() + 1
+        busiest = int(np.argmax(owner_total))
+        others = [e for r, e in enumerate(est) if r != busiest]
+        if owner_total[busiest] > 2 * np.mean(owner_total) and n > 1:
+            assert plans[busiest][2] < owner_total[busiest], "the busiest owner hands part of its pixels over"
+            assert max(others) <= est[busiest] + remote_cost + 1
+
+
+@pytest.mark.parametrize("n,tiles,shares", [
+    (8, (60, 34), [0.125] * 8),
+    (8, (120, 68), [0.135, 0.134, 0.135, 0.135, 0.131, 0.130, 0.127, 0.073]),     # the shares measured at 8 GPUs (DESIGN.md section 6)
+    (2, (5, 3), [0.7, 0.3]),
+    (3, (7, 11), [0.2, 0.5, 0.3]),
+])
+def test_tile_table_follows_the_shares_and_scatters_every_ranks_tiles(n, tiles, shares):
+    """tile_map_build (c3d_runtime.cu): the screen tiles of a partitioned frame are dealt out in proportion to the ranks'
+    shares -- every tile to exactly one rank, counts within one tile of share x tiles, and no rank's tiles bunched together
+    (every band of rows holds about its share of them)"""
+    fn = api.lib().c3d_selftest_tile_map
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    tx, ty = tiles
+    share = np.asarray(shares, dtype=np.float64)
+    share = share / share.sum()
+    out = np.full(tx * ty, 255, dtype=np.uint8)
+    assert 0 == fn(share.ctypes.data, n, tx, ty, out.ctypes.data)
+    assert out.max() < n
+    got = np.bincount(out, minlength=n)
+    assert np.abs(got - share * tx * ty).max() <= 1.0 + 1e-9, (got, share * tx * ty)
+    if tx * ty >= 1000:
+        grid = out.reshape(ty, tx)
+        bands = np.array_split(np.arange(ty), 4)
+        for r in range(n):
+            per_band = np.array([(grid[b] == r).sum() / (len(b) * tx) for b in bands])
+            assert np.abs(per_band - share[r]).max() < 0.25 * share[r] + 0.01, (r, per_band, share[r])
