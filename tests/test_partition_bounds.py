@@ -1,0 +1,120 @@
+"""CPU: the geometric claim behind screen-partitioned frames.
+
+A rank draws a cube only if `cube_owners` (contour3d_b200/csrc/c3d_sweep.cu) says one of its screen tiles can be
+touched.  That decision is taken in fp32 from the projected hull of the cube's eight corners, widened by the
+reference's +-1 pixel search box and a quarter pixel for the arithmetic.  If it were ever too tight, a triangle would
+silently lose pixels at a tile border.  Here the same arithmetic is restated in numpy float32 and checked against the
+oracle's triangles (oracle.tessellate: the reference's own vertices): the pixel box the REFERENCE searches for every
+triangle (render.c:62-89, project.c:28-65, fp64) must lie inside the box `cube_owners` derives for its cube, and a cube the
+fp32 projection cannot bound must be sent to every rank.
+"""
+import numpy as np
+import pytest
+
+from contour3d_b200 import scenes
+from oracle import oracle
+
+F = np.float32
+
+
+def _camera(scene):
+    cam, center = np.array(scene["camera"]), np.array(scene["center"])
+    lx, ly = np.array(scene["local_x"]), np.array(scene["local_y"])
+    n = np.cross(lx, ly)
+    n = n * (1.0 / np.sqrt(n @ n))
+    return cam, center, lx, ly, n
+
+
+def reference_search_boxes(scene, tri_vertices):
+    """per triangle: (ok, imin, imax, jmin, jmax) exactly as render.c:62-89 computes them (fp64)"""
+    cam, center, lx, ly, n = _camera(scene)
+    W, H = float(scene["width"]), float(scene["height"])
+    ray = tri_vertices - cam                                   # (T, 3, 3)
+    nr = ray @ n
+    ok = ~((nr > -1e-8) & (nr < 1e-8))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = (n @ center - n @ cam) / nr
+    ok &= (t > 0.0) & (t < 1.0)
+    delta = cam + t[..., None] * ray - center
+    sx = (delta @ lx) / (lx @ lx)
+    sy = (delta @ ly) / (ly @ ly)
+    good = ok.all(axis=1)
+    with np.errstate(invalid="ignore"):
+        xmin = np.trunc((0.5 + sx.min(axis=1)) * W - 1.0)
+        xmax = np.trunc((0.5 + sx.max(axis=1)) * W + 1.0)
+        ymin = np.trunc((0.5 + sy.min(axis=1)) * H - 1.0)
+        ymax = np.trunc((0.5 + sy.max(axis=1)) * H + 1.0)
+    clampx = lambda v: np.clip(np.nan_to_num(v), 0, W - 1)
+    clampy = lambda v: np.clip(np.nan_to_num(v), 0, H - 1)
+    return good, clampx(xmin), clampx(xmax), clampy(ymin), clampy(ymax)
+
+
+def cube_owner_boxes(scene, grids, ci, cj, ck):
+    """the pixel box of cube_owners() in float32, per cube: (bounded, imin, imax, jmin, jmax); not bounded = every rank"""
+    cam, center, lx, ly, n = _camera(scene)
+    W, H = F(scene["width"]), F(scene["height"])
+    lxlx, lyly = lx @ lx, ly @ ly
+    # make_cull(), c3d_runtime.cu: constants rounded to fp32 once
+    qcam, qn = cam.astype(F), n.astype(F)
+    lxs, lys = (lx / lxlx).astype(F), (ly / lyly).astype(F)
+    ax, ay = F(((cam - center) @ lx) / lxlx), F(((cam - center) @ ly) / lyly)
+    c = F(n @ center - n @ cam)
+    gf = [g.astype(F) for g in grids]
+    xlo = np.full(len(ci), F(3e38)); xhi = np.full(len(ci), F(-3e38)); ylo = xlo.copy(); yhi = xhi.copy()
+    tlo = xlo.copy(); thi = xhi.copy()
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        for corner in range(8):
+            a, b, d = corner & 1, (corner >> 1) & 1, corner >> 2
+            rx, ry, rz = gf[0][ci + a] - qcam[0], gf[1][cj + b] - qcam[1], gf[2][ck + d] - qcam[2]
+            nr = (qn[0] * rx + qn[1] * ry) + qn[2] * rz
+            t = (c / nr).astype(F)
+            sx = (ax + t * ((lxs[0] * rx + lxs[1] * ry) + lxs[2] * rz)).astype(F)
+            sy = (ay + t * ((lys[0] * rx + lys[1] * ry) + lys[2] * rz)).astype(F)
+            xlo, xhi = np.fmin(xlo, sx), np.fmax(xhi, sx)
+            ylo, yhi = np.fmin(ylo, sy), np.fmax(yhi, sy)
+            tlo, thi = np.fmin(tlo, t), np.fmax(thi, t)
+        bounded = (tlo > F(1e-4)) & (thi < F(0.9999)) & (xlo > F(-1e6)) & (xhi < F(1e6)) & (ylo > F(-1e6)) & (yhi < F(1e6))
+        imin = np.clip(np.floor((F(0.5) + xlo) * W - F(1.25)), 0, W - 1)
+        imax = np.clip(np.floor((F(0.5) + xhi) * W + F(1.25)), 0, W - 1)
+        jmin = np.clip(np.floor((F(0.5) + ylo) * H - F(1.25)), 0, H - 1)
+        jmax = np.clip(np.floor((F(0.5) + yhi) * H + F(1.25)), 0, H - 1)
+    return bounded, imin, imax, jmin, jmax
+
+
+CASES = {
+    "demo camera": dict(),
+    "camera inside the volume": dict(camera=(0.2, -0.45, 0.3), center=(0.1, -0.225, 0.15)),
+    "large screen": dict(width=3840, height=2160),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("field", ["noise", "sines"])
+def test_every_triangles_search_box_lies_inside_its_cubes_owner_box(name, field):
+    over = dict(CASES[name])
+    scene = scenes.scene(over.pop("width", 400), over.pop("height", 225))
+    scene.update(over)
+    if field == "noise":
+        n = 28
+        f = scenes.noise(n, seed=11).astype(np.float64)
+        grids = scenes.uniform_grids(n, n, n)
+        thr = 0.05
+    else:
+        n = 24
+        f, grids = scenes.sines(n, seed=9)
+        thr = 0.0
+    tris, _ = oracle.tessellate(f, grids, thr)
+    assert len(tris) > 1000
+    cube = tris["cube"].astype(np.int64)
+    ci, cj, ck = cube % (n - 1), (cube // (n - 1)) % (n - 1), cube // ((n - 1) * (n - 1))
+    good, rx0, rx1, ry0, ry1 = reference_search_boxes(scene, tris["v"])
+    bounded, ox0, ox1, oy0, oy1 = cube_owner_boxes(scene, grids, ci, cj, ck)
+    # a triangle the reference draws (all three vertices project) in a cube the owner test claims to bound: box inside box
+    check = good & bounded
+    assert check.sum() > 500, "the scene was meant to have plenty of ordinary triangles"
+    inside = (rx0 >= ox0) & (rx1 <= ox1) & (ry0 >= oy0) & (ry1 <= oy1)
+    assert inside[check].all(), f"{int((~inside & check).sum())} triangles would lose pixels at a tile border"
+    if name == "camera inside the volume":
+        # cubes at or behind the screen plane cannot be bounded by the fp32 projection: they must go to every rank, and
+        # they are exactly where the reference still draws some triangles while dropping others (render.c:69-70)
+        assert (~bounded).any() and (good & ~bounded).any()
