@@ -16,6 +16,12 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """the single-rank parity tests first, the multi-rank ones (one process per rank, minutes) last: with -x a failure there
+    must not hide what the single-rank path has already shown"""
+    items.sort(key=lambda item: 1 if "test_gpu_multirank" in item.nodeid else 0)
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
     out = {k: z[k] for k in z.files}
