@@ -505,12 +505,14 @@ __host__ __device__ static void work_plan_compute(const unsigned int (*C)[C3D_MA
   const bool help = remote_cost >= 1.;
   double tau = (double)most;                     /* counts are far below 2^53: exact in double */
   if (help) {
+    /* one thread of one block runs this every frame: 36 halvings bring the level to a fraction of a pixel, the division is hoisted */
+    const double inv_cost = 1. / remote_cost;
     double lo = 0., hi = (double)most;
-    for (int it = 0; it < 60; it++) {
+    for (int it = 0; it < 36; it++) {
       const double mid = 0.5 * (lo + hi);
       double give = 0., takes = 0.;
       for (int o = 0; o < n; o++) {
-        if ((double)T[o] > mid) give += (double)T[o] - mid; else takes += (mid - (double)T[o]) / remote_cost;
+        if ((double)T[o] > mid) give += (double)T[o] - mid; else takes += (mid - (double)T[o]) * inv_cost;
       }
       if (give > takes) lo = mid; else hi = mid;
     }
