@@ -126,3 +126,20 @@ def test_random_frames_oracle_matches_reference(tmp_path, seed):
     cs = [dict(field=f, grids=grids, threshold=c["threshold"], color=c["color"]) for c in contours]
     rgb, _, _ = oracle.frame(scene, cs, lines, nthreads=1 + seed % 3)
     assert np.array_equal(read_ppm(out), rgb[::-1])
+
+
+@pytest.mark.parametrize("seed", range(2000, 2060))
+def test_random_frames_with_converters_oracle_matches_reference(tmp_path, seed):
+    """the same fuzz with a non-identity `converter` (cylindrical / stretched / twisted, by seed) on contours and lines"""
+    from fuzz_cases import random_case
+
+    scene, grids, f, contours, lines, ranks, dims = random_case(seed)
+    kind = 1 + seed % 3
+    scene["converter"] = kind
+    case, out = str(tmp_path / "c.bin"), str(tmp_path / "o.ppm")
+    casefile.write_case(case, scene, grids, [f], contours, lines)
+    reference.run_case(case, out, ranks=ranks, dims=dims, timeout=300)
+    cs = [dict(field=f, grids=grids, threshold=c["threshold"], color=c["color"], converter=kind) for c in contours]
+    ls = [dict(l, converter=kind) for l in lines]
+    rgb, _, _ = oracle.frame(scene, cs, ls, nthreads=1 + seed % 3)
+    assert np.array_equal(read_ppm(out), rgb[::-1])
