@@ -118,3 +118,29 @@ def test_every_triangles_search_box_lies_inside_its_cubes_owner_box(name, field)
         # cubes at or behind the screen plane cannot be bounded by the fp32 projection: they must go to every rank, and
         # they are exactly where the reference still draws some triangles while dropping others (render.c:69-70)
         assert (~bounded).any() and (good & ~bounded).any()
+
+
+@pytest.mark.parametrize("seed", range(1000, 1060))
+def test_owner_boxes_hold_for_random_cameras_grids_and_screens(seed):
+    """the same containment on the random frames of tests/fuzz_cases.py: non-uniform coordinates, ragged shapes, cameras
+    anywhere from inside the volume to far away, screens from 5 pixels up, non-square pixels.
+    (How much room the quarter pixel leaves: over 200 such seeds, 1.7 M triangles, the containment still holds with the
+    margin cut from 1.25 to 1.0 -- no allowance for the fp32 arithmetic at all -- and breaks for 899 triangles at 0.99.)"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fuzz_cases import random_case
+
+    scene, grids, f, contours, _, _, _ = random_case(seed)
+    nz, ny, nx = f.shape
+    for c in contours:
+        tris, _ = oracle.tessellate(f, grids, c["threshold"])
+        if 0 == len(tris):
+            continue
+        cube = tris["cube"].astype(np.int64)
+        ci, cj, ck = cube % (nx - 1), (cube // (nx - 1)) % (ny - 1), cube // ((nx - 1) * (ny - 1))
+        assert ck.max() < nz - 1
+        good, rx0, rx1, ry0, ry1 = reference_search_boxes(scene, tris["v"])
+        bounded, ox0, ox1, oy0, oy1 = cube_owner_boxes(scene, grids, ci, cj, ck)
+        check = good & bounded
+        inside = (rx0 >= ox0) & (rx1 <= ox1) & (ry0 >= oy0) & (ry1 <= oy1)
+        assert inside[check].all(), f"seed {seed}: {int((~inside & check).sum())} of {int(check.sum())} triangles would lose pixels at a tile border"
