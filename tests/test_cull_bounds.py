@@ -8,6 +8,8 @@ rendering with and without the shortcuts (tests/test_gpu_parity.py, tools/gpu_sh
 Here the bounds are restated in numpy float32 and checked against the reference's own fragments (a float64 restatement of
 render.c:48-163 on the oracle's triangles) for random cameras, coordinates and screens (tests/fuzz_cases.py): every
 fragment of a triangle lies inside the pixel range of its cube's test and of its own test, at or below their depth caps.
+The fp32 coverage pre-test of `raster_triangle` (a pixel is dropped before the exact fp64 inside test when an edge function
+is below minus its error bound) is restated too: it must keep every pixel the reference covers.
 
 Triangles the shortcuts leave alone by construction are skipped here as there: collapsed ones (a vertex within rounding
 of a cube corner: `patch_irregular` / the `fr` guard), vertices near the screen plane, bounds that are not finite.
@@ -58,7 +60,8 @@ class Camera:
 
 def reference_fragments(cm, tri_v):
     """render.c:48-163 in float64 for one triangle (3, 3): pixel columns, rows and depths of its fragments, or None when the
-    reference drops the triangle (a vertex fails project.c:28-65); also whether the clamped area was used"""
+    reference drops the triangle (a vertex fails project.c:28-65); also whether the clamped area was used, the projected
+    vertices and the inverse area"""
     q = np.zeros((3, 3))
     for m in range(3):
         ray = tri_v[m] - cm.cam
@@ -87,7 +90,28 @@ def reference_fragments(cm, tri_v):
     inside = ~((w0 < -1e-8) | (w1 < -1e-8) | (w2 < -1e-8))
     with np.errstate(divide="ignore", invalid="ignore"):
         dist = 1.0 / (w0 / q[0, 2] + w1 / q[1, 2] + w2 / q[2, 2])
-    return ii[inside], jj[inside], dist[inside], clamped
+    return ii[inside], jj[inside], dist[inside], clamped, q, area_inv
+
+
+def coverage_pretest_keeps(cm, q, area_inv, ii, jj):
+    """raster_triangle(), c3d_kernels.cu: before the exact fp64 inside test a pixel is dropped when one of the three edge
+    functions, evaluated in fp32, lies below -tol (tol = a bound of the fp32 evaluation error + the reference's own 1e-8
+    slack).  True per pixel = not dropped."""
+    sgn = -1.0 if area_inv < 0.0 else 1.0
+    slack = 1.0001e-8 / abs(area_inv)
+    px = ((ii + 0.5) / cm.W - 0.5).astype(F)          # k_pixel_tables: the fp64 pixel centre, rounded once
+    py = ((jj + 0.5) / cm.H - 0.5).astype(F)
+    keep = np.ones(len(ii), dtype=bool)
+    for m in range(3):
+        a, b = q[(m + 1) % 3], q[(m + 2) % 3]
+        ey, ex = b[1] - a[1], b[0] - a[0]
+        fax, fay, fex, fey = F(a[0]), F(a[1]), F(sgn * ex), F(sgn * ey)
+        tol = 4e-7 * ((0.5 + abs(a[0])) * abs(ey) + (0.5 + abs(a[1])) * abs(ex)) + slack
+        ntol = -(F(F(tol) * F(1.000001)) + F(1e-37))
+        r = ((py - fay) * fex).astype(F)
+        e = fma32((px - fax).astype(F), np.full(len(ii), fey, dtype=F), -r)
+        keep &= ~(e < ntol)
+    return keep
 
 
 def project32(cm, rx, ry, rz, fused):
@@ -217,7 +241,9 @@ def check_case(seed, flip=False, max_triangles=700):
             got = reference_fragments(cm, tris["v"][n])
             if got is None:
                 continue
-            ii, jj, dist, clamped = got
+            ii, jj, dist, clamped, q, area_inv = got
+            kept = coverage_pretest_keeps(cm, q, area_inv, ii, jj)
+            assert kept.all(), f"seed {seed}: triangle {n}: the fp32 coverage pre-test drops {int((~kept).sum())} of {len(ii)} covered pixels"
             stats["triangles"] += 1
             stats["fragments"] += len(ii)
             own = triangle_test(cm, grids, f, c["threshold"], ci[n], cj[n], ck[n], tris["edge"][n])
